@@ -1,0 +1,1272 @@
+// api.cu -- C ABI of genedex_b200 (include/genedex_b200.h): index handles, device image
+// construction from host parts, chunked H2D / kernel / D2H pipelines, locate CSR plumbing.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/genedex_b200.h"
+#include "device_build.h"
+#include "device_index.h"
+#include "host_build.h"
+#include "kernels.cuh"
+
+using namespace gdx;
+
+// ---- thread-local error / stats state ----------------------------------------------------------------
+namespace {
+
+thread_local std::string t_error;
+thread_local uint64_t t_error_query = 0;
+thread_local gdx_stats t_stats = {};
+
+gdx_status fail(gdx_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_error = buf;
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return fail(_e == cudaErrorMemoryAllocation ? GDX_ERR_OOM : GDX_ERR_CUDA,            \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,        \
+                        __LINE__);                                                               \
+    } while (0)
+
+#define GDX_TRY(expr)                  \
+    do {                               \
+        gdx_status _s = (expr);        \
+        if (_s != GDX_OK) return _s;   \
+    } while (0)
+
+uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        if (dev >= 0 && dev != prev) {
+            if (cudaSetDevice(dev) != cudaSuccess) return;
+        }
+        ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// grow-only device buffer
+struct DBuf {
+    void *p = nullptr;
+    uint64_t cap = 0;
+    cudaError_t reserve(uint64_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        uint64_t want = align_up(bytes + bytes / 8, 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, want = align_up(bytes, 256));
+            if (e != cudaSuccess) return e;
+        }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+constexpr int kSlots = 3;
+constexpr uint64_t kChunkBytes = 24ull << 20;  // query bytes per pipeline chunk
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DBuf bytes, offsets, out_a, out_b;
+    std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
+    size_t ev_used = 0;
+};
+
+struct Small {  // pinned + device words shared by one call
+    uint64_t *h = nullptr;  // pinned host, 16 words
+    uint64_t *d = nullptr;  // device, 16 words: [0..2] err per slot, [4] steps, [5] walk steps,
+                            //                   [6] big count, [7] big cursor, [8] total
+};
+
+struct Workspace {
+    Slot slot[kSlots];
+    Small small;
+    DBuf starts, ends, counts, hit_offsets, rows, big_list, hits, scan_tmp, symbols;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    bool init() {
+        for (auto &s : slot)
+            if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaMallocHost(&small.h, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
+        if (cudaMalloc(&small.d, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
+        if (cudaEventCreate(&ev_a) != cudaSuccess || cudaEventCreate(&ev_b) != cudaSuccess) return false;
+        return true;
+    }
+    void destroy() {
+        for (auto &s : slot) {
+            if (s.stream) cudaStreamDestroy(s.stream);
+            s.bytes.release();
+            s.offsets.release();
+            s.out_a.release();
+            s.out_b.release();
+            for (auto e : s.ev) cudaEventDestroy(e);
+        }
+        if (small.h) cudaFreeHost(small.h);
+        if (small.d) cudaFree(small.d);
+        for (DBuf *b : {&starts, &ends, &counts, &hit_offsets, &rows, &big_list, &hits, &scan_tmp, &symbols})
+            b->release();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+    }
+    cudaEvent_t next_event(Slot &s) {
+        if (s.ev_used == s.ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            s.ev.push_back(e);
+        }
+        return s.ev[s.ev_used++];
+    }
+};
+
+struct PinnedHits {
+    void *p = nullptr;
+    uint64_t cap = 0;
+    bool in_use = false;
+};
+
+}  // namespace
+
+struct gdx_index {
+    ImageHeader h;
+    void *image = nullptr;
+    bool own_image = false;
+    int device = 0;
+    DevIndex dev;
+    mutable std::mutex mu;
+    mutable std::vector<Workspace *> free_ws;
+    mutable std::vector<PinnedHits> pinned;
+};
+
+namespace {
+
+Workspace *acquire_ws(const gdx_index *idx) {
+    {
+        std::lock_guard<std::mutex> lk(idx->mu);
+        if (!idx->free_ws.empty()) {
+            Workspace *w = idx->free_ws.back();
+            idx->free_ws.pop_back();
+            return w;
+        }
+    }
+    Workspace *w = new Workspace();
+    if (!w->init()) {
+        w->destroy();
+        delete w;
+        return nullptr;
+    }
+    return w;
+}
+void release_ws(const gdx_index *idx, Workspace *w) {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    idx->free_ws.push_back(w);
+}
+struct WsLease {
+    const gdx_index *idx;
+    Workspace *w;
+    explicit WsLease(const gdx_index *i) : idx(i), w(acquire_ws(i)) {}
+    ~WsLease() {
+        if (w) release_ws(idx, w);
+    }
+};
+
+// ---- layout dispatch -----------------------------------------------------------------------------------
+template <class F>
+gdx_status dispatch_layout(const RankLayout &L, F &&f) {
+    if (L.kind == kLayoutK32) return f(K32{});
+    switch (L.planes) {
+    case 1: return f(KG<1>{});
+    case 2: return f(KG<2>{});
+    case 3: return f(KG<3>{});
+    case 4: return f(KG<4>{});
+    case 5: return f(KG<5>{});
+    case 6: return f(KG<6>{});
+    case 7: return f(KG<7>{});
+    case 8: return f(KG<8>{});
+    }
+    return fail(GDX_ERR_UNSUPPORTED, "unsupported number of bit planes %u", L.planes);
+}
+
+// ---- device image construction -------------------------------------------------------------------------
+struct ImageSources {
+    const gdx_alphabet *alphabet;
+    uint32_t storage, sampling_rate, lookup_depth;
+    uint64_t n;
+    const uint64_t *count;             // host, sigma + 1
+    const uint64_t *sentinels;         // host
+    uint64_t ntexts;
+    const uint64_t *border_rows;       // host, sorted ascending together with border_pos
+    const uint64_t *border_pos;        // host
+    uint64_t n_border;
+    const uint8_t *d_bwt;              // device, n bytes
+    // exactly one of the sample sources
+    const uint64_t *h_samples64 = nullptr;  // host
+    const void *d_samples = nullptr;        // device, element width given by d_samples_wide
+    bool d_samples_wide = false;
+};
+
+gdx_status validate_alphabet(const gdx_alphabet &a) {
+    if (a.num_dense_symbols < 2 || a.num_dense_symbols > 256)
+        return fail(GDX_ERR_BAD_ARG, "alphabet size must be in [2,256] incl. the sentinel (alphabet.rs:166-174)");
+    if (a.num_searchable_dense_symbols < 1 || a.num_searchable_dense_symbols > a.num_dense_symbols - 1)
+        return fail(GDX_ERR_BAD_ARG, "there must be at least one searchable symbol (alphabet.rs:186-189)");
+    for (int i = 0; i < 256; ++i)
+        if (a.io_to_dense[i] >= a.num_dense_symbols)
+            return fail(GDX_ERR_BAD_ARG, "io_to_dense[%d] = %u is not a dense symbol", i, a.io_to_dense[i]);
+    return GDX_OK;
+}
+
+gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
+    memset(&h, 0, sizeof h);
+    h.magic = kImageMagic;
+    h.version = GDX_ABI_VERSION;
+    h.n = src.n;
+    h.ntexts = src.ntexts;
+    h.n_border = src.n_border;
+    h.sigma = src.alphabet->num_dense_symbols;
+    h.ns = src.alphabet->num_searchable_dense_symbols;
+    h.storage = src.storage;
+    h.sampling_rate = src.sampling_rate;
+    h.lookup_depth = src.lookup_depth;
+    h.wide = src.n > 0xffffffffull ? 1 : 0;
+    h.layout = choose_layout(h.sigma);
+    memcpy(h.io_to_dense, src.alphabet->io_to_dense, 256);
+    if (src.lookup_depth > kMaxLookupDepth)
+        return fail(GDX_ERR_UNSUPPORTED, "lookup table depth %u > %u", src.lookup_depth, kMaxLookupDepth);
+    const uint64_t P = 1ull << h.layout.log2_pos;
+    h.n_records = div_up(src.n + 1, P);
+    h.n_superblocks = div_up(src.n + 1, 1ull << kSuperblockLog2);
+    h.n_samples = div_up(src.n, src.sampling_rate);
+    uint64_t entries = 0, pw = 1;
+    for (uint32_t d = 0; d <= kMaxLookupDepth; ++d) {
+        h.lut_level_off[d] = entries;
+        h.lut_pow[d] = pw;
+        if (d <= src.lookup_depth) {
+            entries += pw;
+            if (entries > (1ull << 36) || pw > (1ull << 36))
+                return fail(GDX_ERR_UNSUPPORTED, "lookup tables of depth %u are too large", src.lookup_depth);
+            pw *= h.ns;
+        }
+    }
+    const uint64_t esz = h.wide ? 8 : 4;
+    uint64_t off = 0;
+    auto place = [&](uint64_t bytes) {
+        uint64_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    h.off_records = place(h.n_records * h.layout.stride);
+    // pack kernels write totals for whole superblock CTAs
+    h.off_sbc = place(h.n_superblocks * h.layout.noff * 8);
+    h.off_samples = place(h.n_samples * esz);
+    h.off_lookup = place(entries * 2 * esz);
+    h.off_border_rows = place(h.n_border * 8);
+    h.off_border_pos = place(h.n_border * 8);
+    h.off_sentinels = place(h.ntexts * 8);
+    h.off_count = place((uint64_t)(h.sigma + 1) * 8);
+    h.image_bytes = off;
+    return GDX_OK;
+}
+
+gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
+    std::unique_ptr<gdx_index> idx(new gdx_index());
+    GDX_TRY(plan_header(src, idx->h));
+    ImageHeader &h = idx->h;
+    idx->device = device;
+    CUDA_TRY(cudaMalloc(&idx->image, h.image_bytes));
+    idx->own_image = true;
+    auto cleanup = [&](gdx_status st) {
+        cudaFree(idx->image);
+        idx->image = nullptr;
+        return st;
+    };
+#define IMG_TRY(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return cleanup(fail(GDX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,                     \
+                                cudaGetErrorString(_e), __FILE__, __LINE__));                     \
+    } while (0)
+    uint8_t *base = (uint8_t *)idx->image;
+    IMG_TRY(cudaMemset(base, 0, h.image_bytes));
+    IMG_TRY(cudaMemcpy(base + h.off_sentinels, src.sentinels, h.ntexts * 8, cudaMemcpyHostToDevice));
+    if (h.n_border) {
+        IMG_TRY(cudaMemcpy(base + h.off_border_rows, src.border_rows, h.n_border * 8, cudaMemcpyHostToDevice));
+        IMG_TRY(cudaMemcpy(base + h.off_border_pos, src.border_pos, h.n_border * 8, cudaMemcpyHostToDevice));
+    }
+    IMG_TRY(cudaMemcpy(base + h.off_count, src.count, (uint64_t)(h.sigma + 1) * 8, cudaMemcpyHostToDevice));
+
+    // rank records + superblock table
+    uint64_t *sbc = (uint64_t *)(base + h.off_sbc);
+    if (h.layout.kind == kLayoutK32) {
+        k_pack_k32<<<(unsigned)h.n_superblocks, 1024>>>(src.d_bwt, h.n, h.layout.noff, base + h.off_records,
+                                                        h.n_records, sbc);
+    } else {
+        gdx_status st = dispatch_layout(h.layout, [&](auto L) -> gdx_status {
+            using LT = decltype(L);
+            if constexpr (!std::is_same<LT, K32>::value) {
+                constexpr int B = sizeof(typename LT::Planes) / 16;
+                k_pack_kg<B><<<(unsigned)h.n_superblocks, 512>>>(src.d_bwt, h.n, h.sigma, h.layout.stride,
+                                                                 base + h.off_records, h.n_records, sbc);
+            }
+            return GDX_OK;
+        });
+        if (st != GDX_OK) return cleanup(st);
+    }
+    IMG_TRY(cudaGetLastError());
+    k_sb_scan<<<div_up(h.layout.noff, 64), 64>>>(sbc, h.n_superblocks, h.layout.noff,
+                                                 (const uint64_t *)(base + h.off_count));
+    IMG_TRY(cudaGetLastError());
+
+    // SA samples
+    if (h.n_samples) {
+        void *dst = base + h.off_samples;
+        if (src.h_samples64) {
+            if (h.wide) {
+                IMG_TRY(cudaMemcpy(dst, src.h_samples64, h.n_samples * 8, cudaMemcpyHostToDevice));
+            } else {
+                std::vector<uint32_t> narrow(h.n_samples);
+                for (uint64_t i = 0; i < h.n_samples; ++i) narrow[i] = (uint32_t)src.h_samples64[i];
+                IMG_TRY(cudaMemcpy(dst, narrow.data(), h.n_samples * 4, cudaMemcpyHostToDevice));
+            }
+        } else if (src.d_samples) {
+            const unsigned g = (unsigned)div_up(h.n_samples, 256);
+            if (src.d_samples_wide == (h.wide != 0))
+                IMG_TRY(cudaMemcpy(dst, src.d_samples, h.n_samples * (h.wide ? 8 : 4), cudaMemcpyDeviceToDevice));
+            else if (h.wide)
+                k_widen_u32<<<g, 256>>>((const uint32_t *)src.d_samples, h.n_samples, (uint64_t *)dst);
+            else
+                k_narrow_u64<<<g, 256>>>((const uint64_t *)src.d_samples, h.n_samples, (uint32_t *)dst);
+            IMG_TRY(cudaGetLastError());
+        }
+    }
+
+    idx->dev = make_dev_index(h, idx->image);
+
+    // lookup tables: level 0 = [(0, n)] (lookup_table.rs:205-209), level d from level d-1
+    {
+        void *lut = base + h.off_lookup;
+        if (h.wide) {
+            uint64_t e0[2] = {0, h.n};
+            IMG_TRY(cudaMemcpy(lut, e0, sizeof e0, cudaMemcpyHostToDevice));
+        } else {
+            uint32_t e0[2] = {0, (uint32_t)h.n};
+            IMG_TRY(cudaMemcpy(lut, e0, sizeof e0, cudaMemcpyHostToDevice));
+        }
+        for (uint32_t d = 1; d <= h.lookup_depth; ++d) {
+            gdx_status st = dispatch_layout(h.layout, [&](auto L) -> gdx_status {
+                using LT = decltype(L);
+                k_lut_fill<LT><<<(unsigned)div_up(h.lut_pow[d], 256), 256>>>(idx->dev, lut, d);
+                return GDX_OK;
+            });
+            if (st != GDX_OK) return cleanup(st);
+            IMG_TRY(cudaGetLastError());
+        }
+    }
+    IMG_TRY(cudaDeviceSynchronize());
+#undef IMG_TRY
+    *out = idx.release();
+    return GDX_OK;
+}
+
+gdx_status check_config(const gdx_config &c) {
+    if (c.suffix_array_sampling_rate == 0)
+        return fail(GDX_ERR_BAD_ARG, "suffix array sampling rate must be > 0 (config.rs:28)");
+    if (c.storage > GDX_I64) return fail(GDX_ERR_BAD_ARG, "unknown index storage %u", c.storage);
+    return GDX_OK;
+}
+
+gdx_status resolve_device(int32_t requested, int *device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(GDX_ERR_CUDA, "no CUDA device available: %s (genedex_b200 has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (requested < 0) {
+        CUDA_TRY(cudaGetDevice(device));
+    } else {
+        if (requested >= count) return fail(GDX_ERR_BAD_ARG, "device %d out of range (%d devices)", requested, count);
+        *device = requested;
+    }
+    return GDX_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// misc
+// ================================================================================================
+extern "C" uint32_t gdx_abi_version(void) { return GDX_ABI_VERSION; }
+extern "C" const char *gdx_last_error_message(void) { return t_error.c_str(); }
+extern "C" uint64_t gdx_last_error_query(void) { return t_error_query; }
+extern "C" int32_t gdx_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) return 0;
+    return c;
+}
+extern "C" gdx_status gdx_get_stats(gdx_stats *out) {
+    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+    *out = t_stats;
+    return GDX_OK;
+}
+extern "C" gdx_status gdx_host_alloc(uint64_t bytes, void **out) {
+    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+    CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
+    return GDX_OK;
+}
+extern "C" void gdx_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+// ================================================================================================
+// construction
+// ================================================================================================
+extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text_offsets, uint64_t num_texts,
+                                      const gdx_alphabet *alphabet, const gdx_config *config, gdx_index **out) {
+    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!text_offsets || !alphabet || !config) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    if (num_texts == 0) return fail(GDX_ERR_BAD_ARG, "there should be at least one text (construction/mod.rs:300)");
+    GDX_TRY(validate_alphabet(*alphabet));
+    GDX_TRY(check_config(*config));
+    int device;
+    GDX_TRY(resolve_device(config->device, &device));
+    DeviceGuard guard(device);
+
+    ConcatText ct;
+    uint64_t bad = 0;
+    gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
+    if (st != GDX_OK) {
+        t_error_query = bad;
+        return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
+                    (unsigned long long)bad);
+    }
+    const uint64_t n = ct.text.size();
+    if (n > storage_max(config->storage))
+        return fail(GDX_ERR_TEXT_TOO_LONG, "text length %llu exceeds the index storage type (construction/mod.rs:34)",
+                    (unsigned long long)n);
+
+    ImageSources src;
+    src.alphabet = alphabet;
+    src.storage = config->storage;
+    src.sampling_rate = config->suffix_array_sampling_rate;
+    src.lookup_depth = config->lookup_table_depth;
+    src.n = n;
+    src.count = ct.count.data();
+    src.sentinels = ct.sentinels.data();
+    src.ntexts = num_texts;
+
+    if (config->construction == GDX_CONSTRUCT_DEVICE) {
+        DeviceBuildResult r;
+        const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
+        st = device_build_from_text(ct.text.data(), nullptr, n, alphabet->num_dense_symbols,
+                                    config->suffix_array_sampling_rate, r, t_error, false, verify);
+        if (st != GDX_OK) return st;
+        if (verify && r.verify_violations) {
+            r.release();
+            return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)",
+                        (unsigned long long)r.verify_violations);
+        }
+        src.border_rows = r.border_rows.data();
+        src.border_pos = r.border_pos.data();
+        src.n_border = r.border_rows.size();
+        src.d_bwt = r.d_bwt;
+        src.d_samples = r.d_samples;
+        src.d_samples_wide = false;
+        st = build_image(src, device, out);
+        r.release();
+        return st;
+    }
+
+    std::vector<int64_t> sa;
+    suffix_array_sais(ct.text.data(), n, alphabet->num_dense_symbols, sa);
+    HostParts hp;
+    parts_from_suffix_array(ct.text.data(), n, sa.data(), config->suffix_array_sampling_rate, hp);
+    std::vector<int64_t>().swap(sa);
+    uint8_t *d_bwt = nullptr;
+    CUDA_TRY(cudaMalloc(&d_bwt, n ? n : 1));
+    cudaError_t e = cudaMemcpy(d_bwt, hp.bwt.data(), n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_bwt);
+        return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
+    }
+    src.border_rows = hp.border_rows.data();
+    src.border_pos = hp.border_pos.data();
+    src.n_border = hp.border_rows.size();
+    src.d_bwt = d_bwt;
+    src.h_samples64 = hp.samples.data();
+    st = build_image(src, device, out);
+    cudaFree(d_bwt);
+    return st;
+}
+
+static gdx_status sources_from_parts(const gdx_parts *parts, ImageSources &src,
+                                     std::vector<uint64_t> &rows, std::vector<uint64_t> &pos) {
+    if (!parts) return fail(GDX_ERR_BAD_ARG, "parts is NULL");
+    GDX_TRY(validate_alphabet(parts->alphabet));
+    if (parts->sampling_rate == 0) return fail(GDX_ERR_BAD_ARG, "sampling rate must be > 0");
+    if (!parts->count || !parts->sentinel_indices || parts->num_texts == 0)
+        return fail(GDX_ERR_BAD_ARG, "count / sentinel_indices missing");
+    if (parts->text_len > storage_max(parts->storage)) return fail(GDX_ERR_TEXT_TOO_LONG, "text too long for storage");
+    // sort the border map by row (it is a HashMap in the reference)
+    std::vector<std::pair<uint64_t, uint64_t>> b(parts->num_text_borders);
+    for (uint64_t i = 0; i < parts->num_text_borders; ++i)
+        b[i] = {parts->text_border_rows[i], parts->text_border_positions[i]};
+    std::sort(b.begin(), b.end());
+    rows.resize(b.size());
+    pos.resize(b.size());
+    for (size_t i = 0; i < b.size(); ++i) {
+        rows[i] = b[i].first;
+        pos[i] = b[i].second;
+    }
+    src.alphabet = &parts->alphabet;
+    src.storage = parts->storage;
+    src.sampling_rate = parts->sampling_rate;
+    src.lookup_depth = parts->lookup_table_depth;
+    src.n = parts->text_len;
+    src.count = parts->count;
+    src.sentinels = parts->sentinel_indices;
+    src.ntexts = parts->num_texts;
+    src.border_rows = rows.data();
+    src.border_pos = pos.data();
+    src.n_border = rows.size();
+    src.h_samples64 = parts->sampled_suffix_array;
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_create_from_bwt(const uint8_t *bwt, const gdx_parts *parts, int32_t device_req,
+                                                gdx_index **out) {
+    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    if (!bwt) return fail(GDX_ERR_BAD_ARG, "bwt is NULL");
+    ImageSources src;
+    std::vector<uint64_t> rows, pos;
+    GDX_TRY(sources_from_parts(parts, src, rows, pos));
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    DeviceGuard guard(device);
+    uint8_t *d_bwt = nullptr;
+    CUDA_TRY(cudaMalloc(&d_bwt, src.n ? src.n : 1));
+    cudaError_t e = cudaMemcpy(d_bwt, bwt, src.n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d_bwt);
+        return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
+    }
+    src.d_bwt = d_bwt;
+    gdx_status st = build_image(src, device, out);
+    cudaFree(d_bwt);
+    return st;
+}
+
+extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_t device_req, gdx_index **out) {
+    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+    *out = nullptr;
+    ImageSources src;
+    std::vector<uint64_t> rows, pos;
+    GDX_TRY(sources_from_parts(parts, src, rows, pos));
+    if (!parts->interleaved_blocks) return fail(GDX_ERR_BAD_ARG, "interleaved_blocks is NULL");
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    DeviceGuard guard(device);
+    // reference planes -> dense BWT on the device (condensed.rs:343-362), then the common path
+    const uint32_t nplanes = choose_layout(parts->alphabet.num_dense_symbols).planes;
+    const uint64_t nwords = div_up(src.n + 1, 64) * nplanes;
+    uint64_t *d_blocks = nullptr;
+    uint8_t *d_bwt = nullptr;
+    CUDA_TRY(cudaMalloc(&d_blocks, nwords * 8));
+    cudaError_t e = cudaMalloc(&d_bwt, src.n ? src.n : 1);
+    if (e == cudaSuccess) e = cudaMemcpy(d_blocks, parts->interleaved_blocks, nwords * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && src.n) {
+        k_planes_to_bwt<<<(unsigned)div_up(src.n, 256), 256>>>(d_blocks, nplanes, src.n, d_bwt);
+        e = cudaGetLastError();
+    }
+    cudaFree(d_blocks);
+    if (e != cudaSuccess) {
+        if (d_bwt) cudaFree(d_bwt);
+        return fail(GDX_ERR_CUDA, "plane upload failed: %s", cudaGetErrorString(e));
+    }
+    src.d_bwt = d_bwt;
+    gdx_status st = build_image(src, device, out);
+    cudaFree(d_bwt);
+    return st;
+}
+
+extern "C" gdx_status gdx_suffix_array(const uint8_t *dense_text, uint64_t n, uint32_t sigma, uint32_t where,
+                                       int32_t device_req, uint64_t *sa_out) {
+    if (n == 0) return GDX_OK;
+    if (!dense_text || !sa_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    if (sigma < 2 || sigma > 256) return fail(GDX_ERR_BAD_ARG, "alphabet size must be in [2,256]");
+    for (uint64_t i = 0; i < n; ++i)
+        if (dense_text[i] >= sigma) return fail(GDX_ERR_BAD_ARG, "symbol %u at %llu is not dense", dense_text[i], (unsigned long long)i);
+    if (where == GDX_CONSTRUCT_HOST) {
+        std::vector<int64_t> sa;
+        suffix_array_sais(dense_text, n, sigma, sa);
+        for (uint64_t i = 0; i < n; ++i) sa_out[i] = (uint64_t)sa[i];
+        return GDX_OK;
+    }
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    DeviceGuard guard(device);
+    DeviceBuildResult r;
+    gdx_status st = device_build_from_text(dense_text, nullptr, n, sigma, 1, r, t_error, true, true);
+    if (st != GDX_OK) return st;
+    std::vector<uint32_t> sa32(n);
+    cudaError_t e = cudaMemcpy(sa32.data(), r.d_sa, n * 4, cudaMemcpyDeviceToHost);
+    const uint64_t viol = r.verify_violations;
+    r.release();
+    if (e != cudaSuccess) return fail(GDX_ERR_CUDA, "suffix array download failed: %s", cudaGetErrorString(e));
+    for (uint64_t i = 0; i < n; ++i) sa_out[i] = sa32[i];
+    if (viol) return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)", (unsigned long long)viol);
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_download_bwt(const gdx_index *idx, uint8_t *bwt_out) {
+    if (!idx || !bwt_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    const uint64_t n = idx->h.n, chunk = 256ull << 20;
+    uint8_t *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, std::min<uint64_t>(n ? n : 1, chunk)));
+    gdx_status st = GDX_OK;
+    for (uint64_t b = 0; b < n && st == GDX_OK; b += chunk) {
+        const uint64_t e = std::min<uint64_t>(n, b + chunk);
+        st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+            k_records_to_bwt<decltype(L)><<<(unsigned)div_up(e - b, 256), 256>>>(idx->dev, b, e, d);
+            return GDX_OK;
+        });
+        cudaError_t ce = cudaMemcpy(bwt_out + b, d, e - b, cudaMemcpyDeviceToHost);
+        if (st == GDX_OK && ce != cudaSuccess) st = fail(GDX_ERR_CUDA, "BWT download failed: %s", cudaGetErrorString(ce));
+    }
+    cudaFree(d);
+    return st;
+}
+
+extern "C" gdx_status gdx_index_get_count(const gdx_index *idx, uint64_t *count_out) {
+    if (!idx || !count_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    CUDA_TRY(cudaMemcpy(count_out, (const uint8_t *)idx->image + idx->h.off_count, (uint64_t)(idx->h.sigma + 1) * 8,
+                        cudaMemcpyDeviceToHost));
+    return GDX_OK;
+}
+
+extern "C" void gdx_index_destroy(gdx_index *idx) {
+    if (!idx) return;
+    DeviceGuard guard(idx->device);
+    for (Workspace *w : idx->free_ws) {
+        w->destroy();
+        delete w;
+    }
+    for (auto &p : idx->pinned)
+        if (p.p) cudaFreeHost(p.p);
+    if (idx->own_image && idx->image) cudaFree(idx->image);
+    delete idx;
+}
+
+extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out) {
+    if (!idx || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    const ImageHeader &h = idx->h;
+    out->text_len = h.n;
+    out->num_texts = h.ntexts;
+    out->num_dense_symbols = h.sigma;
+    out->num_searchable_dense_symbols = h.ns;
+    out->storage = h.storage;
+    out->sampling_rate = h.sampling_rate;
+    out->lookup_table_depth = h.lookup_depth;
+    out->rank_layout = h.layout.kind;
+    out->rank_record_bytes = h.layout.stride;
+    out->rank_positions_per_record = 1u << h.layout.log2_pos;
+    out->device = idx->device;
+    out->image_bytes = h.image_bytes;
+    out->rank_bytes = h.off_samples - h.off_records;
+    out->sample_bytes = h.off_lookup - h.off_samples;
+    out->lookup_bytes = h.off_border_rows - h.off_lookup;
+    return GDX_OK;
+}
+
+// ================================================================================================
+// replication
+// ================================================================================================
+extern "C" uint64_t gdx_index_header_bytes(void) { return sizeof(ImageHeader); }
+
+extern "C" gdx_status gdx_index_export(const gdx_index *idx, void *header_out, const void **device_image,
+                                       uint64_t *image_bytes) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "idx is NULL");
+    if (header_out) memcpy(header_out, &idx->h, sizeof(ImageHeader));
+    if (device_image) *device_image = idx->image;
+    if (image_bytes) *image_bytes = idx->h.image_bytes;
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_image, int32_t device_req,
+                                            int32_t own_image, gdx_index **out) {
+    if (!header || !device_image || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    *out = nullptr;
+    ImageHeader h;
+    memcpy(&h, header, sizeof h);
+    if (h.magic != kImageMagic || h.version != GDX_ABI_VERSION)
+        return fail(GDX_ERR_BAD_ARG, "not a genedex_b200 image header (magic/version mismatch)");
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    gdx_index *idx = new gdx_index();
+    idx->h = h;
+    idx->image = device_image;
+    idx->own_image = own_image != 0;
+    idx->device = device;
+    idx->dev = make_dev_index(h, device_image);
+    *out = idx;
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_replicate(const gdx_index *idx, const int32_t *devices, int32_t n_devices,
+                                          gdx_index **out_replicas) {
+    if (!idx || !devices || !out_replicas || n_devices < 0) return fail(GDX_ERR_BAD_ARG, "bad argument");
+    for (int i = 0; i < n_devices; ++i) out_replicas[i] = nullptr;
+    for (int i = 0; i < n_devices; ++i) {
+        int device;
+        GDX_TRY(resolve_device(devices[i], &device));
+        DeviceGuard guard(device);
+        void *img = nullptr;
+        CUDA_TRY(cudaMalloc(&img, idx->h.image_bytes));
+        cudaError_t e = cudaMemcpyPeer(img, device, idx->image, idx->device, idx->h.image_bytes);
+        if (e != cudaSuccess) {
+            cudaFree(img);
+            return fail(GDX_ERR_CUDA, "peer copy to device %d failed: %s", device, cudaGetErrorString(e));
+        }
+        gdx_status st = gdx_index_adopt_image(&idx->h, img, device, 1, &out_replicas[i]);
+        if (st != GDX_OK) {
+            cudaFree(img);
+            return st;
+        }
+    }
+    return GDX_OK;
+}
+
+// ================================================================================================
+// search
+// ================================================================================================
+namespace {
+
+template <class L>
+void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint64_t *b, int mode,
+                   uint64_t qbase, uint64_t *err, unsigned long long *steps, int single_path,
+                   cudaStream_t stream) {
+    (void)single_path;
+    if (dq.nq == 0) return;
+    k_search<L><<<(unsigned)div_up(dq.nq, 256), 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps);
+}
+
+gdx_status check_queries(const gdx_queries *q) {
+    if (!q) return fail(GDX_ERR_BAD_ARG, "queries is NULL");
+    if (q->nq && !q->offsets && q->fixed_len && !q->bytes) return fail(GDX_ERR_BAD_ARG, "queries->bytes is NULL");
+    return GDX_OK;
+}
+
+uint64_t query_bytes_end(const gdx_queries *q, uint64_t i) {
+    return q->offsets ? q->offsets[i] : i * q->fixed_len;
+}
+
+// Chunked pipeline over kSlots streams: H2D(query bytes) -> k_search -> D2H(results) per chunk.
+// If dev_a/dev_b are given the results stay on the device (locate path) and nothing is copied back.
+gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *qs, uint64_t *out_a,
+                       uint64_t *out_b, int mode, uint64_t *dev_a, uint64_t *dev_b) {
+    const uint64_t nq = qs->nq;
+    for (int s = 0; s < kSlots; ++s) ws->slot[s].ev_used = 0;
+    CUDA_TRY(cudaMemset(ws->small.d, 0xff, 4 * sizeof(uint64_t)));
+    CUDA_TRY(cudaMemset(ws->small.d + 4, 0, 12 * sizeof(uint64_t)));
+    unsigned long long *d_steps = reinterpret_cast<unsigned long long *>(ws->small.d + 4);
+    const uint64_t base0 = query_bytes_end(qs, 0);
+    uint64_t q0 = 0;
+    int k = 0;
+    while (q0 < nq) {
+        // chunk [q0, q1): about kChunkBytes of query bytes, at least one query
+        uint64_t q1;
+        if (qs->offsets) {
+            const uint64_t *b = qs->offsets + q0 + 1, *e = qs->offsets + nq + 1;
+            const uint64_t *it = std::upper_bound(b, e, qs->offsets[q0] + kChunkBytes);
+            q1 = q0 + (uint64_t)(it - b);
+            if (q1 == q0) q1 = q0 + 1;
+            q1 = std::min<uint64_t>(q1, std::min<uint64_t>(nq, q0 + (4ull << 20)));
+        } else {
+            const uint64_t per = qs->fixed_len ? std::max<uint64_t>(1, kChunkBytes / qs->fixed_len) : (4ull << 20);
+            q1 = std::min<uint64_t>(nq, q0 + std::min<uint64_t>(per, 4ull << 20));
+        }
+        const uint64_t cq = q1 - q0;
+        const uint64_t byte0 = query_bytes_end(qs, q0), byte1 = query_bytes_end(qs, q1);
+        Slot &sl = ws->slot[k % kSlots];
+        // growing a slot buffer frees the old one: only safe once the slot's stream has drained
+        if (sl.bytes.cap < byte1 - byte0 + 16 || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
+            (!dev_a && (sl.out_a.cap < cq * 8 || (mode == 0 && sl.out_b.cap < cq * 8))))
+            CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        CUDA_TRY(sl.bytes.reserve(byte1 - byte0 + 16));
+        if (byte1 > byte0)
+            CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, qs->bytes + (byte0 - 0), byte1 - byte0, cudaMemcpyHostToDevice,
+                                     sl.stream));
+        DevQueries dq;
+        dq.bytes = sl.bytes.as<uint8_t>();
+        dq.offsets = nullptr;
+        dq.fixed_len = qs->fixed_len;
+        dq.nq = cq;
+        dq.base = 0;
+        if (qs->offsets) {
+            CUDA_TRY(sl.offsets.reserve((cq + 1) * 8));
+            CUDA_TRY(cudaMemcpyAsync(sl.offsets.p, qs->offsets + q0, (cq + 1) * 8, cudaMemcpyHostToDevice,
+                                     sl.stream));
+            dq.offsets = sl.offsets.as<uint64_t>();
+            dq.base = byte0;
+        }
+        uint64_t *a, *b;
+        if (dev_a) {
+            a = dev_a + q0;
+            b = dev_b ? dev_b + q0 : nullptr;
+        } else {
+            CUDA_TRY(sl.out_a.reserve(cq * 8));
+            a = sl.out_a.as<uint64_t>();
+            b = nullptr;
+            if (mode == 0) {
+                CUDA_TRY(sl.out_b.reserve(cq * 8));
+                b = sl.out_b.as<uint64_t>();
+            }
+        }
+        cudaEvent_t e0 = ws->next_event(sl), e1 = ws->next_event(sl);
+        CUDA_TRY(cudaEventRecord(e0, sl.stream));
+        gdx_status st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+            launch_search<decltype(L)>(idx, dq, a, b, mode, q0, ws->small.d + (k % kSlots), d_steps, 0, sl.stream);
+            return GDX_OK;
+        });
+        GDX_TRY(st);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(e1, sl.stream));
+        if (!dev_a) {
+            CUDA_TRY(cudaMemcpyAsync(out_a + q0, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        t_stats.kernel_launches += 1;
+        q0 = q1;
+        ++k;
+    }
+    (void)base0;
+    for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(ws->slot[s].stream));
+    CUDA_TRY(cudaMemcpy(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    double ms = 0;
+    for (int s = 0; s < kSlots; ++s)
+        for (size_t i = 0; i + 1 < ws->slot[s].ev_used; i += 2) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ws->slot[s].ev[i], ws->slot[s].ev[i + 1]);
+            ms += t;
+        }
+    t_stats.queries = nq;
+    t_stats.lf_steps = ws->small.h[4];
+    t_stats.kernel_ms_search = ms;
+    uint64_t bad = kNoError;
+    for (int s = 0; s < kSlots; ++s) bad = std::min(bad, ws->small.h[s]);
+    if (bad != kNoError) {
+        t_error_query = bad;
+        return fail(GDX_ERR_INVALID_SYMBOL,
+                    "query %llu: symbol in io representation should be valid (alphabet.rs:195-198)",
+                    (unsigned long long)bad);
+    }
+    return GDX_OK;
+}
+
+gdx_status begin_call(const gdx_index *idx, const char *what) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "%s: idx is NULL", what);
+    t_stats = gdx_stats{};
+    return GDX_OK;
+}
+
+// CSR + expand + walk on device-resident intervals; results in ws->hit_offsets (n+1) and ws->hits.
+gdx_status locate_device_intervals(const gdx_index *idx, Workspace *ws, const uint64_t *d_starts,
+                                   const uint64_t *d_ends, uint64_t n, uint64_t *total_out) {
+    cudaStream_t st = ws->slot[0].stream;
+    CUDA_TRY(ws->counts.reserve((n + 1) * 8));
+    CUDA_TRY(ws->hit_offsets.reserve((n + 1) * 8));
+    CUDA_TRY(cudaMemsetAsync(ws->small.d + 4, 0, 12 * sizeof(uint64_t), st));
+    CUDA_TRY(cudaMemsetAsync(ws->counts.as<uint64_t>() + n, 0, 8, st));
+    unsigned long long *d_big = reinterpret_cast<unsigned long long *>(ws->small.d + 6);
+    CUDA_TRY(cudaEventRecord(ws->ev_a, st));
+    if (n) k_interval_counts<<<(unsigned)div_up(n, 256), 256, 0, st>>>(d_starts, d_ends, n, ws->counts.as<uint64_t>(), d_big);
+    size_t tmp_bytes = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ws->counts.as<uint64_t>(),
+                                           ws->hit_offsets.as<uint64_t>(), n + 1, st));
+    CUDA_TRY(ws->scan_tmp.reserve(tmp_bytes));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->scan_tmp.p, tmp_bytes, ws->counts.as<uint64_t>(),
+                                           ws->hit_offsets.as<uint64_t>(), n + 1, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->small.h + 8, ws->hit_offsets.as<uint64_t>() + n, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->small.h + 6, d_big, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t total = ws->small.h[8], nbig = ws->small.h[6];
+    *total_out = total;
+    t_stats.kernel_launches += 2;
+    if (total) {
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t need = (total > ws->rows.cap / 8 ? total * 8 : 0) + (total > ws->hits.cap / 16 ? total * 16 : 0);
+        if (need > free_b + ws->rows.cap + ws->hits.cap)
+            return fail(GDX_ERR_OOM, "%llu hits do not fit into device memory; split the batch",
+                        (unsigned long long)total);
+        CUDA_TRY(ws->rows.reserve(total * 8));
+        CUDA_TRY(ws->hits.reserve(total * 16));
+        CUDA_TRY(ws->big_list.reserve((nbig + 1) * 8));
+        unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(ws->small.d + 7);
+        k_expand_rows<<<(unsigned)div_up(n, 256), 256, 0, st>>>(d_starts, d_ends, ws->hit_offsets.as<uint64_t>(), n,
+                                                               ws->rows.as<uint64_t>(), ws->big_list.as<uint64_t>(),
+                                                               d_cursor);
+        if (nbig) {
+            dim3 grid((unsigned)nbig, 32);
+            k_expand_big_rows<<<grid, 256, 0, st>>>(d_starts, d_ends, ws->hit_offsets.as<uint64_t>(),
+                                                    ws->big_list.as<uint64_t>(), ws->rows.as<uint64_t>());
+            t_stats.kernel_launches += 1;
+        }
+        unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 5);
+        gdx_status s2 = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+            k_locate_walk<decltype(L)><<<(unsigned)div_up(total, 256), 256, 0, st>>>(
+                idx->dev, ws->rows.as<uint64_t>(), total, ws->hits.as<ulonglong2>(), d_walk);
+            return GDX_OK;
+        });
+        GDX_TRY(s2);
+        CUDA_TRY(cudaGetLastError());
+        t_stats.kernel_launches += 2;
+    }
+    CUDA_TRY(cudaEventRecord(ws->ev_b, st));
+    return GDX_OK;
+}
+
+gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out) {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    PinnedHits *best = nullptr;
+    for (auto &p : idx->pinned)
+        if (!p.in_use && p.cap >= bytes && (!best || p.cap < best->cap)) best = &p;
+    if (!best) {
+        for (auto &p : idx->pinned)  // recycle the largest free but too small buffer
+            if (!p.in_use && (!best || p.cap > best->cap)) best = &p;
+        if (best) {
+            cudaFreeHost(best->p);
+            best->p = nullptr;
+            best->cap = 0;
+        } else {
+            idx->pinned.push_back(PinnedHits{});
+            best = &idx->pinned.back();
+        }
+        const uint64_t want = align_up(bytes + bytes / 4 + 4096, 4096);
+        cudaError_t e = cudaMallocHost(&best->p, want);
+        if (e != cudaSuccess) {
+            best->p = nullptr;
+            return fail(GDX_ERR_OOM, "pinned host allocation of %llu bytes failed: %s", (unsigned long long)want,
+                        cudaGetErrorString(e));
+        }
+        best->cap = want;
+    }
+    best->in_use = true;
+    *out = best->p;
+    return GDX_OK;
+}
+
+gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64_t total, uint64_t *hit_offsets,
+                         gdx_hit **hits, uint64_t *num_hits) {
+    cudaStream_t st = ws->slot[0].stream;
+    void *h = nullptr;
+    GDX_TRY(acquire_pinned_hits(idx, total * sizeof(gdx_hit), &h));
+    if (total) CUDA_TRY(cudaMemcpyAsync(h, ws->hits.p, total * sizeof(gdx_hit), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hit_offsets, ws->hit_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ws->ev_a, ws->ev_b);
+    t_stats.kernel_ms_locate = ms;
+    t_stats.hits = total;
+    t_stats.walk_steps = ws->small.h[5];
+    *hits = (gdx_hit *)h;
+    *num_hits = total;
+    return GDX_OK;
+}
+
+}  // namespace
+
+extern "C" gdx_status gdx_cursors_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *starts,
+                                       uint64_t *ends) {
+    GDX_TRY(begin_call(idx, "gdx_cursors_many"));
+    GDX_TRY(check_queries(queries));
+    if (queries->nq && (!starts || !ends)) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+    DeviceGuard guard(idx->device);
+    WsLease lease(idx);
+    if (!lease.w) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+    return search_host(idx, lease.w, queries, starts, ends, 0, nullptr, nullptr);
+}
+
+extern "C" gdx_status gdx_count_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *counts) {
+    GDX_TRY(begin_call(idx, "gdx_count_many"));
+    GDX_TRY(check_queries(queries));
+    if (queries->nq && !counts) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+    DeviceGuard guard(idx->device);
+    WsLease lease(idx);
+    if (!lease.w) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+    return search_host(idx, lease.w, queries, counts, nullptr, 1, nullptr, nullptr);
+}
+
+extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
+                                      gdx_hit **hits, uint64_t *num_hits) {
+    GDX_TRY(begin_call(idx, "gdx_locate_many"));
+    GDX_TRY(check_queries(queries));
+    if (!hit_offsets || !hits || !num_hits) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+    *hits = nullptr;
+    *num_hits = 0;
+    DeviceGuard guard(idx->device);
+    WsLease lease(idx);
+    Workspace *ws = lease.w;
+    if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+    const uint64_t n = queries->nq;
+    // a buffer may only be replaced once nothing in flight uses it: every call ends synchronized
+    CUDA_TRY(ws->starts.reserve((n + 1) * 8));
+    CUDA_TRY(ws->ends.reserve((n + 1) * 8));
+    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 0, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
+    uint64_t total = 0;
+    GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
+    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+}
+
+extern "C" gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, const uint64_t *ends,
+                                           uint64_t n, uint64_t *hit_offsets, gdx_hit **hits, uint64_t *num_hits) {
+    GDX_TRY(begin_call(idx, "gdx_locate_intervals"));
+    if (!hit_offsets || !hits || !num_hits || (n && (!starts || !ends))) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    *hits = nullptr;
+    *num_hits = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if (starts[i] > ends[i] || ends[i] > idx->h.n)
+            return fail(GDX_ERR_BAD_ARG, "interval %llu is not inside [0, text_len]", (unsigned long long)i);
+    DeviceGuard guard(idx->device);
+    WsLease lease(idx);
+    Workspace *ws = lease.w;
+    if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStream_t st = ws->slot[0].stream;
+    CUDA_TRY(ws->starts.reserve((n + 1) * 8));
+    CUDA_TRY(ws->ends.reserve((n + 1) * 8));
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(ws->starts.p, starts, n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
+    }
+    uint64_t total = 0;
+    GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
+    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+}
+
+extern "C" void gdx_free_hits(const gdx_index *idx, gdx_hit *hits) {
+    if (!idx || !hits) return;
+    std::lock_guard<std::mutex> lk(idx->mu);
+    for (auto &p : idx->pinned)
+        if (p.p == hits) p.in_use = false;
+}
+
+extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, uint64_t *ends,
+                                      const uint8_t *io_symbols, uint64_t n) {
+    GDX_TRY(begin_call(idx, "gdx_extend_many"));
+    if (n == 0) return GDX_OK;
+    if (!starts || !ends || !io_symbols) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    for (uint64_t i = 0; i < n; ++i)  // text_with_rank_support/mod.rs:106-110 bounds assert
+        if (starts[i] > idx->h.n || ends[i] > idx->h.n)
+            return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)i);
+    DeviceGuard guard(idx->device);
+    WsLease lease(idx);
+    Workspace *ws = lease.w;
+    if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaStream_t st = ws->slot[0].stream;
+    CUDA_TRY(ws->starts.reserve(n * 8));
+    CUDA_TRY(ws->ends.reserve(n * 8));
+    CUDA_TRY(ws->symbols.reserve(n));
+    CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 8, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->starts.p, starts, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->symbols.p, io_symbols, n, cudaMemcpyHostToDevice, st));
+    GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+        k_extend<decltype(L)><<<(unsigned)div_up(n, 256), 256, 0, st>>>(
+            idx->dev, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), ws->symbols.as<uint8_t>(), n, ws->small.d);
+        return GDX_OK;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    t_stats.kernel_launches = 1;
+    if (ws->small.h[0] != kNoError) {
+        t_error_query = ws->small.h[0];
+        return fail(GDX_ERR_INVALID_SYMBOL, "cursor %llu: symbol in io representation should be valid (alphabet.rs:195-198)",
+                    (unsigned long long)ws->small.h[0]);
+    }
+    CUDA_TRY(cudaMemcpy(starts, ws->starts.p, n * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(ends, ws->ends.p, n * 8, cudaMemcpyDeviceToHost));
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_cursor_for_query(const gdx_index *idx, const uint8_t *query, uint64_t len, uint64_t *start,
+                                           uint64_t *end) {
+    if (!idx || !start || !end || (len && !query)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    // single-query path of the reference (lib.rs:217-235): when the lookup-table interval is already
+    // empty, the next symbol to the left is still translated (and may panic) before the loop breaks.
+    const uint32_t D = idx->h.lookup_depth;
+    gdx_queries q = {query, nullptr, len, 1};
+    uint8_t dummy = 0;
+    if (len == 0) q.bytes = &dummy;
+    gdx_status st = gdx_cursors_many(idx, &q, start, end);
+    if (st != GDX_OK) return st;
+    if (D > 0 && len > D && *start == *end) {
+        gdx_queries suffix = {query + (len - D), nullptr, D, 1};
+        uint64_t s2 = 0, e2 = 0;
+        GDX_TRY(gdx_cursors_many(idx, &suffix, &s2, &e2));
+        if (s2 == e2 && idx->h.io_to_dense[query[len - D - 1]] == 0) {
+            t_error_query = 0;
+            return fail(GDX_ERR_INVALID_SYMBOL, "symbol in io representation should be valid (alphabet.rs:195-198)");
+        }
+    }
+    return GDX_OK;
+}
+
+// ================================================================================================
+// device-resident entry points
+// ================================================================================================
+static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, uint64_t *a, uint64_t *b, int mode,
+                                uint64_t *d_error, void *stream) {
+    if (!idx || !dq_in) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    DevQueries dq;
+    dq.bytes = dq_in->bytes;
+    dq.offsets = dq_in->offsets;
+    dq.fixed_len = dq_in->fixed_len;
+    dq.nq = dq_in->nq;
+    dq.base = 0;
+    GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+        launch_search<decltype(L)>(idx, dq, a, b, mode, 0, d_error, nullptr, 0, (cudaStream_t)stream);
+        return GDX_OK;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_cursors_many_device(const gdx_index *idx, const gdx_queries *d_queries, uint64_t *d_starts,
+                                              uint64_t *d_ends, uint64_t *d_error, void *stream) {
+    return search_device(idx, d_queries, d_starts, d_ends, 0, d_error, stream);
+}
+extern "C" gdx_status gdx_count_many_device(const gdx_index *idx, const gdx_queries *d_queries, uint64_t *d_counts,
+                                            uint64_t *d_error, void *stream) {
+    return search_device(idx, d_queries, d_counts, nullptr, 1, d_error, stream);
+}
+
+extern "C" gdx_status gdx_locate_intervals_device(const gdx_index *idx, const uint64_t *d_starts,
+                                                  const uint64_t *d_ends, uint64_t n, const uint64_t *d_hit_offsets,
+                                                  uint64_t num_hits, gdx_hit *d_hits, void *stream) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "idx is NULL");
+    if (n == 0 || num_hits == 0) return GDX_OK;
+    if (!d_starts || !d_ends || !d_hit_offsets || !d_hits) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // stream-ordered scratch: rows (8 B per hit), worklist of wide intervals, two counters
+    uint64_t *rows = nullptr, *big = nullptr;
+    CUDA_TRY(cudaMallocAsync((void **)&rows, num_hits * 8, st));
+    CUDA_TRY(cudaMallocAsync((void **)&big, (n + 2) * 8, st));
+    CUDA_TRY(cudaMemsetAsync(big, 0, 16, st));
+    k_expand_rows<<<(unsigned)div_up(n, 256), 256, 0, st>>>(d_starts, d_ends, d_hit_offsets, n, rows, big + 2,
+                                                           reinterpret_cast<unsigned long long *>(big));
+    CUDA_TRY(cudaGetLastError());
+    uint64_t nbig = 0;  // the number of wide intervals decides the next grid: one small D2H + sync
+    CUDA_TRY(cudaMemcpyAsync(&nbig, big, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (nbig) {
+        dim3 grid((unsigned)nbig, 32);
+        k_expand_big_rows<<<grid, 256, 0, st>>>(d_starts, d_ends, d_hit_offsets, big + 2, rows);
+    }
+    GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+        k_locate_walk<decltype(L)><<<(unsigned)div_up(num_hits, 256), 256, 0, st>>>(
+            idx->dev, rows, num_hits, reinterpret_cast<ulonglong2 *>(d_hits), nullptr);
+        return GDX_OK;
+    }));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaFreeAsync(rows, st));
+    CUDA_TRY(cudaFreeAsync(big, st));
+    return GDX_OK;
+}
+
+// ================================================================================================
+// random-gather ceiling
+// ================================================================================================
+__global__ void k_fill_random(uint64_t *p, uint64_t nwords) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords;
+         i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = mix64(i);
+}
+
+extern "C" gdx_status gdx_measure_random_gather(int32_t device_req, uint64_t table_bytes, uint32_t record_bytes,
+                                                uint64_t loads, int32_t chained, double *gbps_out,
+                                                double *gloads_out) {
+    if (record_bytes != 32 && record_bytes != 64 && record_bytes != 128)
+        return fail(GDX_ERR_BAD_ARG, "record_bytes must be 32, 64 or 128");
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    DeviceGuard guard(device);
+    uint64_t nrec = 1;
+    while (nrec * 2 * record_bytes <= table_bytes) nrec *= 2;
+    uint8_t *table = nullptr;
+    uint64_t *sink = nullptr;
+    CUDA_TRY(cudaMalloc(&table, nrec * record_bytes));
+    cudaError_t e = cudaMalloc(&sink, 8);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    float ms = 0;
+    const unsigned blocks = 148 * 8, threads = 256;
+    uint32_t rounds = (uint32_t)std::max<uint64_t>(1, loads / (2ull * blocks * threads));
+    auto launch = [&](uint32_t r) {
+        if (record_bytes == 32) k_gather<32><<<blocks, threads>>>(table, nrec - 1, r, chained, sink);
+        else if (record_bytes == 64) k_gather<64><<<blocks, threads>>>(table, nrec - 1, r, chained, sink);
+        else k_gather<128><<<blocks, threads>>>(table, nrec - 1, r, chained, sink);
+    };
+    if (e == cudaSuccess) {
+        k_fill_random<<<blocks, threads>>>((uint64_t *)table, nrec * record_bytes / 8);
+        launch(rounds / 8 + 1);  // warm-up
+        e = cudaEventCreate(&e0);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaEventRecord(e0);
+    if (e == cudaSuccess) {
+        launch(rounds);
+        e = cudaEventRecord(e1);
+    }
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(table);
+    if (sink) cudaFree(sink);
+    if (e != cudaSuccess) return fail(GDX_ERR_CUDA, "gather microbenchmark failed: %s", cudaGetErrorString(e));
+    const double nloads = 2.0 * blocks * threads * (double)rounds;
+    if (gloads_out) *gloads_out = nloads / (ms * 1e-3) / 1e9;
+    if (gbps_out) *gbps_out = nloads * record_bytes / (ms * 1e-3) / 1e9;
+    return GDX_OK;
+}

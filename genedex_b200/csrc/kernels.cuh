@@ -1,0 +1,555 @@
+// kernels.cuh -- hand-written sm_100a kernels of the search path.
+//
+//   k_search        K1+K2: lookup-table seed + backward search, one thread per query, both interval
+//                   borders' records in flight together      (batch_computed_cursors.rs:36-172,
+//                                                              lookup_table.rs:68-161, condensed.rs:137-341)
+//   k_extend        one LF pair per cursor                   (cursor.rs:34-51)
+//   k_interval_counts / k_expand_rows / k_expand_big_rows    rows of every hit (CSR)
+//   k_locate_walk   K3+K4: LF-walk to the next SA sample + text-id mapping, one thread per hit
+//                                                             (sampled_suffix_array.rs:110-138,
+//                                                              text_id_search_tree.rs:35-64)
+//   k_pack_*        BWT -> rank records (+ per-superblock totals)        (condensed.rs:59-124,365-415)
+//   k_lut_fill      lookup level d from level d-1            (lookup_table.rs:163-258)
+//   k_planes_to_bwt reference bit planes -> dense BWT        (condensed.rs:343-362)
+//   k_gather        random-gather ceiling microbenchmark     
+//
+// All hot loads are random sector accesses into HBM: there is no reuse to stage through shared
+// memory or TMA, so the design levers are (1) one aligned record per rank, fetched with a single
+// 256-bit LDG.NA (no L1 allocation, keeps L1 for the query bytes and the superblock table),
+// (2) both borders issued back to back, (3) enough resident warps to cover DRAM latency.
+#ifndef GDX_KERNELS_CUH
+#define GDX_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/block/block_scan.cuh>
+
+#include "device_index.h"
+
+namespace gdx {
+
+struct DevQueries {
+    const uint8_t *bytes;
+    const uint64_t *offsets;  // nq + 1 entries or nullptr
+    uint64_t fixed_len;
+    uint64_t nq;
+    uint64_t base;            // subtracted from offsets[] (chunked uploads)
+};
+
+constexpr uint64_t kNoError = ~0ull;
+
+// ---- loads -------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg256_na(const void *p, uint64_t w[4]) {
+    asm("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+        : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+        : "l"(p));
+}
+__device__ __forceinline__ void ldg128_na(const void *p, uint64_t &lo, uint64_t &hi) {
+    asm("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
+}
+
+// ---- layout traits -----------------------------------------------------------------------------
+struct K32 {
+    static constexpr uint32_t kLog2P = 6;
+    struct Planes {
+        uint64_t w[4];
+    };
+    struct Rec {
+        uint64_t w[4];
+    };
+    static __device__ __forceinline__ Planes load_planes(const DevIndex &ix, uint64_t i) {
+        Planes r;
+        ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        return r;
+    }
+    static __device__ __forceinline__ Rec load(const DevIndex &ix, uint64_t i, uint32_t) {
+        Rec r;
+        ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        return r;
+    }
+    static __device__ __forceinline__ Rec with_offset(const DevIndex &, const Planes &p, uint64_t,
+                                                      uint32_t) {
+        Rec r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.w[k] = p.w[k];
+        return r;
+    }
+    static __device__ __forceinline__ uint32_t symbol_at(const Planes &p, uint64_t i) {
+        return k32_symbol_at(p.w, (uint32_t)(i & 63));
+    }
+    static __device__ __forceinline__ uint32_t local_rank(const Rec &r, uint32_t c, uint64_t i) {
+        return k32_local_rank(r.w, c, (uint32_t)(i & 63));
+    }
+    // LF of the symbol without an in-record offset (sigma == 6: dense 5 = `N`), see rank_core.h
+    static __device__ __noinline__ uint64_t lf_derived(const DevIndex &ix, uint64_t i) {
+        uint64_t w[4];
+        ldg256_na(ix.records + ((i >> 6) << 5), w);
+        uint64_t others = k32_local_rank_sum(w, (uint32_t)(i & 63));
+        const uint64_t *sb = ix.sbc + (i >> kSuperblockLog2) * 4;
+#pragma unroll
+        for (uint32_t c = 1; c <= 4; ++c) others += __ldg(sb + (c - 1)) - __ldg(ix.count + c);
+        uint64_t rank0 = lower_bound_u64(ix.border_rows, ix.n_border, i);
+        return __ldg(ix.count + 5) + (i - rank0 - others);
+    }
+};
+
+template <int B>
+struct KG {
+    static constexpr uint32_t kLog2P = 7;
+    struct Planes {
+        uint64_t lo[B], hi[B];
+    };
+    struct Rec {
+        uint64_t lo[B], hi[B];
+        uint32_t off;
+    };
+    static __device__ __forceinline__ const uint8_t *rec_ptr(const DevIndex &ix, uint64_t i) {
+        return ix.records + (i >> 7) * ix.stride;
+    }
+    static __device__ __forceinline__ Planes load_planes(const DevIndex &ix, uint64_t i) {
+        Planes r;
+        const uint8_t *p = rec_ptr(ix, i);
+#pragma unroll
+        for (int k = 0; k < B; ++k) ldg128_na(p + 16 * k, r.lo[k], r.hi[k]);
+        return r;
+    }
+    static __device__ __forceinline__ Rec load(const DevIndex &ix, uint64_t i, uint32_t c) {
+        Rec r;
+        const uint8_t *p = rec_ptr(ix, i);
+#pragma unroll
+        for (int k = 0; k < B; ++k) ldg128_na(p + 16 * k, r.lo[k], r.hi[k]);
+        r.off = __ldg(reinterpret_cast<const uint16_t *>(p + 16 * B) + (c - 1));
+        return r;
+    }
+    static __device__ __forceinline__ Rec with_offset(const DevIndex &ix, const Planes &pl, uint64_t i,
+                                                      uint32_t c) {
+        Rec r;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            r.lo[k] = pl.lo[k];
+            r.hi[k] = pl.hi[k];
+        }
+        r.off = __ldg(reinterpret_cast<const uint16_t *>(rec_ptr(ix, i) + 16 * B) + (c - 1));
+        return r;
+    }
+    static __device__ __forceinline__ uint32_t symbol_at(const Planes &p, uint64_t i) {
+        return kg_symbol_at<B>(p.lo, p.hi, (uint32_t)(i & 127));
+    }
+    static __device__ __forceinline__ uint32_t local_rank(const Rec &r, uint32_t c, uint64_t i) {
+        return r.off + kg_block_count<B>(r.lo, r.hi, c, (uint32_t)(i & 127));
+    }
+    static __device__ __forceinline__ uint64_t lf_derived(const DevIndex &, uint64_t i) { return i; }
+};
+
+__device__ __forceinline__ uint64_t sbc_load(const DevIndex &ix, uint64_t i, uint32_t c) {
+    return __ldg(ix.sbc + (i >> kSuperblockLog2) * ix.noff + (c - 1));
+}
+
+// LF(c, s), LF(c, e) with all four loads issued before the first use (lib.rs:273-275)
+template <class L>
+__device__ __forceinline__ void lf_pair(const DevIndex &ix, uint32_t c, uint64_t &s, uint64_t &e) {
+    if (c > ix.noff) {  // derived symbol: rare and divergent by nature
+        s = L::lf_derived(ix, s);
+        e = L::lf_derived(ix, e);
+        return;
+    }
+    typename L::Rec rs = L::load(ix, s, c);
+    typename L::Rec re = L::load(ix, e, c);
+    uint64_t bs = sbc_load(ix, s, c), be = sbc_load(ix, e, c);
+    s = bs + L::local_rank(rs, c, s);
+    e = be + L::local_rank(re, c, e);
+}
+
+template <class L>
+__device__ __forceinline__ uint64_t lf_one(const DevIndex &ix, uint32_t c, uint64_t i) {
+    if (c > ix.noff) return L::lf_derived(ix, i);
+    typename L::Rec r = L::load(ix, i, c);
+    return sbc_load(ix, i, c) + L::local_rank(r, c, i);
+}
+
+__device__ __forceinline__ void lut_load(const DevIndex &ix, uint64_t entry, uint64_t &s, uint64_t &e) {
+    if (ix.wide) {
+        ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ix.lookup) + entry);
+        s = v.x;
+        e = v.y;
+    } else {
+        uint2 v = __ldg(reinterpret_cast<const uint2 *>(ix.lookup) + entry);
+        s = v.x;
+        e = v.y;
+    }
+}
+
+__device__ __forceinline__ void report_error(uint64_t *err, uint64_t q) {
+    if (err) atomicMin(reinterpret_cast<unsigned long long *>(err), (unsigned long long)q);
+}
+
+// ---- K1 + K2: seed + backward search ----------------------------------------------------------------
+// mode 0: out_a = starts, out_b = ends; mode 1: out_a = counts.
+// Follows the batched path of the reference: a symbol is translated only when the search reaches
+// it (batch_computed_cursors.rs:84-87,106-113), queries leave when all symbols are consumed or the
+// interval is empty (:131-158), results are written to the query's own slot (= input order, :160-172).
+template <class L>
+__global__ void __launch_bounds__(256)
+k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__restrict__ out_a,
+         uint64_t *__restrict__ out_b, int mode, uint64_t q_index_base, uint64_t *err,
+         unsigned long long *stat_steps) {
+    __shared__ uint8_t tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = ix.io_to_dense[i];
+    __syncthreads();
+
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps = 0;
+    if (q < qs.nq) {
+        uint64_t begin, len;
+        if (qs.offsets) {
+            begin = __ldg(qs.offsets + q) - qs.base;
+            len = __ldg(qs.offsets + q + 1) - qs.base - begin;
+        } else {
+            begin = q * qs.fixed_len;
+            len = qs.fixed_len;
+        }
+        const uint8_t *p = qs.bytes + begin;
+        bool bad = false;
+
+        // K1: lookup_table.rs:68-161 -- first suffix symbol is the least significant digit
+        const uint64_t depth = len < ix.lookup_depth ? len : ix.lookup_depth;
+        uint64_t pos = len - depth;
+        uint64_t li = 0;
+        for (uint64_t j = 0; j < depth; ++j) {
+            uint32_t c = tab[__ldg(p + pos + j)];
+            // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
+            // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
+            if (c == 0 || c > ix.ns) bad = true;
+            li += (uint64_t)(c - 1) * ix.lut_pow[j];
+        }
+        uint64_t s = 0, e = 0;
+        if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
+
+        // K2: batch_computed_cursors.rs:62-70
+        while (!bad && pos > 0 && s != e) {
+            uint32_t c = tab[__ldg(p + pos - 1)];
+            if (c == 0) {
+                bad = true;
+                break;
+            }
+            lf_pair<L>(ix, c, s, e);
+            --pos;
+            ++steps;
+        }
+        if (bad) {
+            report_error(err, q_index_base + q);
+            s = e = 0;
+        }
+        if (mode == 0) {
+            out_a[q] = s;
+            out_b[q] = e;
+        } else {
+            out_a[q] = e - s;
+        }
+    }
+    if (stat_steps) {
+        uint32_t tot = __reduce_add_sync(0xffffffffu, steps);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(stat_steps, (unsigned long long)tot);
+    }
+}
+
+// ---- Cursor::extend_query_front for many cursors (cursor.rs:34-51) -----------------------------------
+template <class L>
+__global__ void __launch_bounds__(256)
+k_extend(const __grid_constant__ DevIndex ix, uint64_t *__restrict__ starts, uint64_t *__restrict__ ends,
+         const uint8_t *__restrict__ io_symbols, uint64_t n, uint64_t *err) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    uint32_t c = ix.io_to_dense[io_symbols[q]];
+    if (c == 0) {  // the reference translates before it looks at the interval (cursor.rs:35-37)
+        report_error(err, q);
+        return;
+    }
+    uint64_t s = starts[q], e = ends[q];
+    if (s != e) {
+        lf_pair<L>(ix, c, s, e);
+        starts[q] = s;
+        ends[q] = e;
+    }
+}
+
+// ---- CSR plumbing for locate --------------------------------------------------------------------------
+constexpr uint32_t kExpandInline = 32;
+
+// counts[q] = width of interval q; *big_count = number of intervals wider than kExpandInline
+__global__ void k_interval_counts(const uint64_t *__restrict__ starts, const uint64_t *__restrict__ ends,
+                                  uint64_t n, uint64_t *__restrict__ counts,
+                                  unsigned long long *big_count) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint64_t c = ends[q] - starts[q];
+    counts[q] = c;
+    if (c > kExpandInline) atomicAdd(big_count, 1ull);
+}
+
+// rows[hit_offsets[q] + j] = starts[q] + j; intervals wider than kExpandInline go to a worklist
+__global__ void k_expand_rows(const uint64_t *__restrict__ starts, const uint64_t *__restrict__ ends,
+                              const uint64_t *__restrict__ hit_offsets, uint64_t n,
+                              uint64_t *__restrict__ rows, uint64_t *__restrict__ big_list,
+                              unsigned long long *big_cursor) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint64_t s = starts[q], cnt = ends[q] - s, off = hit_offsets[q];
+    if (cnt > kExpandInline) {
+        big_list[atomicAdd(big_cursor, 1ull)] = q;
+        return;
+    }
+    for (uint64_t j = 0; j < cnt; ++j) rows[off + j] = s + j;
+}
+
+// one CTA per wide interval, coalesced fill
+__global__ void k_expand_big_rows(const uint64_t *__restrict__ starts, const uint64_t *__restrict__ ends,
+                                  const uint64_t *__restrict__ hit_offsets,
+                                  const uint64_t *__restrict__ big_list, uint64_t *__restrict__ rows) {
+    const uint64_t q = big_list[blockIdx.x];
+    const uint64_t s = starts[q], cnt = ends[q] - s, off = hit_offsets[q];
+    for (uint64_t j = (uint64_t)blockIdx.y * blockDim.x + threadIdx.x; j < cnt;
+         j += (uint64_t)gridDim.y * blockDim.x)
+        rows[off + j] = s + j;
+}
+
+// ---- K3 + K4: LF-walk to the next sample, then position -> (text id, position in text) ---------------
+template <class L>
+__global__ void __launch_bounds__(256)
+k_locate_walk(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ rows, uint64_t nh,
+              ulonglong2 *__restrict__ hits, unsigned long long *stat_steps) {
+    const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t steps = 0;
+    if (h < nh) {
+        uint64_t i = rows[h];
+        uint64_t pos;
+        for (;;) {  // sampled_suffix_array.rs:117-136
+            const bool sampled = ix.sampling_shift != 0xffffffffu
+                                     ? (i & ((1ull << ix.sampling_shift) - 1)) == 0
+                                     : (i % ix.sampling_rate) == 0;
+            if (sampled) {
+                const uint64_t k = ix.sampling_shift != 0xffffffffu ? i >> ix.sampling_shift
+                                                                    : i / ix.sampling_rate;
+                pos = (ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k)
+                               : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.samples) + k)) +
+                      steps;
+                break;
+            }
+            typename L::Planes pl = L::load_planes(ix, i);
+            const uint32_t c = L::symbol_at(pl, i);
+            if (c == 0) {  // :121-126 text_border_lookup[&i]
+                const uint64_t k = lower_bound_u64(ix.border_rows, ix.n_border, i);
+                pos = __ldg(ix.border_pos + k) + steps;
+                break;
+            }
+            if (c > ix.noff) {
+                i = L::lf_derived(ix, i);
+            } else {
+                typename L::Rec r = L::with_offset(ix, pl, i, c);
+                i = sbc_load(ix, i, c) + L::local_rank(r, c, i);
+            }
+            ++steps;
+        }
+        // text_id_search_tree.rs:35-64: lower_bound over the sentinel positions
+        uint64_t id = lower_bound_u64(ix.sentinels, ix.ntexts, pos);
+        if (id >= ix.ntexts) id = ix.ntexts - 1;
+        const uint64_t base = id == 0 ? 0 : __ldg(ix.sentinels + id - 1) + 1;
+        hits[h] = make_ulonglong2(id, pos - base);
+    }
+    if (stat_steps) {
+        uint32_t tot = __reduce_add_sync(0xffffffffu, steps);
+        if ((threadIdx.x & 31) == 0 && tot) atomicAdd(stat_steps, (unsigned long long)tot);
+    }
+}
+
+// ---- construction of the derived structures on the device --------------------------------------------
+// One CTA per superblock (65536 positions); thread t packs block t.  sb_tot[sb*noff + c-1] receives
+// the number of c in the superblock; k_sb_scan turns that into sbc (exclusive prefix + count[c]).
+__global__ void __launch_bounds__(1024)
+k_pack_k32(const uint8_t *__restrict__ bwt, uint64_t n, uint32_t noff, uint8_t *__restrict__ records,
+           uint64_t n_records, uint64_t *__restrict__ sb_tot) {
+    using Scan = cub::BlockScan<uint32_t, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    const uint64_t blk = (uint64_t)blockIdx.x * 1024 + threadIdx.x;
+    const uint64_t p0 = blk << 6;
+    uint64_t w[4] = {0, 0, 0, 0};
+    if (p0 < n) {
+        const uint32_t nsym = n - p0 < 64 ? (uint32_t)(n - p0) : 64u;
+        for (uint32_t j = 0; j < nsym; ++j) {
+            const uint32_t s = bwt[p0 + j];
+            w[0] |= (uint64_t)(s & 1u) << j;
+            w[1] |= (uint64_t)((s >> 1) & 1u) << j;
+            w[2] |= (uint64_t)((s >> 2) & 1u) << j;
+        }
+    }
+    for (uint32_t c = 1; c <= noff; ++c) {
+        // positions >= n hold all-zero planes = symbol 0, so they never match c >= 1
+        uint32_t cnt = (uint32_t)popc64(match_planes<3>(w, c)), excl, total;
+        Scan(tmp).ExclusiveSum(cnt, excl, total);
+        __syncthreads();
+        w[3] |= (uint64_t)(excl & 0xffffu) << (16u * (c - 1u));
+        if (threadIdx.x == 0) sb_tot[(uint64_t)blockIdx.x * noff + (c - 1)] = total;
+    }
+    if (blk < n_records) {
+        uint4 *dst = reinterpret_cast<uint4 *>(records + (blk << 5));
+        dst[0] = make_uint4((uint32_t)w[0], (uint32_t)(w[0] >> 32), (uint32_t)w[1], (uint32_t)(w[1] >> 32));
+        dst[1] = make_uint4((uint32_t)w[2], (uint32_t)(w[2] >> 32), (uint32_t)w[3], (uint32_t)(w[3] >> 32));
+    }
+}
+
+template <int B>
+__global__ void __launch_bounds__(512)
+k_pack_kg(const uint8_t *__restrict__ bwt, uint64_t n, uint32_t sigma, uint32_t stride,
+          uint8_t *__restrict__ records, uint64_t n_records, uint64_t *__restrict__ sb_tot) {
+    using Scan = cub::BlockScan<uint32_t, 512>;
+    __shared__ typename Scan::TempStorage tmp;
+    const uint64_t blk = (uint64_t)blockIdx.x * 512 + threadIdx.x;
+    const uint64_t p0 = blk << 7;
+    uint64_t lo[B], hi[B];
+#pragma unroll
+    for (int p = 0; p < B; ++p) lo[p] = hi[p] = 0;
+    if (p0 < n) {
+        const uint32_t nsym = n - p0 < 128 ? (uint32_t)(n - p0) : 128u;
+        for (uint32_t j = 0; j < nsym; ++j) {
+            const uint32_t s = bwt[p0 + j];
+#pragma unroll
+            for (int p = 0; p < B; ++p) {
+                const uint64_t bit = (uint64_t)((s >> p) & 1u) << (j & 63u);
+                if (j < 64) lo[p] |= bit; else hi[p] |= bit;
+            }
+        }
+    }
+    uint8_t *rec = records + blk * stride;
+    const uint32_t noff = sigma - 1;
+    for (uint32_t c = 1; c <= noff; ++c) {
+        uint32_t cnt = (uint32_t)(popc64(match_planes<B>(lo, c)) + popc64(match_planes<B>(hi, c)));
+        uint32_t excl, total;
+        Scan(tmp).ExclusiveSum(cnt, excl, total);
+        __syncthreads();
+        if (blk < n_records) reinterpret_cast<uint16_t *>(rec + 16 * B)[c - 1] = (uint16_t)excl;
+        if (threadIdx.x == 0) sb_tot[(uint64_t)blockIdx.x * noff + (c - 1)] = total;
+    }
+    if (blk < n_records) {
+#pragma unroll
+        for (int p = 0; p < B; ++p)
+            reinterpret_cast<ulonglong2 *>(rec)[p] = make_ulonglong2(lo[p], hi[p]);
+    }
+}
+
+// in place: sbc[sb][c-1] = count[c] + sum_{sb' < sb} tot[sb'][c-1]   (condensed.rs:104-116 + lib.rs:273-275)
+__global__ void k_sb_scan(uint64_t *__restrict__ sbc, uint64_t n_superblocks, uint32_t noff,
+                          const uint64_t *__restrict__ count) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;  // symbol c+1
+    if (c >= noff) return;
+    uint64_t acc = count[c + 1];
+    for (uint64_t sb = 0; sb < n_superblocks; ++sb) {
+        const uint64_t t = sbc[sb * noff + c];
+        sbc[sb * noff + c] = acc;
+        acc += t;
+    }
+}
+
+// lookup_table.rs:225-258: entry i of level d = extend(entry i / ns of level d-1, symbol i % ns + 1)
+template <class L>
+__global__ void __launch_bounds__(256)
+k_lut_fill(const __grid_constant__ DevIndex ix, void *__restrict__ lookup, uint32_t d) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ix.lut_pow[d]) return;
+    uint64_t s, e;
+    lut_load(ix, ix.lut_level_off[d - 1] + i / ix.ns, s, e);
+    const uint32_t c = (uint32_t)(i % ix.ns) + 1;
+    if (s != e) lf_pair<L>(ix, c, s, e);  // cursor.rs:40-51
+    const uint64_t entry = ix.lut_level_off[d] + i;
+    if (ix.wide)
+        reinterpret_cast<ulonglong2 *>(lookup)[entry] = make_ulonglong2(s, e);
+    else
+        reinterpret_cast<uint2 *>(lookup)[entry] = make_uint2((uint32_t)s, (uint32_t)e);
+}
+
+// condensed.rs:343-362 symbol_at over the reference's own plane array: [block][plane] u64
+__global__ void k_planes_to_bwt(const uint64_t *__restrict__ blocks, uint32_t nplanes, uint64_t n,
+                                uint8_t *__restrict__ bwt) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t *pl = blocks + (i >> 6) * nplanes;
+    uint32_t s = 0;
+    for (uint32_t p = 0; p < nplanes; ++p) s |= (uint32_t)((pl[p] >> (i & 63)) & 1u) << p;
+    bwt[i] = (uint8_t)s;
+}
+
+// symbol_at over the device records: the dense BWT back (export utility)
+template <class L>
+__global__ void __launch_bounds__(256)
+k_records_to_bwt(const __grid_constant__ DevIndex ix, uint64_t begin, uint64_t end, uint8_t *__restrict__ out) {
+    const uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= end) return;
+    typename L::Planes pl = L::load_planes(ix, i);
+    out[i - begin] = (uint8_t)L::symbol_at(pl, i);
+}
+
+__global__ void k_widen_u32(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void k_narrow_u64(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)in[i];
+}
+
+// ---- random-gather ceiling ----------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finalizer
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+// every thread issues `rounds` x 2 loads of REC bytes at pseudo-random record indices
+// (the table holds record_mask + 1 = a power of two records).
+// chained = 0: addresses depend only on a counter (pure bandwidth / MLP ceiling);
+// chained = 1: the next pair of addresses depends on the loaded data, like an LF step.
+template <int REC>
+__global__ void __launch_bounds__(256)
+k_gather(const uint8_t *__restrict__ table, uint64_t record_mask, uint32_t rounds, int chained,
+         uint64_t *__restrict__ sink) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t a = mix64(tid * 2 + 1), b = mix64(tid * 2 + 2), acc = 0;
+    for (uint32_t r = 0; r < rounds; ++r) {
+        const uint8_t *pa = table + (a & record_mask) * REC, *pb = table + (b & record_mask) * REC;
+        uint64_t wa[4], wb[4];
+        if (REC == 32) {
+            ldg256_na(pa, wa);
+            ldg256_na(pb, wb);
+        } else {
+            uint64_t t0[4], t1[4];
+            ldg256_na(pa, wa);
+            ldg256_na(pa + 32, t0);
+            ldg256_na(pb, wb);
+            ldg256_na(pb + 32, t1);
+            wa[0] ^= t0[0] ^ t0[3];
+            wb[0] ^= t1[0] ^ t1[3];
+            if (REC == 128) {
+                ldg256_na(pa + 64, t0);
+                ldg256_na(pa + 96, t1);
+                wa[1] ^= t0[1] ^ t1[2];
+                ldg256_na(pb + 64, t0);
+                ldg256_na(pb + 96, t1);
+                wb[1] ^= t0[1] ^ t1[2];
+            }
+        }
+        const uint64_t xa = wa[0] ^ wa[1] ^ wa[2] ^ wa[3], xb = wb[0] ^ wb[1] ^ wb[2] ^ wb[3];
+        acc += xa + xb;
+        if (chained) {
+            a = mix64(a ^ xa);
+            b = mix64(b ^ xb);
+        } else {
+            a = mix64(a);
+            b = mix64(b);
+        }
+    }
+    if (acc == 0x1234567812345678ull) sink[0] = acc;  // keep the loads alive
+}
+
+}  // namespace gdx
+#endif

@@ -1,0 +1,181 @@
+"""CPU tests of the host-side logic of the product: the C ABI loads and exports every declared
+symbol, host construction (SA-IS) equals the oracle's suffix array, and the device rank-record
+arithmetic (rank_core.h, emulated on the host) equals the oracle's rank for every symbol/position.
+No GPU compute is called here."""
+import ctypes as C
+import os
+import random
+import re
+import subprocess
+
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SETTINGS = dict(deadline=None, suppress_health_check=list(HealthCheck))
+
+
+@pytest.fixture(scope="module")
+def gdx():
+    import genedex_b200
+    return genedex_b200
+
+
+def test_library_exports_every_declared_symbol(gdx):
+    header = open(os.path.join(ROOT, "include", "genedex_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # drop comments
+    declared = set(re.findall(r"\b(gdx_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    lib = C.CDLL(gdx._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert declared == set(gdx._lib.PROTOTYPES), "Python prototypes and header disagree"
+    assert lib.gdx_abi_version() == 1
+    assert lib.gdx_index_header_bytes() > 256
+
+
+def test_struct_sizes_match_the_header(gdx, tmp_path):
+    # compile a tiny C program against the header and compare sizeof() with the ctypes mirrors
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "genedex_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(gdx_alphabet),sizeof(gdx_config),sizeof(gdx_hit),sizeof(gdx_queries),sizeof(gdx_parts),'
+                   'sizeof(gdx_index_info),sizeof(gdx_stats));return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    L = gdx._lib
+    want = [C.sizeof(t) for t in (L.gdx_alphabet, L.gdx_config, L.gdx_hit, L.gdx_queries, L.gdx_parts,
+                                  L.gdx_index_info, L.gdx_stats)]
+    assert got == want
+
+
+def test_no_cpu_fallback(gdx):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gdx.GenedexError) as e:
+        gdx.FmIndexConfig("i32").construct_index([b"ACGT"], gdx.alphabet.ascii_dna())
+    assert "no CPU fallback" in str(e.value)
+
+
+def _host_sa(gdx, dense, sigma):
+    lib = gdx._lib.load()
+    t = np.ascontiguousarray(dense, dtype=np.uint8)
+    out = np.zeros(max(t.size, 1), dtype=np.uint64)
+    rc = lib.gdx_suffix_array(t.ctypes.data, t.size, sigma, gdx._lib.GDX_CONSTRUCT_HOST, -1, out.ctypes.data)
+    assert rc == 0
+    return out[:t.size].tolist()
+
+
+@settings(max_examples=150, **SETTINGS)
+@given(data=st.data())
+def test_host_sais_equals_naive_and_oracle(gdx, data):
+    kind = data.draw(st.sampled_from(["random", "runs", "periodic", "wide"]))
+    if kind == "random":
+        sigma = 6
+        dense = data.draw(st.lists(st.integers(0, 5), min_size=1, max_size=400))
+    elif kind == "runs":
+        sigma = 6
+        parts = data.draw(st.lists(st.tuples(st.integers(0, 5), st.integers(1, 90)), min_size=1, max_size=10))
+        dense = [c for c, k in parts for _ in range(k)]
+    elif kind == "periodic":
+        sigma = 4
+        unit = data.draw(st.lists(st.integers(1, 3), min_size=1, max_size=5))
+        dense = unit * data.draw(st.integers(1, 80)) + [0]
+    else:
+        sigma = 256
+        dense = data.draw(st.lists(st.integers(0, 255), min_size=1, max_size=300))
+    assert _host_sa(gdx, dense, sigma) == O.naive_suffix_array(dense)
+
+
+def test_host_sais_medium_equals_oracle(gdx):
+    rng = np.random.default_rng(5)
+    text = rng.integers(1, 5, 200_000, dtype=np.uint8)
+    text[1000:9000] = 5           # a long run of N
+    text[50_000] = 0
+    text[50_001] = 0              # an empty text in the middle
+    text[-1] = 0
+    io = np.frombuffer(b"\x00ACGTN", dtype=np.uint8)[text]
+    # split at sentinels to rebuild the same dense text through the oracle
+    texts = bytes(io.tobytes()).split(b"\x00")[:-1]
+    idx = O.OracleIndex.build(texts, O.ALPHABETS["ascii_dna_with_n"](), "u32", sampling_rate=1)
+    assert np.array_equal(idx.dense_text(), text)
+    assert _host_sa(gdx, text, 6) == idx.suffix_array().tolist()
+
+
+# ---- device record arithmetic, emulated on the host ---------------------------------------------------
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    out = tmp_path_factory.mktemp("emul") / "libemul.so"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out),
+                           os.path.join(ROOT, "tests", "host_emul", "emul.cpp")])
+    lib = C.CDLL(str(out))
+    lib.emul_build.restype = C.c_void_p
+    lib.emul_build.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.emul_free.argtypes = [C.c_void_p]
+    lib.emul_lf.restype = C.c_uint64
+    lib.emul_lf.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
+    lib.emul_symbol_at.restype = C.c_uint32
+    lib.emul_symbol_at.argtypes = [C.c_void_p, C.c_uint64]
+    lib.emul_layout.argtypes = [C.c_void_p, C.c_void_p]
+    return lib
+
+
+def _check_records(emul, bwt, sigma, positions=None):
+    bwt = np.ascontiguousarray(bwt, dtype=np.uint8)
+    n = bwt.size
+    keep = bwt if n else np.zeros(1, np.uint8)
+    freq = np.bincount(bwt, minlength=sigma + 1).astype(np.uint64)
+    count = np.zeros(sigma + 1, dtype=np.uint64)
+    count[1:] = np.cumsum(freq[:sigma])
+    border_rows = np.flatnonzero(bwt == 0).astype(np.uint64)
+    br = border_rows if border_rows.size else np.zeros(1, np.uint64)
+    h = emul.emul_build(keep.ctypes.data, n, sigma, count.ctypes.data, br.ctypes.data, border_rows.size)
+    try:
+        r = O.OracleRank(bwt, sigma, "u32")
+        pos = range(n + 1) if positions is None else positions
+        for i in pos:
+            if i < n:
+                assert emul.emul_symbol_at(h, i) == bwt[i]
+            for c in range(1, sigma):
+                assert emul.emul_lf(h, c, i) == int(count[c]) + r.rank(c, i), (sigma, c, i)
+        lay = (C.c_uint32 * 6)()
+        emul.emul_layout(h, lay)
+        return list(lay)
+    finally:
+        emul.emul_free(h)
+
+
+@settings(max_examples=40, **SETTINGS)
+@given(data=st.data())
+def test_record_arithmetic_equals_oracle_rank(emul, data):
+    sigma = data.draw(st.sampled_from([2, 3, 4, 5, 6, 7, 8, 9, 16, 17, 21, 27, 33, 64, 100, 129, 256]))
+    n = data.draw(st.sampled_from([0, 1, 63, 64, 65, 127, 128, 129, 500]))
+    rng = np.random.default_rng(data.draw(st.integers(0, 2 ** 32)))
+    bwt = rng.integers(0, sigma, n, dtype=np.uint16).astype(np.uint8) if sigma <= 256 else None
+    lay = _check_records(emul, bwt, sigma)
+    if sigma <= 6:
+        assert lay[0] == 0 and lay[3] == 32 and lay[4] == 6
+        assert lay[5] == (5 if sigma == 6 else 0)
+    else:
+        assert lay[0] == 1 and lay[4] == 7 and lay[3] % 32 == 0
+    if sigma == 21:
+        assert lay[3] == 128  # protein: one 128-byte line per 128 positions
+
+
+def test_record_arithmetic_across_superblocks(emul):
+    rng = np.random.default_rng(3)
+    for sigma in (6, 21):
+        n = 65536 * 2 + 777
+        bwt = rng.integers(0, sigma, n).astype(np.uint8)
+        bwt[60000:70000] = sigma - 1  # a long run over a superblock border
+        pos = sorted(set(rng.integers(0, n + 1, 600).tolist() +
+                         [0, 63, 64, 65535, 65536, 65537, 131071, 131072, n - 1, n]))
+        _check_records(emul, bwt, sigma, pos)
+    # u16 block offsets must survive a superblock made of one symbol (text_with_rank_support.rs:85-89)
+    _check_records(emul, np.full(65536, 1, np.uint8), 2, [0, 1, 64, 65535, 65536])
+    _check_records(emul, np.full(65536 + 64, 3, np.uint8), 6, [0, 65535, 65536, 65599, 65600])
