@@ -35,8 +35,12 @@ def random_texts(rng: random.Random, oa, ntexts, max_len, with_unsearchable=True
     return [bytes(rng.choice(syms) for _ in range(rng.randrange(max_len + 1))) for _ in range(ntexts)]
 
 
-def random_queries(rng: random.Random, oa, texts, n_sampled, n_random, max_len):
+def random_queries(rng: random.Random, oa, texts, n_sampled, n_random, max_len, searchable_only=False):
+    """Windows sampled from the texts plus random strings over the searchable symbols.  With a lookup
+    table (depth > 0) a query must not contain a valid-but-unsearchable symbol such as N: the reference
+    mis-indexes its table there (lookup_table.rs:154-157), so such windows are dropped on request."""
     syms = searchable_io_symbols(oa)
+    ok = set(syms) | {c for c in range(256) if oa.io_to_dense[c] and oa.io_to_dense[c] <= oa.num_searchable}
     qs = []
     nonempty = [t for t in texts if t]
     for _ in range(n_sampled):
@@ -44,7 +48,10 @@ def random_queries(rng: random.Random, oa, texts, n_sampled, n_random, max_len):
             break
         t = rng.choice(nonempty)
         p = rng.randrange(len(t))
-        qs.append(t[p:p + rng.randrange(max_len + 1)])
+        q = t[p:p + rng.randrange(max_len + 1)]
+        if searchable_only and any(c not in ok for c in q):
+            continue
+        qs.append(q)
     for _ in range(n_random):
         qs.append(bytes(rng.choice(syms) for _ in range(rng.randrange(max_len + 1))))
     rng.shuffle(qs)

@@ -2,7 +2,10 @@
 over a table far larger than L2.  Writes one JSON line per configuration."""
 import ctypes as C
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import genedex_b200 as gdx
 
