@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -56,6 +57,21 @@ gdx_status fail(gdx_status st, const char *fmt, ...) {
 uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
+// Random 32 B record reads: ask the L2 to fetch single sectors from DRAM instead of sector pairs
+// (cudaLimitMaxL2FetchGranularity is a per-context hint).  GDX_L2_FETCH_GRANULARITY=0 leaves the
+// driver default, 32/64/128 sets it.  Applied once per device, with that device current.
+void apply_l2_fetch_granularity(int dev) {
+    static std::mutex mu;
+    static bool done[64] = {};
+    if (dev < 0 || dev >= 64) return;
+    std::lock_guard<std::mutex> lk(mu);
+    if (done[dev]) return;
+    done[dev] = true;
+    const char *env = getenv("GDX_L2_FETCH_GRANULARITY");
+    const int want = env ? atoi(env) : 32;
+    if (want > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
+}
+
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
@@ -64,6 +80,7 @@ struct DeviceGuard {
         if (dev >= 0 && dev != prev) {
             if (cudaSetDevice(dev) != cudaSuccess) return;
         }
+        apply_l2_fetch_granularity(dev >= 0 ? dev : prev);
         ok = true;
     }
     ~DeviceGuard() {

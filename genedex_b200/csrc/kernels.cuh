@@ -146,7 +146,8 @@ __device__ __forceinline__ uint64_t sbc_load(const DevIndex &ix, uint64_t i, uin
     return __ldg(ix.sbc + (i >> kSuperblockLog2) * ix.noff + (c - 1));
 }
 
-// LF(c, s), LF(c, e) with all four loads issued before the first use (lib.rs:273-275)
+// LF(c, s), LF(c, e) with all loads issued before the first use (lib.rs:273-275).  Once the interval
+// is narrower than a block both borders usually live in the same record: it is fetched once.
 template <class L>
 __device__ __forceinline__ void lf_pair(const DevIndex &ix, uint32_t c, uint64_t &s, uint64_t &e) {
     if (c > ix.noff) {  // derived symbol: rare and divergent by nature
@@ -154,9 +155,17 @@ __device__ __forceinline__ void lf_pair(const DevIndex &ix, uint32_t c, uint64_t
         e = L::lf_derived(ix, e);
         return;
     }
+    const bool same_block = (s >> L::kLog2P) == (e >> L::kLog2P);
     typename L::Rec rs = L::load(ix, s, c);
+    const uint64_t bs = sbc_load(ix, s, c);
+    if (same_block) {
+        const uint64_t ns = bs + L::local_rank(rs, c, s);
+        e = bs + L::local_rank(rs, c, e);
+        s = ns;
+        return;
+    }
     typename L::Rec re = L::load(ix, e, c);
-    uint64_t bs = sbc_load(ix, s, c), be = sbc_load(ix, e, c);
+    const uint64_t be = sbc_load(ix, e, c);
     s = bs + L::local_rank(rs, c, s);
     e = be + L::local_rank(re, c, e);
 }
