@@ -106,13 +106,6 @@ def sample_queries_on_device(text, nq, m, seed, device):
     return out.reshape(-1), starts_out
 
 
-class _CudaBytes:
-    """Zero-copy torch view of a raw device allocation (for the NCCL broadcast of the index image)."""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -262,7 +255,6 @@ def run_ours(args, rank, world, local_rank):
     # index: built on rank 0 (device construction), one NCCL broadcast of the image to the replicas
     t0 = time.perf_counter()
     alphabet = gdx.alphabet.ascii_dna_with_n()
-    keepalive = None
     if rank == 0:
         cfg = (gdx.FmIndexConfig("u32").suffix_array_sampling_rate(args.sampling_rate)
                .lookup_table_depth(args.lookup_depth).device(local_rank)
@@ -271,34 +263,11 @@ def run_ours(args, rank, world, local_rank):
         del text_host
     t_build = time.perf_counter() - t0
     t_bcast = 0.0
-    if world > 1:
+    if world > 1:  # one NCCL broadcast of the device image GPU0 -> peers (genedex_b200/replicate.py)
+        from genedex_b200.replicate import replicate_index
         t0 = time.perf_counter()
-        hbytes = int(lib.gdx_index_header_bytes())
-        hdr = torch.zeros(hbytes, dtype=torch.uint8, device=dev)
-        size = torch.zeros(1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            hbuf = (C.c_uint8 * hbytes)()
-            img, nbytes = C.c_void_p(), C.c_uint64()
-            assert lib.gdx_index_export(pidx.handle, hbuf, C.byref(img), C.byref(nbytes)) == 0
-            hdr.copy_(torch.frombuffer(bytearray(hbuf), dtype=torch.uint8))
-            size[0] = nbytes.value
-        dist.broadcast(hdr, 0)
-        dist.broadcast(size, 0)
-        nbytes_v = int(size.item())
-        if rank == 0:
-            image = torch.as_tensor(_CudaBytes(img.value, nbytes_v), device=dev)
-        else:
-            image = torch.empty(nbytes_v, dtype=torch.uint8, device=dev)
-        step = 1 << 30
-        for b in range(0, nbytes_v, step):  # the image replica goes GPU0 -> peers over NVLink
-            dist.broadcast(image[b:min(nbytes_v, b + step)], 0)
+        pidx = replicate_index(pidx if rank == 0 else None, alphabet, dev, rank)
         torch.cuda.synchronize()
-        if rank != 0:
-            hb = (C.c_uint8 * hbytes).from_buffer_copy(hdr.cpu().numpy().tobytes())
-            h = C.c_void_p()
-            assert lib.gdx_index_adopt_image(hb, image.data_ptr(), local_rank, 0, C.byref(h)) == 0
-            pidx = gdx.FmIndex(h, alphabet, keepalive=image)
-        keepalive = image
         t_bcast = time.perf_counter() - t0
     info = pidx.info()
 
@@ -436,7 +405,6 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "locate": locate,
     }
-    del keepalive
     print(json.dumps(out))
 
 

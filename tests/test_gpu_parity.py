@@ -425,3 +425,11 @@ def test_config_c1_parity(gdx):
             for i in list(range(0, nq, 50_021)):
                 for t, p in phits[int(poff[i]):int(poff[i + 1])]:
                     assert raw[int(p):int(p) + m].upper() == q[i * m:(i + 1) * m].tobytes().upper()
+
+
+def test_cpp_mirror_kats(gdx, tmp_path):
+    import subprocess
+
+    from test_host_logic import build_cpp_api_test
+    out = subprocess.run([build_cpp_api_test(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp api ok" in out.stdout, out.stdout + out.stderr

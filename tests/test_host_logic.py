@@ -179,3 +179,18 @@ def test_record_arithmetic_across_superblocks(emul):
     # u16 block offsets must survive a superblock made of one symbol (text_with_rank_support.rs:85-89)
     _check_records(emul, np.full(65536, 1, np.uint8), 2, [0, 1, 64, 65535, 65536])
     _check_records(emul, np.full(65536 + 64, 3, np.uint8), 6, [0, 65535, 65536, 65599, 65600])
+
+
+def build_cpp_api_test(out_dir):
+    exe = os.path.join(str(out_dir), "test_api")
+    libdir = os.path.join(ROOT, "genedex_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_api.cpp"), "-L", libdir, "-lgenedex_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    # include/genedex_b200.hpp mirrors the crate's interface for C++ hosts; it must compile against
+    # the header and link against the library (running it needs a GPU: tests/test_gpu_parity.py)
+    assert os.path.exists(build_cpp_api_test(tmp_path))
