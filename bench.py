@@ -329,13 +329,16 @@ def run_ours(args, rank, world, local_rank):
     # ---- locate (configs[2] side measurement): LF-walk + text-id mapping through the C ABI -----------
     locate = None
     if not args.no_locate:
+        hit_off = torch.empty(nq + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
         for _ in range(2):
-            hit_off, hits = pidx.locate_many_packed(q_np, None, m, nq)
+            _, hits, release = pidx.locate_many_view(q_np, None, m, nq, hit_offsets=hit_off)
+            release()
         barrier()
         t0 = time.perf_counter()
-        reps = max(1, min(args.steps, 3))
+        reps = max(1, min(args.steps, 5))
         for _ in range(reps):
-            hit_off, hits = pidx.locate_many_packed(q_np, None, m, nq)
+            _, hits, release = pidx.locate_many_view(q_np, None, m, nq, hit_offsets=hit_off)
+            release()  # the pooled pinned buffer stays valid until the next locate call
         barrier()
         loc_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / reps)
         lst = pidx.stats()

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/genedex_b200.h"
@@ -116,11 +117,14 @@ struct DBuf {
 };
 
 constexpr int kSlots = 3;
-constexpr uint64_t kChunkBytes = 24ull << 20;  // query bytes per pipeline chunk
+const uint64_t kChunkBytes = [] {  // query bytes per pipeline chunk
+    const char *e = getenv("GDX_CHUNK_MB");
+    return (uint64_t)(e && atoi(e) > 0 ? atoi(e) : 24) << 20;
+}();
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    DBuf bytes, offsets, out_a, out_b;
+    DBuf bytes, offsets, out_a, out_b, sort;
     std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
     size_t ev_used = 0;
 };
@@ -151,6 +155,7 @@ struct Workspace {
             s.offsets.release();
             s.out_a.release();
             s.out_b.release();
+            s.sort.release();
             for (auto e : s.ev) cudaEventDestroy(e);
         }
         if (small.h) cudaFreeHost(small.h);
@@ -798,11 +803,61 @@ namespace {
 
 template <class L>
 void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint64_t *b, int mode,
-                   uint64_t qbase, uint64_t *err, unsigned long long *steps, int single_path,
+                   uint64_t qbase, uint64_t *err, unsigned long long *steps, const uint32_t *perm,
                    cudaStream_t stream) {
-    (void)single_path;
     if (dq.nq == 0) return;
-    k_search<L><<<(unsigned)div_up(dq.nq, 256), 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps);
+    k_search<L><<<(unsigned)div_up(dq.nq, 256), 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+}
+
+// ---- suffix sort of a query batch (locality of the first search steps, see k_query_keys) -------------
+constexpr uint64_t kSortMinQueries = 1ull << 15;
+
+bool sort_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GDX_SORT_QUERIES");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
+struct SortPlan {
+    uint32_t key_bits = 0, key_syms = 0;
+    size_t tmp_bytes = 0;
+    uint64_t total_bytes = 0;  // keys a/b + idx a/b + cub temp, 256 B aligned pieces
+    bool use = false;
+};
+
+SortPlan plan_sort(const gdx_index *idx, uint64_t nq) {
+    SortPlan p;
+    if (!sort_enabled() || nq < kSortMinQueries || nq >= 0xffffffffull) return p;
+    uint32_t bits = 1;
+    while ((1u << bits) < idx->h.ns) ++bits;
+    p.key_bits = bits;
+    p.key_syms = std::min<uint32_t>(32 / bits, 16);
+    cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
+    if (cub::DeviceRadixSort::SortPairs(nullptr, p.tmp_bytes, dk, dv, (int64_t)nq, 0, (int)(p.key_bits * p.key_syms)) !=
+        cudaSuccess)
+        return p;
+    p.total_bytes = 4 * align_up(nq * 4, 256) + align_up(p.tmp_bytes, 256);
+    p.use = true;
+    return p;
+}
+
+// scratch: total_bytes of device memory; returns the permutation (sorted query indices) in *perm
+gdx_status sort_queries(const gdx_index *idx, const DevQueries &dq, const SortPlan &p, void *scratch,
+                        cudaStream_t stream, const uint32_t **perm) {
+    uint8_t *base = (uint8_t *)scratch;
+    const uint64_t piece = align_up(dq.nq * 4, 256);
+    uint32_t *ka = (uint32_t *)base, *kb = (uint32_t *)(base + piece), *ia = (uint32_t *)(base + 2 * piece),
+             *ib = (uint32_t *)(base + 3 * piece);
+    void *tmp = base + 4 * piece;
+    k_query_keys<<<(unsigned)div_up(dq.nq, 256), 256, 0, stream>>>(idx->dev, dq, p.key_bits, p.key_syms, ka, ia);
+    CUDA_TRY(cudaGetLastError());
+    cub::DoubleBuffer<uint32_t> dk(ka, kb), dv(ia, ib);
+    size_t tb = p.tmp_bytes;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, dk, dv, (int64_t)dq.nq, 0, (int)(p.key_bits * p.key_syms), stream));
+    *perm = dv.Current();
+    return GDX_OK;
 }
 
 gdx_status check_queries(const gdx_queries *q) {
@@ -844,8 +899,10 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         const uint64_t byte0 = query_bytes_end(qs, q0), byte1 = query_bytes_end(qs, q1);
         Slot &sl = ws->slot[k % kSlots];
         // growing a slot buffer frees the old one: only safe once the slot's stream has drained
+        const SortPlan sp = plan_sort(idx, cq);
         if (sl.bytes.cap < byte1 - byte0 + 16 || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
-            (!dev_a && (sl.out_a.cap < cq * 8 || (mode == 0 && sl.out_b.cap < cq * 8))))
+            (!dev_a && (sl.out_a.cap < cq * 8 || (mode == 0 && sl.out_b.cap < cq * 8))) ||
+            (sp.use && sl.sort.cap < sp.total_bytes))
             CUDA_TRY(cudaStreamSynchronize(sl.stream));
         CUDA_TRY(sl.bytes.reserve(byte1 - byte0 + 16));
         if (byte1 > byte0)
@@ -879,8 +936,14 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         }
         cudaEvent_t e0 = ws->next_event(sl), e1 = ws->next_event(sl);
         CUDA_TRY(cudaEventRecord(e0, sl.stream));
+        const uint32_t *perm = nullptr;
+        if (sp.use) {
+            CUDA_TRY(sl.sort.reserve(sp.total_bytes));
+            GDX_TRY(sort_queries(idx, dq, sp, sl.sort.p, sl.stream, &perm));
+            t_stats.kernel_launches += 2;
+        }
         gdx_status st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-            launch_search<decltype(L)>(idx, dq, a, b, mode, q0, ws->small.d + (k % kSlots), d_steps, 0, sl.stream);
+            launch_search<decltype(L)>(idx, dq, a, b, mode, q0, ws->small.d + (k % kSlots), d_steps, perm, sl.stream);
             return GDX_OK;
         });
         GDX_TRY(st);
@@ -1181,11 +1244,20 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
     dq.fixed_len = dq_in->fixed_len;
     dq.nq = dq_in->nq;
     dq.base = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SortPlan sp = plan_sort(idx, dq.nq);
+    const uint32_t *perm = nullptr;
+    void *scratch = nullptr;
+    if (sp.use) {  // stream-ordered scratch from the device's memory pool
+        CUDA_TRY(cudaMallocAsync(&scratch, sp.total_bytes, st));
+        GDX_TRY(sort_queries(idx, dq, sp, scratch, st, &perm));
+    }
     GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-        launch_search<decltype(L)>(idx, dq, a, b, mode, 0, d_error, nullptr, 0, (cudaStream_t)stream);
+        launch_search<decltype(L)>(idx, dq, a, b, mode, 0, d_error, nullptr, perm, st);
         return GDX_OK;
     }));
     CUDA_TRY(cudaGetLastError());
+    if (scratch) CUDA_TRY(cudaFreeAsync(scratch, st));
     return GDX_OK;
 }
 

@@ -193,23 +193,64 @@ __device__ __forceinline__ void report_error(uint64_t *err, uint64_t q) {
     if (err) atomicMin(reinterpret_cast<unsigned long long *>(err), (unsigned long long)q);
 }
 
+// ---- sort key of a query: its last symbols, last symbol most significant ---------------------------
+// Backward search consumes a query right to left, so queries that share a suffix walk the same
+// records for their first steps.  Sorting the batch by suffix makes neighbouring threads/CTAs walk
+// them at the same time: the top of the search trie is then served by L2 instead of DRAM (the
+// north-star "query batches are sorted by lookup-table prefix so they share L2").  The sort only
+// permutes the order in which threads pick queries; every result still goes to the query's own slot.
+__global__ void __launch_bounds__(256)
+k_query_keys(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_t key_bits, uint32_t key_syms,
+             uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= qs.nq) return;
+    uint64_t begin, len;
+    if (qs.offsets) {
+        begin = __ldg(qs.offsets + q) - qs.base;
+        len = __ldg(qs.offsets + q + 1) - qs.base - begin;
+    } else {
+        begin = q * qs.fixed_len;
+        len = qs.fixed_len;
+    }
+    const uint8_t *p = qs.bytes + begin;
+    uint32_t key = 0;
+    for (uint32_t j = 0; j < key_syms; ++j) {
+        uint32_t code = 0;
+        if (j < len) {
+            const uint32_t c = ix.io_to_dense[__ldg(p + len - 1 - j)];
+            code = (c >= 1 && c <= ix.ns) ? c - 1 : 0;
+        }
+        key = (key << key_bits) | code;
+    }
+    keys[q] = key;
+    idx[q] = (uint32_t)q;
+}
+
 // ---- K1 + K2: seed + backward search ----------------------------------------------------------------
 // mode 0: out_a = starts, out_b = ends; mode 1: out_a = counts.
 // Follows the batched path of the reference: a symbol is translated only when the search reaches
 // it (batch_computed_cursors.rs:84-87,106-113), queries leave when all symbols are consumed or the
 // interval is empty (:131-158), results are written to the query's own slot (= input order, :160-172).
+// perm (optional): thread t searches query perm[t] (suffix-sorted order, see k_query_keys).
+// The last kQueryStage bytes of the query are staged once into a private shared-memory slot with
+// aligned word loads; the per-step symbol fetch is then an LDS, not a global byte load.
+constexpr uint32_t kQueryStage = 64;                       // bytes staged per query
+constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, covers any misalignment
+
 template <class L>
 __global__ void __launch_bounds__(256)
 k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__restrict__ out_a,
          uint64_t *__restrict__ out_b, int mode, uint64_t q_index_base, uint64_t *err,
-         unsigned long long *stat_steps) {
+         unsigned long long *stat_steps, const uint32_t *__restrict__ perm) {
     __shared__ uint8_t tab[256];
+    __shared__ uint32_t stage[256 * kQuerySlotWords];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = ix.io_to_dense[i];
     __syncthreads();
 
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
-    if (q < qs.nq) {
+    if (t < qs.nq) {
+        const uint64_t q = perm ? (uint64_t)__ldg(perm + t) : t;
         uint64_t begin, len;
         if (qs.offsets) {
             begin = __ldg(qs.offsets + q) - qs.base;
@@ -219,6 +260,22 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             len = qs.fixed_len;
         }
         const uint8_t *p = qs.bytes + begin;
+
+        // stage bytes [len - tail, len) of the query: aligned words covering them
+        const uint32_t tail = len < kQueryStage ? (uint32_t)len : kQueryStage;
+        const uint64_t tail_begin = len - tail;  // query position of the first staged byte
+        uint32_t *slot = stage + threadIdx.x * kQuerySlotWords;
+        const uint8_t *first = p + tail_begin;
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 3u);
+        if (tail) {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(first - mis);
+            const uint32_t nw = (mis + tail + 3u) >> 2;
+#pragma unroll 1
+            for (uint32_t k = 0; k < nw; ++k) slot[k] = __ldg(w + k);
+        }
+        const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(slot) + mis;
+        // dense symbol of query position i
+#define GDX_SYMBOL_AT(i) tab[(i) >= tail_begin ? sbytes[(i) - tail_begin] : __ldg(p + (i))]
         bool bad = false;
 
         // K1: lookup_table.rs:68-161 -- first suffix symbol is the least significant digit
@@ -226,7 +283,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         uint64_t pos = len - depth;
         uint64_t li = 0;
         for (uint64_t j = 0; j < depth; ++j) {
-            uint32_t c = tab[__ldg(p + pos + j)];
+            const uint32_t c = GDX_SYMBOL_AT(pos + j);
             // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
             // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
             if (c == 0 || c > ix.ns) bad = true;
@@ -237,7 +294,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
 
         // K2: batch_computed_cursors.rs:62-70
         while (!bad && pos > 0 && s != e) {
-            uint32_t c = tab[__ldg(p + pos - 1)];
+            const uint32_t c = GDX_SYMBOL_AT(pos - 1);
             if (c == 0) {
                 bad = true;
                 break;
@@ -256,6 +313,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         } else {
             out_a[q] = e - s;
         }
+#undef GDX_SYMBOL_AT
     }
     if (stat_steps) {
         uint32_t tot = __reduce_add_sync(0xffffffffu, steps);

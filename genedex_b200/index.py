@@ -193,6 +193,24 @@ class FmIndex:
         _check(self._lib.gdx_locate_many(self._h, C.byref(q), hit_offsets.ctypes.data, C.byref(hp), C.byref(nh)))
         return hit_offsets, self._take_hits(hp, nh.value)
 
+    def locate_many_view(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
+                         nq: int | None = None, hit_offsets: np.ndarray | None = None):
+        """Zero-copy form of locate_many_packed: -> (hit_offsets, hits view on the library's pinned
+        buffer, release) -- call release() when done with the view (gdx_free_hits)."""
+        nq = (offsets.size - 1) if offsets is not None else nq
+        if hit_offsets is None:
+            hit_offsets = np.empty(nq + 1, dtype=np.uint64)
+        hp, nh = C.c_void_p(), C.c_uint64()
+        q = _queries_struct(data, offsets, fixed_len, nq)
+        _check(self._lib.gdx_locate_many(self._h, C.byref(q), hit_offsets.ctypes.data, C.byref(hp), C.byref(nh)))
+        n = nh.value
+        if n:
+            buf = (C.c_uint64 * (2 * n)).from_address(hp.value)
+            hits = np.frombuffer(buf, dtype=np.uint64).reshape(n, 2)
+        else:
+            hits = np.zeros((0, 2), dtype=np.uint64)
+        return hit_offsets, hits, (lambda: self._lib.gdx_free_hits(self._h, hp))
+
     def _take_hits(self, hp: C.c_void_p, n: int) -> np.ndarray:
         try:
             if n == 0:
