@@ -299,14 +299,15 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_region0 = time.time()
-    ev0.record()
-    for _ in range(args.steps):
+    evs[0].record()
+    for i in range(args.steps):
         step_device()
-    ev1.record()
+        evs[i + 1].record()
     barrier()
-    kernel_ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    kernel_ms = max_over_ranks(evs[0].elapsed_time(evs[-1]) / args.steps)
     assert int(d_err.item()) == -1
     counts_device_path = d_counts.cpu().numpy().astype(np.uint64)
 
@@ -394,7 +395,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": workload_name(args), "queries_per_gpu": nq,
                    "l2": "inputs larger than L2: 1.55 GB rank records accessed at random, 375 MB of queries",
                    "index_image_bytes": int(info.image_bytes), "rank_record_bytes": R,
-                   "lf_steps_per_step": steps_exec, "setup_s": {"data": round(t_data, 2), "index_build": round(t_build, 2),
+                   "lf_steps_per_step": steps_exec, "step_ms_min_median_max": [round(min(step_ms), 3),
+                                                                            round(statistics.median(step_ms), 3),
+                                                                            round(max(step_ms), 3)],
+                   "launches_per_step": "k_query_keys + cub radix sort (suffix order) + k_search", "setup_s": {"data": round(t_data, 2), "index_build": round(t_build, 2),
                                                                  "replicate": round(t_bcast, 2)}},
         "clocks": clock_info,
         "e2e": {"value": world * nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * m,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -117,10 +118,17 @@ struct DBuf {
 };
 
 constexpr int kSlots = 3;
-const uint64_t kChunkBytes = [] {  // query bytes per pipeline chunk
-    const char *e = getenv("GDX_CHUNK_MB");
-    return (uint64_t)(e && atoi(e) > 0 ? atoi(e) : 24) << 20;
-}();
+// Pipeline chunking: the byte budget of successive chunks doubles from kChunkFirst to kChunkMax
+// (fast pipeline fill, then few large launches: less launch overhead and deeper shared suffixes for the
+// per-chunk query sort) and the batch ends with a chunk of about kChunkTail (short drain).
+uint64_t env_mb(const char *name, uint64_t dflt) {
+    const char *e = getenv(name);
+    return (uint64_t)(e && atoi(e) > 0 ? atoi(e) : dflt) << 20;
+}
+const uint64_t kChunkFirst = env_mb("GDX_CHUNK_FIRST_MB", 8);
+const uint64_t kChunkMax = env_mb("GDX_CHUNK_MAX_MB", 64);
+const uint64_t kChunkTail = env_mb("GDX_CHUNK_TAIL_MB", 8);
+constexpr uint64_t kChunkMaxQueries = 64ull << 20;
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -879,22 +887,34 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     CUDA_TRY(cudaMemset(ws->small.d, 0xff, 4 * sizeof(uint64_t)));
     CUDA_TRY(cudaMemset(ws->small.d + 4, 0, 12 * sizeof(uint64_t)));
     unsigned long long *d_steps = reinterpret_cast<unsigned long long *>(ws->small.d + 4);
-    const uint64_t base0 = query_bytes_end(qs, 0);
+    static const bool trace = getenv("GDX_TRACE") && atoi(getenv("GDX_TRACE")) != 0;
+    struct TraceRow {
+        int k;
+        uint64_t nq, bytes;
+        cudaEvent_t h2d_begin, k_begin, k_end, d2h_end;
+    };
+    std::vector<TraceRow> trace_rows;
+    const auto t_host0 = std::chrono::steady_clock::now();
+    const uint64_t byte_end = query_bytes_end(qs, nq);
+    uint64_t budget = kChunkFirst;
     uint64_t q0 = 0;
     int k = 0;
     while (q0 < nq) {
-        // chunk [q0, q1): about kChunkBytes of query bytes, at least one query
+        // chunk [q0, q1): about `budget` query bytes, at least one query
+        const uint64_t remaining = byte_end - query_bytes_end(qs, q0);
+        uint64_t want = budget;
+        if (remaining <= budget) want = remaining > 2 * kChunkTail ? remaining - kChunkTail : remaining;
         uint64_t q1;
         if (qs->offsets) {
             const uint64_t *b = qs->offsets + q0 + 1, *e = qs->offsets + nq + 1;
-            const uint64_t *it = std::upper_bound(b, e, qs->offsets[q0] + kChunkBytes);
+            const uint64_t *it = std::upper_bound(b, e, qs->offsets[q0] + want);
             q1 = q0 + (uint64_t)(it - b);
             if (q1 == q0) q1 = q0 + 1;
-            q1 = std::min<uint64_t>(q1, std::min<uint64_t>(nq, q0 + (4ull << 20)));
         } else {
-            const uint64_t per = qs->fixed_len ? std::max<uint64_t>(1, kChunkBytes / qs->fixed_len) : (4ull << 20);
-            q1 = std::min<uint64_t>(nq, q0 + std::min<uint64_t>(per, 4ull << 20));
+            q1 = q0 + (qs->fixed_len ? std::max<uint64_t>(1, want / qs->fixed_len) : kChunkMaxQueries);
         }
+        q1 = std::min<uint64_t>(q1, std::min<uint64_t>(nq, q0 + kChunkMaxQueries));
+        budget = std::min<uint64_t>(budget * 2, kChunkMax);
         const uint64_t cq = q1 - q0;
         const uint64_t byte0 = query_bytes_end(qs, q0), byte1 = query_bytes_end(qs, q1);
         Slot &sl = ws->slot[k % kSlots];
@@ -905,6 +925,11 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             (sp.use && sl.sort.cap < sp.total_bytes))
             CUDA_TRY(cudaStreamSynchronize(sl.stream));
         CUDA_TRY(sl.bytes.reserve(byte1 - byte0 + 16));
+        cudaEvent_t ev_h2d = nullptr;
+        if (trace) {
+            cudaEventCreate(&ev_h2d);
+            cudaEventRecord(ev_h2d, sl.stream);
+        }
         if (byte1 > byte0)
             CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, qs->bytes + (byte0 - 0), byte1 - byte0, cudaMemcpyHostToDevice,
                                      sl.stream));
@@ -936,6 +961,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         }
         cudaEvent_t e0 = ws->next_event(sl), e1 = ws->next_event(sl);
         CUDA_TRY(cudaEventRecord(e0, sl.stream));
+        if (trace) trace_rows.push_back(TraceRow{k, cq, byte1 - byte0, ev_h2d, e0, e1, nullptr});
         const uint32_t *perm = nullptr;
         if (sp.use) {
             CUDA_TRY(sl.sort.reserve(sp.total_bytes));
@@ -953,12 +979,35 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             CUDA_TRY(cudaMemcpyAsync(out_a + q0, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
             if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
+        if (trace) {
+            cudaEventCreate(&trace_rows.back().d2h_end);
+            cudaEventRecord(trace_rows.back().d2h_end, sl.stream);
+        }
         t_stats.kernel_launches += 1;
         q0 = q1;
         ++k;
     }
-    (void)base0;
+    const double t_issue = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count() : 0;
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(ws->slot[s].stream));
+    if (trace && !trace_rows.empty()) {
+        const double t_sync = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+        fprintf(stderr, "[gdx trace] host: all chunks issued at %.3f ms, streams drained at %.3f ms\n", t_issue, t_sync);
+        cudaEvent_t base = trace_rows[0].h2d_begin;
+        for (auto &r : trace_rows) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaError_t te = cudaEventElapsedTime(&a, base, r.h2d_begin);
+            if (te != cudaSuccess) fprintf(stderr, "[gdx trace] elapsed: %s\n", cudaGetErrorString(te));
+            cudaEventElapsedTime(&b, base, r.k_begin);
+            cudaEventElapsedTime(&c, base, r.k_end);
+            cudaEventElapsedTime(&d, base, r.d2h_end);
+            fprintf(stderr, "[gdx trace] chunk %2d slot %d nq %8llu bytes %10llu | h2d %.3f..%.3f | kernels %.3f..%.3f | d2h ..%.3f\n",
+                    r.k, r.k % kSlots, (unsigned long long)r.nq, (unsigned long long)r.bytes, a, b, b, c, d);
+        }
+        for (auto &r : trace_rows) {
+            cudaEventDestroy(r.h2d_begin);
+            cudaEventDestroy(r.d2h_end);
+        }
+    }
     CUDA_TRY(cudaMemcpy(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     double ms = 0;
     for (int s = 0; s < kSlots; ++s)

@@ -42,6 +42,9 @@ def test_kat_multitext(gdx):  # tests/fmindex.rs:82-126
     assert set(idx.locate(b"gt")) == {H(0, 8), H(1, 2), H(1, 6), H(1, 10)}
     assert [set(h) for h in idx.locate_many([b"gg", b"gt"])] == [{H(0, 6), H(0, 7)},
                                                                  {H(0, 8), H(1, 2), H(1, 6), H(1, 10)}]
+    # "ta" does occur in the second text (positions 3 and 7); "tc" occurs nowhere
+    assert [len(h) for h in idx.locate_many([b"gg", b"gt", b"ta", b"tc"])] == [2, 4, 2, 0]
+    assert idx.count_many([b"gg", b"gt", b"ta", b"tc"]) == [2, 4, 2, 0]
     assert idx.num_texts() == 2 and idx.total_text_len() == 26
 
 
