@@ -53,7 +53,8 @@ class gdx_index_info(C.Structure):
                 ("sampling_rate", C.c_uint32), ("lookup_table_depth", C.c_uint32), ("rank_layout", C.c_uint32),
                 ("rank_record_bytes", C.c_uint32), ("rank_positions_per_record", C.c_uint32),
                 ("device", C.c_int32), ("image_bytes", C.c_uint64), ("rank_bytes", C.c_uint64),
-                ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64)]
+                ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64), ("num_samples", C.c_uint64),
+                ("num_text_borders", C.c_uint64)]
 
 
 class gdx_stats(C.Structure):
@@ -76,6 +77,8 @@ PROTOTYPES = {
     "gdx_suffix_array": (C.c_int, [_vp, _u64, _u32, _u32, _i32, _vp]),
     "gdx_index_download_bwt": (C.c_int, [_vp, _vp]),
     "gdx_index_get_count": (C.c_int, [_vp, _vp]),
+    "gdx_index_download_samples": (C.c_int, [_vp, _vp]),
+    "gdx_index_download_text_borders": (C.c_int, [_vp, _vp, _vp]),
     "gdx_index_destroy": (None, [_vp]),
     "gdx_index_get_info": (C.c_int, [_vp, _P(gdx_index_info)]),
     "gdx_index_header_bytes": (_u64, []),

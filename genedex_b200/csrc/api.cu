@@ -704,6 +704,31 @@ extern "C" gdx_status gdx_index_download_bwt(const gdx_index *idx, uint8_t *bwt_
     return st;
 }
 
+extern "C" gdx_status gdx_index_download_samples(const gdx_index *idx, uint64_t *samples_out) {
+    if (!idx || !samples_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    const uint64_t ns = idx->h.n_samples;
+    const uint8_t *src = (const uint8_t *)idx->image + idx->h.off_samples;
+    if (idx->h.wide) {
+        CUDA_TRY(cudaMemcpy(samples_out, src, ns * 8, cudaMemcpyDeviceToHost));
+    } else {
+        // narrow samples land in the upper half of the output buffer and are widened in place
+        uint32_t *tmp = reinterpret_cast<uint32_t *>(samples_out) + ns;
+        CUDA_TRY(cudaMemcpy(tmp, src, ns * 4, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < ns; ++i) samples_out[i] = tmp[i];
+    }
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_download_text_borders(const gdx_index *idx, uint64_t *rows_out, uint64_t *positions_out) {
+    if (!idx || !rows_out || !positions_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    const uint8_t *base = (const uint8_t *)idx->image;
+    CUDA_TRY(cudaMemcpy(rows_out, base + idx->h.off_border_rows, idx->h.n_border * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(positions_out, base + idx->h.off_border_pos, idx->h.n_border * 8, cudaMemcpyDeviceToHost));
+    return GDX_OK;
+}
+
 extern "C" gdx_status gdx_index_get_count(const gdx_index *idx, uint64_t *count_out) {
     if (!idx || !count_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
     DeviceGuard guard(idx->device);
@@ -743,6 +768,8 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->rank_bytes = h.off_samples - h.off_records;
     out->sample_bytes = h.off_lookup - h.off_samples;
     out->lookup_bytes = h.off_border_rows - h.off_lookup;
+    out->num_samples = h.n_samples;
+    out->num_text_borders = h.n_border;
     return GDX_OK;
 }
 

@@ -242,6 +242,17 @@ class FmIndex:
         _check(self._lib.gdx_index_download_bwt(self._h, out.ctypes.data))
         return out[: self.total_text_len()]
 
+    def download_samples(self) -> np.ndarray:
+        out = np.zeros(max(int(self.info().num_samples), 1), dtype=np.uint64)
+        _check(self._lib.gdx_index_download_samples(self._h, out.ctypes.data))
+        return out[: int(self.info().num_samples)]
+
+    def download_text_borders(self):
+        n = int(self.info().num_text_borders)
+        rows, pos = np.zeros(max(n, 1), dtype=np.uint64), np.zeros(max(n, 1), dtype=np.uint64)
+        _check(self._lib.gdx_index_download_text_borders(self._h, rows.ctypes.data, pos.ctypes.data))
+        return rows[:n], pos[:n]
+
     def count_array(self) -> np.ndarray:
         out = np.zeros(self.info().num_dense_symbols + 1, dtype=np.uint64)
         _check(self._lib.gdx_index_get_count(self._h, out.ctypes.data))

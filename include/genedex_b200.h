@@ -129,6 +129,7 @@ typedef struct gdx_index_info {
     int32_t device;
     uint64_t image_bytes;          /* size of the device image */
     uint64_t rank_bytes, sample_bytes, lookup_bytes;
+    uint64_t num_samples, num_text_borders;
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */
@@ -170,6 +171,10 @@ gdx_status gdx_suffix_array(const uint8_t *dense_text, uint64_t n, uint32_t num_
  * with symbol_at (src/text_with_rank_support/condensed.rs:343-362), and count[] (lib.rs:95). */
 gdx_status gdx_index_download_bwt(const gdx_index *idx, uint8_t *bwt_out);
 gdx_status gdx_index_get_count(const gdx_index *idx, uint64_t *count_out /* num_dense_symbols + 1 */);
+/* the sampled suffix array widened to 64 bit (info.num_samples entries,
+ * src/sampled_suffix_array.rs:18-23) and text_border_lookup sorted by row (info.num_text_borders) */
+gdx_status gdx_index_download_samples(const gdx_index *idx, uint64_t *samples_out);
+gdx_status gdx_index_download_text_borders(const gdx_index *idx, uint64_t *rows_out, uint64_t *positions_out);
 
 void gdx_index_destroy(gdx_index *idx);
 gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);

@@ -1,0 +1,284 @@
+"""BASELINE.json configs beyond the headline bench line, at full size, with parity checks.
+
+  python tools/run_configs.py [c2d10 c2d13 c2mix c3 c4d0 c4d5] [--scale 1.0] [--out profiles/r1_configs.jsonl]
+
+Every config builds its index on the device, runs count_many / locate_many through the C ABI with
+host buffers (e2e) and with device-resident queries (kernel only), and checks
+  * a bounded sample bit-exactly against the CPU oracle (reference three-array layout, built from the
+    BWT / samples / border map read back from the device index), and
+  * size-independent properties on the whole batch: a query sampled at (text, pos) is located there,
+    #hits == count, located hits really are occurrences (verified against the text).
+The same functions back tests/test_gpu_full_size.py.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636, 138394717,
+        133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345, 83257441, 80373285, 58617616,
+        64444167, 46709983, 50818468, 156040895, 57227415]  # chr1-22, X, Y
+PROTEIN = b"ACDEFGHIKLMNPQRSTVWY"
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def make_protein_text(n, dev, seed):
+    torch = _torch()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(PROTEIN), dtype=torch.uint8, device=dev)
+    out = torch.empty(n, dtype=torch.uint8, device=dev)
+    step = 1 << 28
+    for b in range(0, n, step):
+        e = min(n, b + step)
+        out[b:e] = lut[torch.randint(0, 20, (e - b,), generator=g, device=dev, dtype=torch.uint8).long()]
+    return out
+
+
+def sample_windows(text, text_offsets, nq, m, seed, dev, forbidden=None):
+    """nq windows of length m that lie inside one text and do not contain `forbidden`;
+    returns (query bytes [nq*m], text ids, positions in text)."""
+    torch = _torch()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    n = text.numel()
+    offs = torch.as_tensor(np.asarray(text_offsets, dtype=np.int64), device=dev)
+    ar = torch.arange(m, device=dev)
+    out = torch.empty((nq, m), dtype=torch.uint8, device=dev)
+    tid_out = torch.empty(nq, dtype=torch.int64, device=dev)
+    pos_out = torch.empty(nq, dtype=torch.int64, device=dev)
+    filled = 0
+    while filled < nq:
+        want = min(nq - filled, 1 << 21)
+        cand = torch.randint(0, n - m, (int(want * 1.3) + 16,), generator=g, device=dev)
+        tid = torch.searchsorted(offs, cand, right=True) - 1
+        ok = cand + m <= offs[tid + 1]
+        win = text[cand[:, None] + ar[None, :]]
+        if forbidden is not None:
+            ok &= ~(win == forbidden).any(dim=1)
+        win, cand, tid = win[ok][:want], cand[ok][:want], tid[ok][:want]
+        k = win.shape[0]
+        out[filled:filled + k] = win
+        tid_out[filled:filled + k] = tid
+        pos_out[filled:filled + k] = cand - offs[tid]
+        filled += k
+    return out.reshape(-1), tid_out, pos_out
+
+
+def random_queries(nq, m, symbols, seed, dev):
+    torch = _torch()
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(symbols), dtype=torch.uint8, device=dev)
+    return lut[torch.randint(0, len(symbols), (nq * m,), generator=g, device=dev, dtype=torch.uint8).long()]
+
+
+def oracle_from_product(pidx, oracle_alphabet, sentinels, depth, s, with_locate):
+    from oracle import oracle as O
+    bwt = pidx.download_bwt()
+    samples = rows = pos = None
+    if with_locate:
+        samples = pidx.download_samples()
+        rows, pos = pidx.download_text_borders()
+    return O.OracleIndex.from_parts(bwt, oracle_alphabet, pidx.count_array(), sentinels, samples, s, rows, pos,
+                                    lookup_depth=depth, storage="u32", nthreads=0)
+
+
+def time_device_count(gdx, pidx, q_dev, m, nq, reps=5):
+    torch = _torch()
+    lib = gdx._lib.load()
+    d_counts = torch.zeros(nq, dtype=torch.int64, device=q_dev.device)
+    qs = gdx._lib.gdx_queries(q_dev.data_ptr(), None, m, nq)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        assert lib.gdx_count_many_device(pidx.handle, C.byref(qs), d_counts.data_ptr(), None, stream) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        assert lib.gdx_count_many_device(pidx.handle, C.byref(qs), d_counts.data_ptr(), None, stream) == 0
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, d_counts.cpu().numpy().astype(np.uint64)
+
+
+def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev, m, nq, depth, s,
+             origin=None, oracle_sample=200_000, locate=True, verify_text=None):
+    """texts_io: host uint8 array of all texts back to back; origin = (text ids, positions) of the first
+    len(origin[0]) queries (those were sampled from the texts)."""
+    torch = _torch()
+    t0 = time.perf_counter()
+    cfg = (gdx.FmIndexConfig("u32").suffix_array_sampling_rate(s).lookup_table_depth(depth)
+           .construct_on_device(True, verify=True))
+    pidx = cfg.construct_index_packed(texts_io, np.asarray(text_offsets, dtype=np.uint64), alphabet)
+    build_s = time.perf_counter() - t0
+    info = pidx.info()
+    q_host = torch.empty(nq * m, dtype=torch.uint8).pin_memory()
+    q_host.copy_(q_dev)
+    q_np = q_host.numpy()
+    counts = torch.empty(nq, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+
+    kernel_ms, counts_dev = time_device_count(gdx, pidx, q_dev, m, nq)
+    for _ in range(2):
+        pidx.count_many_packed(q_np, None, m, nq, out=counts)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        pidx.count_many_packed(q_np, None, m, nq, out=counts)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+    st = pidx.stats()
+    assert np.array_equal(counts, counts_dev), f"{name}: device-resident and host-buffer counts differ"
+    res = {"config": name, "text_len": int(info.text_len), "num_texts": int(info.num_texts), "queries": nq,
+           "query_len": m, "lookup_depth": depth, "sampling_rate": s, "sigma": int(info.num_dense_symbols),
+           "rank_record_bytes": int(info.rank_record_bytes), "index_bytes": int(info.image_bytes),
+           "build_s": round(build_s, 2), "lf_steps": int(st.lf_steps),
+           "count_kernel_ms": round(kernel_ms, 3), "count_queries_per_s": nq / (kernel_ms * 1e-3),
+           "count_e2e_ms": round(e2e_ms, 3), "count_e2e_queries_per_s": nq / (e2e_ms * 1e-3)}
+    n_orig = 0 if origin is None else int(origin[0].size)
+    if n_orig:
+        assert int(counts[:n_orig].min()) >= 1, f"{name}: a query sampled from the text has count 0"
+
+    if locate:
+        hit_off = np.empty(nq + 1, dtype=np.uint64)
+        for _ in range(2):
+            _, hits, release = pidx.locate_many_view(q_np, None, m, nq, hit_offsets=hit_off)
+            release()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            _, hits, release = pidx.locate_many_view(q_np, None, m, nq, hit_offsets=hit_off)
+            release()
+        loc_ms = (time.perf_counter() - t0) * 1e3 / 3
+        lst = pidx.stats()
+        assert np.array_equal((hit_off[1:] - hit_off[:-1]), counts), f"{name}: #hits != count"
+        if n_orig:  # the origin of every sampled query is among its hits
+            tid, pos = origin
+            single = (hit_off[1:n_orig + 1] - hit_off[:n_orig]) == 1
+            first = hits[hit_off[:n_orig].astype(np.int64)]
+            assert np.array_equal(first[single, 0].astype(np.int64), tid[single]), f"{name}: wrong text id"
+            assert np.array_equal(first[single, 1].astype(np.int64), pos[single]), f"{name}: wrong position"
+            multi = np.flatnonzero(~single)[:2000]
+            for i in multi:
+                hs = hits[int(hit_off[i]):int(hit_off[i + 1])]
+                assert ((hs[:, 0] == tid[i]) & (hs[:, 1] == pos[i])).any(), f"{name}: origin of query {i} not located"
+        if verify_text is not None:  # located hits are occurrences
+            rng = np.random.default_rng(1)
+            for i in rng.integers(0, nq, 3000):
+                for t, p in hits[int(hit_off[i]):int(hit_off[i + 1])][:4]:
+                    b = int(text_offsets[int(t)]) + int(p)
+                    assert verify_text(texts_io[b:b + m], q_np[i * m:(i + 1) * m]), f"{name}: hit is not an occurrence"
+        res.update({"locate_e2e_ms": round(loc_ms, 3), "locate_e2e_queries_per_s": nq / (loc_ms * 1e-3),
+                    "hits": int(lst.hits), "walk_steps": int(lst.walk_steps),
+                    "locate_kernels_ms": round(lst.kernel_ms_locate, 3)})
+
+    if oracle_sample:
+        from oracle import oracle as O
+        sentinels = np.asarray(text_offsets[1:], dtype=np.uint64) + np.arange(len(text_offsets) - 1, dtype=np.uint64)
+        oidx = oracle_from_product(pidx, oracle_alphabet, sentinels, depth, s, locate)
+        # a sample from the front (sampled-from-text queries) and from the back (random queries)
+        k = min(oracle_sample // 2, nq // 2)
+        sel = np.concatenate([np.arange(k), np.arange(nq - k, nq)])
+        qsel = np.ascontiguousarray(q_np.reshape(nq, m)[sel].reshape(-1))
+        off = np.arange(sel.size + 1, dtype=np.uint64) * m
+        t0 = time.perf_counter()
+        ocounts = oidx.count_many_packed(qsel, off, nthreads=0)
+        cpu_s = time.perf_counter() - t0
+        assert np.array_equal(ocounts, counts[sel]), f"{name}: counts differ from the oracle"
+        res.update({"oracle_sample": int(sel.size), "oracle_count_queries_per_s": sel.size / cpu_s,
+                    "oracle_cores": int(O.lib().gdxo_online_cores())})
+        if locate:
+            ooff, ohits = oidx.locate_many_packed(qsel, off, nthreads=0)
+            for j, i in enumerate(sel[:: max(1, sel.size // 20000)]):
+                jj = j * max(1, sel.size // 20000)
+                a, b = int(ooff[jj]), int(ooff[jj + 1])
+                assert np.array_equal(ohits[a:b], hits[int(hit_off[i]):int(hit_off[i + 1])]), \
+                    f"{name}: hits of query {i} differ from the oracle"
+        res["parity"] = "counts bit-exact on the oracle sample" + (", hits bit-exact (SA-row order)" if locate else "")
+    return res
+
+
+def dna_fold(a, b):
+    return bytes(a).upper() == bytes(b).upper()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="*", default=["c2d10", "c2d13", "c2mix", "c3", "c4d0", "c4d5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="scale text and query counts (tests use < 1)")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    for line in run(args.configs, args.scale):
+        print(json.dumps(line), flush=True)
+        if args.out:
+            with open(args.out, "a") as f:
+                f.write(json.dumps(line) + "\n")
+
+
+def run(configs, scale=1.0):
+    torch = _torch()
+    import bench
+    import genedex_b200 as gdx
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = []
+    dna = [c for c in configs if c.startswith("c2") or c == "c3"]
+    if dna:
+        n = int(3_100_000_000 * scale)
+        nq, m = int(7_500_000 * scale), 50
+        text = bench.make_text_on_device(n, 0.05, dev)
+        host = text.cpu().numpy()
+        for c in dna:
+            if c == "c3":
+                lens = np.array(HG38, dtype=np.float64) * scale
+                offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))])
+                offs = np.minimum(offs, n)
+                depth, mix = 0, False
+            else:
+                offs = np.array([0, n], dtype=np.int64)
+                depth, mix = {"c2d10": (10, False), "c2d13": (13, False), "c2mix": (0, True)}[c]
+            tn = int(offs[-1])
+            nsamp = nq // 2 if mix else nq
+            q, tid, pos = sample_windows(text[:tn], offs, nsamp, m, bench.QUERY_SEED, dev, forbidden=bench.N_CODE)
+            if mix:
+                q = torch.cat([q, random_queries(nq - nsamp, m, b"ACGT", bench.QUERY_SEED + 9, dev)])
+            origin = (tid.cpu().numpy(), pos.cpu().numpy())
+            out.append(run_case(c, gdx, host[:tn], offs, gdx.alphabet.ascii_dna_with_n(),
+                                O.ALPHABETS["ascii_dna_with_n"](), q, m, nq, depth, 4, origin=origin,
+                                locate=True, verify_text=dna_fold))
+            yield out[-1]
+            del q
+            torch.cuda.empty_cache()
+        del text, host
+        torch.cuda.empty_cache()
+    prot = [c for c in configs if c.startswith("c4")]
+    if prot:
+        n = int(500_000_000 * scale)
+        nq, m = int(10_000_000 * scale), 12
+        text = make_protein_text(n, dev, 0x5EED0004)
+        host = text.cpu().numpy()
+        offs = np.array([0, n], dtype=np.int64)
+        q1, tid, pos = sample_windows(text, offs, nq // 2, m, 0x5EED0005, dev)
+        q = torch.cat([q1, random_queries(nq - nq // 2, m, PROTEIN, 0x5EED0006, dev)])
+        origin = (tid.cpu().numpy(), pos.cpu().numpy())
+        del text
+        torch.cuda.empty_cache()
+        for c in prot:
+            depth = {"c4d0": 0, "c4d5": 5}[c]
+            out.append(run_case(c, gdx, host, offs, gdx.Alphabet.from_io_symbols(PROTEIN, 0), O.ALPHABETS["protein20"](),
+                                q, m, nq, depth, 4, origin=origin, locate=True,
+                                verify_text=lambda a, b: bytes(a) == bytes(b)))
+            yield out[-1]
+
+
+if __name__ == "__main__":
+    main()
