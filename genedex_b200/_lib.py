@@ -16,6 +16,7 @@ GDX_OK, GDX_ERR_INVALID_SYMBOL, GDX_ERR_BAD_ARG, GDX_ERR_CUDA, GDX_ERR_OOM, GDX_
 GDX_I32, GDX_U32, GDX_I64 = 0, 1, 2
 GDX_CONSTRUCT_HOST, GDX_CONSTRUCT_DEVICE = 0, 1
 GDX_FLAG_VERIFY_SUFFIX_ARRAY = 1
+GDX_FLAG_NO_TEXT = 2
 
 
 class gdx_alphabet(C.Structure):
@@ -54,13 +55,14 @@ class gdx_index_info(C.Structure):
                 ("rank_record_bytes", C.c_uint32), ("rank_positions_per_record", C.c_uint32),
                 ("device", C.c_int32), ("image_bytes", C.c_uint64), ("rank_bytes", C.c_uint64),
                 ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64), ("num_samples", C.c_uint64),
-                ("num_text_borders", C.c_uint64)]
+                ("num_text_borders", C.c_uint64), ("text_bytes", C.c_uint64)]
 
 
 class gdx_stats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("lf_steps", C.c_uint64), ("hits", C.c_uint64),
                 ("walk_steps", C.c_uint64), ("kernel_ms_search", C.c_double),
-                ("kernel_ms_locate", C.c_double), ("kernel_launches", C.c_uint64)]
+                ("kernel_ms_locate", C.c_double), ("kernel_launches", C.c_uint64),
+                ("verified_queries", C.c_uint64)]
 
 
 # every symbol include/genedex_b200.h declares: name -> (restype, argtypes)

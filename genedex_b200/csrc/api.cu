@@ -263,6 +263,7 @@ struct ImageSources {
     const uint64_t *border_pos;        // host
     uint64_t n_border;
     const uint8_t *d_bwt;              // device, n bytes
+    const uint8_t *d_text = nullptr;   // device, n bytes dense text (optional: enables the text section)
     // exactly one of the sample sources
     const uint64_t *h_samples64 = nullptr;  // host
     const void *d_samples = nullptr;        // device, element width given by d_samples_wide
@@ -328,6 +329,12 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     h.off_border_pos = place(h.n_border * 8);
     h.off_sentinels = place(h.ntexts * 8);
     h.off_count = place((uint64_t)(h.sigma + 1) * 8);
+    h.text_bits = 0;
+    h.off_text = off;
+    if (src.d_text) {
+        h.text_bits = h.sigma <= 16 ? 4 : 8;
+        h.off_text = place(h.text_bits == 4 ? (src.n + 1) / 2 : src.n);
+    }
     h.image_bytes = off;
     return GDX_OK;
 }
@@ -403,6 +410,12 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
                 k_narrow_u64<<<g, 256>>>((const uint64_t *)src.d_samples, h.n_samples, (uint32_t *)dst);
             IMG_TRY(cudaGetLastError());
         }
+    }
+
+    if (h.text_bits && h.n) {
+        const uint64_t items = h.text_bits == 4 ? (h.n + 1) / 2 : h.n;
+        k_pack_text<<<(unsigned)div_up(items, 256), 256>>>(src.d_text, h.n, h.text_bits, base + h.off_text);
+        IMG_TRY(cudaGetLastError());
     }
 
     idx->dev = make_dev_index(h, idx->image);
@@ -520,10 +533,25 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     src.sentinels = ct.sentinels.data();
     src.ntexts = num_texts;
 
+    // the dense text goes to the device once: input of the device suffix sort and source of the
+    // optional text section of the image
+    const bool keep_text = (config->flags & GDX_FLAG_NO_TEXT) == 0;
+    struct DevText {
+        uint8_t *p = nullptr;
+        ~DevText() {
+            if (p) cudaFree(p);
+        }
+    } d_text;
+    if (keep_text || config->construction == GDX_CONSTRUCT_DEVICE) {
+        CUDA_TRY(cudaMalloc(&d_text.p, n ? n : 1));
+        CUDA_TRY(cudaMemcpy(d_text.p, ct.text.data(), n, cudaMemcpyHostToDevice));
+        if (keep_text) src.d_text = d_text.p;
+    }
+
     if (config->construction == GDX_CONSTRUCT_DEVICE) {
         DeviceBuildResult r;
         const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
-        st = device_build_from_text(ct.text.data(), nullptr, n, alphabet->num_dense_symbols,
+        st = device_build_from_text(nullptr, d_text.p, n, alphabet->num_dense_symbols,
                                     config->suffix_array_sampling_rate, r, t_error, false, verify);
         if (st != GDX_OK) return st;
         if (verify && r.verify_violations) {
@@ -770,6 +798,7 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->lookup_bytes = h.off_border_rows - h.off_lookup;
     out->num_samples = h.n_samples;
     out->num_text_borders = h.n_border;
+    out->text_bytes = h.text_bits ? h.image_bytes - h.off_text : 0;
     return GDX_OK;
 }
 
@@ -836,12 +865,25 @@ extern "C" gdx_status gdx_index_replicate(const gdx_index *idx, const int32_t *d
 // ================================================================================================
 namespace {
 
+bool verify_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("GDX_VERIFY");
+        return !e || atoi(e) != 0;
+    }();
+    return on;
+}
+
+// mode 0: cursors (starts, ends); 1: counts; 2: locate intervals (interval or resolved hit)
 template <class L>
 void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint64_t *b, int mode,
                    uint64_t qbase, uint64_t *err, unsigned long long *steps, const uint32_t *perm,
                    cudaStream_t stream) {
     if (dq.nq == 0) return;
-    k_search<L><<<(unsigned)div_up(dq.nq, 256), 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+    const unsigned grid = (unsigned)div_up(dq.nq, 256);
+    if (mode != 0 && idx->dev.text && verify_enabled())
+        k_search<L, true><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+    else
+        k_search<L, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
 }
 
 // ---- suffix sort of a query batch (locality of the first search steps, see k_query_keys) -------------
@@ -1045,6 +1087,8 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         }
     t_stats.queries = nq;
     t_stats.lf_steps = ws->small.h[4];
+    t_stats.walk_steps = ws->small.h[5];
+    t_stats.verified_queries = ws->small.h[9];
     t_stats.kernel_ms_search = ms;
     uint64_t bad = kNoError;
     for (int s = 0; s < kSlots; ++s) bad = std::min(bad, ws->small.h[s]);
@@ -1163,7 +1207,7 @@ gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64
     cudaEventElapsedTime(&ms, ws->ev_a, ws->ev_b);
     t_stats.kernel_ms_locate = ms;
     t_stats.hits = total;
-    t_stats.walk_steps = ws->small.h[5];
+    t_stats.walk_steps += ws->small.h[5];
     *hits = (gdx_hit *)h;
     *num_hits = total;
     return GDX_OK;
@@ -1207,7 +1251,7 @@ extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *q
     // a buffer may only be replaced once nothing in flight uses it: every call ends synchronized
     CUDA_TRY(ws->starts.reserve((n + 1) * 8));
     CUDA_TRY(ws->ends.reserve((n + 1) * 8));
-    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 0, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
+    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 2, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
     uint64_t total = 0;
     GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
     return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);

@@ -10,6 +10,9 @@
 //   border_pos   SA[i] for those rows                            (text_border_lookup values)
 //   sentinels    sorted sentinel positions of the concatenated text (text id mapping)
 //   count        u64 [sigma + 1]  (src/lib.rs:95), only the rare derived-rank path reads it
+//   text         (optional) the concatenated dense text, 4 bits per symbol (sigma <= 16) or 8: lets
+//                count/locate finish a query whose interval has narrowed to one row by one text
+//                comparison instead of one random rank record per remaining symbol
 #ifndef GDX_DEVICE_INDEX_H
 #define GDX_DEVICE_INDEX_H
 
@@ -35,7 +38,9 @@ struct ImageHeader {
     uint32_t sigma, ns, storage, sampling_rate, lookup_depth, pad0;
     RankLayout layout;
     uint64_t off_records, off_sbc, off_samples, off_lookup, off_border_rows, off_border_pos,
-        off_sentinels, off_count;
+        off_sentinels, off_count, off_text;
+    uint32_t text_bits;  // 0 = no text section, 4 or 8
+    uint32_t pad1;
     uint64_t image_bytes;
     uint64_t lut_level_off[kMaxLookupDepth + 1];  // entry offset of level d
     uint64_t lut_pow[kMaxLookupDepth + 1];        // ns^d
@@ -52,11 +57,12 @@ struct DevIndex {
     const uint64_t *border_pos;
     const uint64_t *sentinels;
     const uint64_t *count;
+    const uint8_t *text;
     uint64_t n, ntexts, n_border;
     uint32_t sigma, ns, sampling_rate, lookup_depth;
     uint32_t wide, noff, stride, derived_symbol;
     uint32_t sampling_shift;  // log2(sampling_rate) if it is a power of two, else 0xffffffff
-    uint32_t pad;
+    uint32_t text_bits;
     uint64_t lut_level_off[kMaxLookupDepth + 1];
     uint64_t lut_pow[kMaxLookupDepth + 1];
     uint8_t io_to_dense[256];
@@ -73,6 +79,8 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.border_pos = (const uint64_t *)(base + h.off_border_pos);
     d.sentinels = (const uint64_t *)(base + h.off_sentinels);
     d.count = (const uint64_t *)(base + h.off_count);
+    d.text = h.text_bits ? base + h.off_text : nullptr;
+    d.text_bits = h.text_bits;
     d.n = h.n;
     d.ntexts = h.ntexts;
     d.n_border = h.n_border;
@@ -90,7 +98,6 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
         while ((1u << s) < h.sampling_rate) ++s;
         d.sampling_shift = s;
     }
-    d.pad = 0;
     for (uint32_t i = 0; i <= kMaxLookupDepth; ++i) {
         d.lut_level_off[i] = h.lut_level_off[i];
         d.lut_pow[i] = h.lut_pow[i];

@@ -52,6 +52,7 @@ __device__ __forceinline__ void ldg128_na(const void *p, uint64_t &lo, uint64_t 
 // ---- layout traits -----------------------------------------------------------------------------
 struct K32 {
     static constexpr uint32_t kLog2P = 6;
+    static constexpr int kSearchMinBlocks = 6;  // 40 registers: 1536 threads per SM
     struct Planes {
         uint64_t w[4];
     };
@@ -97,6 +98,7 @@ struct K32 {
 template <int B>
 struct KG {
     static constexpr uint32_t kLog2P = 7;
+    static constexpr int kSearchMinBlocks = B <= 3 ? 5 : (B <= 5 ? 4 : 3);
     struct Planes {
         uint64_t lo[B], hi[B];
     };
@@ -193,6 +195,46 @@ __device__ __forceinline__ void report_error(uint64_t *err, uint64_t q) {
     if (err) atomicMin(reinterpret_cast<unsigned long long *>(err), (unsigned long long)q);
 }
 
+// ---- SA[row] by LF-walk to the next sample (sampled_suffix_array.rs:110-138) -------------------------
+template <class L>
+__device__ __forceinline__ uint64_t resolve_row(const DevIndex &ix, uint64_t i, uint32_t &steps) {
+    for (;;) {
+        const bool sampled = ix.sampling_shift != 0xffffffffu ? (i & ((1ull << ix.sampling_shift) - 1)) == 0
+                                                              : (i % ix.sampling_rate) == 0;
+        if (sampled) {
+            const uint64_t k = ix.sampling_shift != 0xffffffffu ? i >> ix.sampling_shift : i / ix.sampling_rate;
+            return (ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k)
+                            : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.samples) + k)) +
+                   steps;
+        }
+        typename L::Planes pl = L::load_planes(ix, i);
+        const uint32_t c = L::symbol_at(pl, i);
+        if (c == 0) {  // :121-126 text_border_lookup[&i]
+            const uint64_t k = lower_bound_u64(ix.border_rows, ix.n_border, i);
+            return __ldg(ix.border_pos + k) + steps;
+        }
+        if (c > ix.noff) {
+            i = L::lf_derived(ix, i);
+        } else {
+            typename L::Rec r = L::with_offset(ix, pl, i, c);
+            i = sbc_load(ix, i, c) + L::local_rank(r, c, i);
+        }
+        ++steps;
+    }
+}
+
+// dense symbol at concatenated-text position p (text section of the image)
+__device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) {
+    if (ix.text_bits == 4) return (__ldg(ix.text + (p >> 1)) >> ((p & 1) * 4)) & 15u;
+    return __ldg(ix.text + p);
+}
+
+// interval flag of the locate plumbing: start = resolved text position, end = kDirectHit
+constexpr uint64_t kDirectHit = ~0ull;
+// switch from LF steps to "resolve the row + compare against the text" when the interval has one row
+// and at least this many symbols are left (a walk + sample + text read costs about 5 random sectors)
+constexpr uint32_t kVerifyMinRemaining = 8;
+
 // ---- sort key of a query: its last symbols, last symbol most significant ---------------------------
 // Backward search consumes a query right to left, so queries that share a suffix walk the same
 // records for their first steps.  Sorting the batch by suffix makes neighbouring threads/CTAs walk
@@ -237,8 +279,15 @@ k_query_keys(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_t 
 constexpr uint32_t kQueryStage = 64;                       // bytes staged per query
 constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, covers any misalignment
 
-template <class L>
-__global__ void __launch_bounds__(256)
+// VERIFY (count / locate only, needs the text section): as soon as the interval holds exactly one row
+// and >= kVerifyMinRemaining symbols are left, SA[row] is resolved (LF-walk to a sample) and the rest
+// of the query is compared with the text right to left.  The reference would shrink that interval to
+// [x, x+1) or to empty by the same comparisons, one rank per symbol (cursor.rs:40-51): count and hit
+// are identical, the invalid-symbol panic fires at the same symbol, only the interval itself is not
+// produced -- so mode 0 (cursors) never uses it.  mode 2 = locate: out_a/out_b carry either the
+// interval or (text position, kDirectHit).
+template <class L, bool VERIFY>
+__global__ void __launch_bounds__(256, L::kSearchMinBlocks)
 k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__restrict__ out_a,
          uint64_t *__restrict__ out_b, int mode, uint64_t q_index_base, uint64_t *err,
          unsigned long long *stat_steps, const uint32_t *__restrict__ perm) {
@@ -248,7 +297,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
     __syncthreads();
 
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t steps = 0;
+    uint32_t steps = 0, vsteps = 0, vrows = 0;
     if (t < qs.nq) {
         const uint64_t q = perm ? (uint64_t)__ldg(perm + t) : t;
         uint64_t begin, len;
@@ -293,7 +342,31 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
 
         // K2: batch_computed_cursors.rs:62-70
+        bool direct = false;
         while (!bad && pos > 0 && s != e) {
+            if (VERIFY && e - s == 1 && pos >= kVerifyMinRemaining) {
+                // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
+                const uint64_t at = resolve_row<L>(ix, s, vsteps);
+                vrows = 1;
+                bool match = true;
+                for (uint64_t j = pos; match && j-- > 0;) {
+                    const uint32_t c = GDX_SYMBOL_AT(j);
+                    if (c == 0) {  // the reference reaches this symbol with a non-empty interval
+                        bad = true;
+                        break;
+                    }
+                    const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
+                    match = back <= at && text_symbol(ix, at - back) == c;
+                }
+                if (match && !bad) {
+                    direct = true;
+                    s = at - pos;  // text position of the whole query
+                    e = s + 1;
+                } else {
+                    s = e = 0;
+                }
+                break;
+            }
             const uint32_t c = GDX_SYMBOL_AT(pos - 1);
             if (c == 0) {
                 bad = true;
@@ -306,18 +379,28 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         if (bad) {
             report_error(err, q_index_base + q);
             s = e = 0;
+            direct = false;
         }
         if (mode == 0) {
             out_a[q] = s;
             out_b[q] = e;
-        } else {
+        } else if (mode == 1) {
             out_a[q] = e - s;
+        } else {
+            out_a[q] = s;
+            out_b[q] = direct ? kDirectHit : e;
         }
 #undef GDX_SYMBOL_AT
     }
-    if (stat_steps) {
+    if (stat_steps) {  // [0] LF steps of the search, [1] walk steps of verified rows, [5] verified rows
         uint32_t tot = __reduce_add_sync(0xffffffffu, steps);
         if ((threadIdx.x & 31) == 0 && tot) atomicAdd(stat_steps, (unsigned long long)tot);
+        if (VERIFY) {
+            tot = __reduce_add_sync(0xffffffffu, vsteps);
+            if ((threadIdx.x & 31) == 0 && tot) atomicAdd(stat_steps + 1, (unsigned long long)tot);
+            tot = __reduce_add_sync(0xffffffffu, vrows);
+            if ((threadIdx.x & 31) == 0 && tot) atomicAdd(stat_steps + 5, (unsigned long long)tot);
+        }
     }
 }
 
@@ -343,6 +426,7 @@ k_extend(const __grid_constant__ DevIndex ix, uint64_t *__restrict__ starts, uin
 
 // ---- CSR plumbing for locate --------------------------------------------------------------------------
 constexpr uint32_t kExpandInline = 32;
+constexpr uint64_t kResolvedBit = 1ull << 63;  // rows[] entry is a text position, not an SA row
 
 // counts[q] = width of interval q; *big_count = number of intervals wider than kExpandInline
 __global__ void k_interval_counts(const uint64_t *__restrict__ starts, const uint64_t *__restrict__ ends,
@@ -350,7 +434,7 @@ __global__ void k_interval_counts(const uint64_t *__restrict__ starts, const uin
                                   unsigned long long *big_count) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const uint64_t c = ends[q] - starts[q];
+    const uint64_t c = ends[q] == kDirectHit ? 1 : ends[q] - starts[q];
     counts[q] = c;
     if (c > kExpandInline) atomicAdd(big_count, 1ull);
 }
@@ -362,7 +446,12 @@ __global__ void k_expand_rows(const uint64_t *__restrict__ starts, const uint64_
                               unsigned long long *big_cursor) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const uint64_t s = starts[q], cnt = ends[q] - s, off = hit_offsets[q];
+    const uint64_t s = starts[q], off = hit_offsets[q];
+    if (ends[q] == kDirectHit) {  // already a text position (verified in k_search): tag it for the walk
+        rows[off] = s | kResolvedBit;
+        return;
+    }
+    const uint64_t cnt = ends[q] - s;
     if (cnt > kExpandInline) {
         big_list[atomicAdd(big_cursor, 1ull)] = q;
         return;
@@ -389,35 +478,8 @@ k_locate_walk(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ 
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
     if (h < nh) {
-        uint64_t i = rows[h];
-        uint64_t pos;
-        for (;;) {  // sampled_suffix_array.rs:117-136
-            const bool sampled = ix.sampling_shift != 0xffffffffu
-                                     ? (i & ((1ull << ix.sampling_shift) - 1)) == 0
-                                     : (i % ix.sampling_rate) == 0;
-            if (sampled) {
-                const uint64_t k = ix.sampling_shift != 0xffffffffu ? i >> ix.sampling_shift
-                                                                    : i / ix.sampling_rate;
-                pos = (ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k)
-                               : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.samples) + k)) +
-                      steps;
-                break;
-            }
-            typename L::Planes pl = L::load_planes(ix, i);
-            const uint32_t c = L::symbol_at(pl, i);
-            if (c == 0) {  // :121-126 text_border_lookup[&i]
-                const uint64_t k = lower_bound_u64(ix.border_rows, ix.n_border, i);
-                pos = __ldg(ix.border_pos + k) + steps;
-                break;
-            }
-            if (c > ix.noff) {
-                i = L::lf_derived(ix, i);
-            } else {
-                typename L::Rec r = L::with_offset(ix, pl, i, c);
-                i = sbc_load(ix, i, c) + L::local_rank(r, c, i);
-            }
-            ++steps;
-        }
+        const uint64_t row = rows[h];
+        const uint64_t pos = (row & kResolvedBit) ? (row & ~kResolvedBit) : resolve_row<L>(ix, row, steps);
         // text_id_search_tree.rs:35-64: lower_bound over the sentinel positions
         uint64_t id = lower_bound_u64(ix.sentinels, ix.ntexts, pos);
         if (id >= ix.ntexts) id = ix.ntexts - 1;
@@ -553,6 +615,18 @@ k_records_to_bwt(const __grid_constant__ DevIndex ix, uint64_t begin, uint64_t e
     if (i >= end) return;
     typename L::Planes pl = L::load_planes(ix, i);
     out[i - begin] = (uint8_t)L::symbol_at(pl, i);
+}
+
+// dense text -> text section: two symbols per byte (low nibble = even position) or a plain copy
+__global__ void k_pack_text(const uint8_t *__restrict__ text, uint64_t n, uint32_t bits, uint8_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (bits == 4) {
+        if (2 * i >= n) return;
+        const uint32_t lo = text[2 * i], hi = 2 * i + 1 < n ? text[2 * i + 1] : 0;
+        out[i] = (uint8_t)(lo | (hi << 4));
+    } else if (i < n) {
+        out[i] = text[i];
+    }
 }
 
 __global__ void k_widen_u32(const uint32_t *__restrict__ in, uint64_t n, uint64_t *__restrict__ out) {

@@ -100,7 +100,14 @@ class FmIndexConfig:
     # -- additions of this engine (not in the reference): where to build, on which GPU
     def construct_on_device(self, on_device: bool = True, verify: bool = False) -> "FmIndexConfig":
         self._construction = _lib.GDX_CONSTRUCT_DEVICE if on_device else _lib.GDX_CONSTRUCT_HOST
-        self._flags = _lib.GDX_FLAG_VERIFY_SUFFIX_ARRAY if verify else 0
+        self._flags = (self._flags & ~_lib.GDX_FLAG_VERIFY_SUFFIX_ARRAY) | (
+            _lib.GDX_FLAG_VERIFY_SUFFIX_ARRAY if verify else 0)
+        return self
+
+    def keep_text(self, keep: bool = True) -> "FmIndexConfig":
+        """Keep the packed text in the device image (default): one-row intervals are finished by a
+        text comparison in count/locate.  Without it every LF step runs; results are identical."""
+        self._flags = (self._flags & ~_lib.GDX_FLAG_NO_TEXT) | (0 if keep else _lib.GDX_FLAG_NO_TEXT)
         return self
 
     def device(self, ordinal: int) -> "FmIndexConfig":

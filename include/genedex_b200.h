@@ -73,6 +73,10 @@ typedef struct gdx_config {
 
 /* re-check the device-built suffix array in O(n) (permutation + order) before it is used */
 #define GDX_FLAG_VERIFY_SUFFIX_ARRAY 1u
+/* do not keep the packed text in the device image (saves n/2 bytes for sigma <= 16, n otherwise);
+ * count/locate then run every LF step instead of finishing one-row intervals by a text comparison.
+ * Results are identical either way. */
+#define GDX_FLAG_NO_TEXT 2u
 
 /* src/lib.rs:331-335 Hit { text_id, position } */
 typedef struct gdx_hit {
@@ -130,6 +134,7 @@ typedef struct gdx_index_info {
     uint64_t image_bytes;          /* size of the device image */
     uint64_t rank_bytes, sample_bytes, lookup_bytes;
     uint64_t num_samples, num_text_borders;
+    uint64_t text_bytes;           /* packed text section, 0 if absent */
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */
@@ -141,6 +146,7 @@ typedef struct gdx_stats {
     double kernel_ms_search; /* CUDA-event time of the search kernel(s)              */
     double kernel_ms_locate; /* CUDA-event time of the locate kernels                */
     uint64_t kernel_launches;
+    uint64_t verified_queries; /* queries finished by one text comparison instead of LF steps */
 } gdx_stats;
 
 uint32_t gdx_abi_version(void);

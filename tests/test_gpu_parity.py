@@ -436,3 +436,58 @@ def test_cpp_mirror_kats(gdx, tmp_path):
     from test_host_logic import build_cpp_api_test
     out = subprocess.run([build_cpp_api_test(tmp_path)], capture_output=True, text=True)
     assert out.returncode == 0 and "cpp api ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_text_verification_shortcut_semantics(gdx):
+    """count/locate finish one-row intervals by comparing the rest of the query with the text
+    (k_search<.., VERIFY>).  Everything observable must stay identical to the LF-only reference path:
+    counts, hits, and the laziness of the invalid-symbol panic -- also for matches that would start
+    before a text, cross a text border, or hit a mismatch / invalid byte anywhere."""
+    rng = random.Random(77)
+    texts = [bytes(rng.choice(b"ACGTN" if i % 2 else b"ACGT") for _ in range(rng.randrange(1500, 2500)))
+             for i in range(4)] + [b"", b"ACGTACGTAC"]
+    for depth, on_device in ((0, False), (3, True)):
+        oidx, pidx = util.build_pair(gdx, texts, "ascii_dna_with_n", "u32", 4, depth, on_device)
+        assert pidx.info().text_bytes > 0
+        cfg = gdx.FmIndexConfig("u32").lookup_table_depth(depth).keep_text(False)
+        lf_only = cfg.construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        assert lf_only.info().text_bytes == 0
+        valid, invalid = [], []
+        for _ in range(1500):
+            t = rng.choice([x for x in texts if len(x) > 100])
+            m = rng.randrange(12, 90)
+            p = rng.randrange(0, len(t) - m)
+            q = bytearray(t[p:p + m])
+            kind = rng.randrange(6)
+            if kind == 1:      # mismatch somewhere
+                k = rng.randrange(m)
+                q[k] = rng.choice([c for c in b"ACGT" if c != q[k]])
+            elif kind == 2:    # would have to start before its text
+                q = bytearray(bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(1, 12))) + t[:m])
+            elif kind == 3:    # crosses a text border
+                t2 = rng.choice([x for x in texts if len(x) > 100])
+                q = bytearray(t[-(m // 2):] + t2[: m // 2])
+            elif kind == 4:    # an invalid byte at a random place
+                q[rng.randrange(len(q))] = ord("X")
+            if depth > 0 and b"N" in bytes(q).upper():
+                continue
+            (invalid if b"X" in q else valid).append(bytes(q))
+        util.assert_same_results(oidx, pidx, valid)
+        util.assert_same_results(oidx, lf_only, valid)
+        assert pidx.stats().verified_queries > 0 or True
+        data, offsets = O.pack(valid)
+        pidx.count_many_packed(data, offsets)
+        assert pidx.stats().verified_queries > 100  # the shortcut really ran
+        lf_only.count_many_packed(data, offsets)
+        assert lf_only.stats().verified_queries == 0
+        for q in invalid:  # one query per call: panic <=> exception, otherwise equal results
+            try:
+                want = oidx.count_many([q]).tolist()
+            except O.OraclePanic:
+                with pytest.raises(gdx.InvalidSymbolError):
+                    pidx.count_many([q])
+                with pytest.raises(gdx.InvalidSymbolError):
+                    pidx.locate_many([q])
+                continue
+            assert pidx.count_many([q]) == want
+            assert [[(h.text_id, h.position) for h in hs] for hs in pidx.locate_many([q])] == oidx.locate_many([q])
