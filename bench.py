@@ -384,7 +384,10 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_kind = measured_peak_gbs()
     steps_exec = int(st.lf_steps)
     R = int(info.rank_record_bytes)
-    alg_bytes = nq * (m + 16 + (8 if args.lookup_depth > 0 else 0)) + 2 * R * steps_exec
+    # SURVEY 8d per query: m + [8 if D>0] + 2*R*steps + 16; a query finished by text verification adds its
+    # walk (R per LF step), one SA-sample sector and one sector of packed text instead of further LF steps
+    alg_bytes = (nq * (m + 16 + (8 if args.lookup_depth > 0 else 0)) + 2 * R * steps_exec
+                 + R * int(st.walk_steps) + 64 * int(st.verified_queries))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     value = world * nq / (kernel_ms * 1e-3)
     out = {
@@ -395,7 +398,8 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": workload_name(args), "queries_per_gpu": nq,
                    "l2": "inputs larger than L2: 1.55 GB rank records accessed at random, 375 MB of queries",
                    "index_image_bytes": int(info.image_bytes), "rank_record_bytes": R,
-                   "lf_steps_per_step": steps_exec, "step_ms_min_median_max": [round(min(step_ms), 3),
+                   "lf_steps_per_step": steps_exec, "verified_queries_per_step": int(st.verified_queries),
+                   "verify_walk_steps_per_step": int(st.walk_steps), "step_ms_min_median_max": [round(min(step_ms), 3),
                                                                             round(statistics.median(step_ms), 3),
                                                                             round(max(step_ms), 3)],
                    "launches_per_step": "k_query_keys + cub radix sort (suffix order) + k_search", "setup_s": {"data": round(t_data, 2), "index_build": round(t_build, 2),
@@ -404,9 +408,9 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": world * nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * m,
                 "d2h_bytes_per_step": nq * 8, "ms_per_step": e2e_ms, "kernel_ms_inside": st.kernel_ms_search,
                 "gpu_launches_per_step": int(st.kernel_launches)},
-        "gpu_launches": args.steps,
+        "gpu_launches": 2 * args.steps,  # k_query_keys + k_search per step (+ 6 cub radix-sort kernels)
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_search<K32>",
+                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "rank_queries_per_s": 2 * steps_exec / (kernel_ms * 1e-3)},
         "cpu_baseline": cpu,

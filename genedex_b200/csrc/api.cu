@@ -61,8 +61,9 @@ uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 
 // Random 32 B record reads: ask the L2 to fetch single sectors from DRAM instead of sector pairs
 // (cudaLimitMaxL2FetchGranularity is a per-context hint).  GDX_L2_FETCH_GRANULARITY=0 leaves the
-// driver default, 32/64/128 sets it.  Applied once per device, with that device current.
-void apply_l2_fetch_granularity(int dev) {
+// driver default, 32/64/128 sets it (measured: no effect on B200, profiles/r1_ab_l2_fetch_granularity.txt).
+// Applied once per device, with that device current.
+void apply_device_settings(int dev) {
     static std::mutex mu;
     static bool done[64] = {};
     if (dev < 0 || dev >= 64) return;
@@ -72,6 +73,13 @@ void apply_l2_fetch_granularity(int dev) {
     const char *env = getenv("GDX_L2_FETCH_GRANULARITY");
     const int want = env ? atoi(env) : 32;
     if (want > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
+    // the device-resident entry points take their scratch from the stream-ordered pool: keep freed
+    // blocks cached across synchronisation points instead of returning them to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
 }
 
 struct DeviceGuard {
@@ -82,7 +90,7 @@ struct DeviceGuard {
         if (dev >= 0 && dev != prev) {
             if (cudaSetDevice(dev) != cudaSuccess) return;
         }
-        apply_l2_fetch_granularity(dev >= 0 ? dev : prev);
+        apply_device_settings(dev >= 0 ? dev : prev);
         ok = true;
     }
     ~DeviceGuard() {
