@@ -18,3 +18,12 @@ for i in range(4):
     t0 = time.perf_counter()
     idx.count_many_packed(qn, None, args.query_len, args.queries, out=cn)
     print("call", i, "ms", (time.perf_counter() - t0) * 1e3, file=sys.stderr)
+print("---- locate", file=sys.stderr)
+hit_off = torch.empty(args.queries + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+for i in range(4):
+    t0 = time.perf_counter()
+    _, hits, release = idx.locate_many_view(qn, None, args.query_len, args.queries, hit_offsets=hit_off)
+    t1 = time.perf_counter()
+    release()
+    st = idx.stats()
+    print("locate call", i, "ms", (t1 - t0) * 1e3, "kernel_ms_locate", st.kernel_ms_locate, "search", st.kernel_ms_search, file=sys.stderr)
