@@ -141,6 +141,11 @@ constexpr uint64_t kChunkMaxQueries = 64ull << 20;
 struct Slot {
     cudaStream_t stream = nullptr;
     DBuf bytes, offsets, out_a, out_b, sort;
+    // pipelined locate: per-chunk CSR + rows + hits
+    DBuf counts, local_off, scan_tmp, rows, hits, big;
+    uint64_t *d_words = nullptr;  // device: [0] number of wide intervals, [1] worklist cursor
+    uint64_t *h_words = nullptr;  // pinned: [0] hits of the chunk, [1] number of wide intervals
+    cudaEvent_t ev_total = nullptr;
     std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
     size_t ev_used = 0;
 };
@@ -157,8 +162,12 @@ struct Workspace {
     DBuf starts, ends, counts, hit_offsets, rows, big_list, hits, scan_tmp, symbols;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     bool init() {
-        for (auto &s : slot)
+        for (auto &s : slot) {
             if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+            if (cudaMalloc(&s.d_words, 4 * sizeof(uint64_t)) != cudaSuccess) return false;
+            if (cudaMallocHost(&s.h_words, 4 * sizeof(uint64_t)) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&s.ev_total, cudaEventDisableTiming) != cudaSuccess) return false;
+        }
         if (cudaMallocHost(&small.h, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
         if (cudaMalloc(&small.d, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
         if (cudaEventCreate(&ev_a) != cudaSuccess || cudaEventCreate(&ev_b) != cudaSuccess) return false;
@@ -172,6 +181,10 @@ struct Workspace {
             s.out_a.release();
             s.out_b.release();
             s.sort.release();
+            for (DBuf *b : {&s.counts, &s.local_off, &s.scan_tmp, &s.rows, &s.hits, &s.big}) b->release();
+            if (s.d_words) cudaFree(s.d_words);
+            if (s.h_words) cudaFreeHost(s.h_words);
+            if (s.ev_total) cudaEventDestroy(s.ev_total);
             for (auto e : s.ev) cudaEventDestroy(e);
         }
         if (small.h) cudaFreeHost(small.h);
@@ -955,10 +968,118 @@ uint64_t query_bytes_end(const gdx_queries *q, uint64_t i) {
     return q->offsets ? q->offsets[i] : i * q->fixed_len;
 }
 
+gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out, uint64_t *cap_out);
+void release_pinned_hits(const gdx_index *idx, void *p);
+
+// State of a pipelined gdx_locate_many: every chunk of the search pipeline continues, on its own
+// stream, with counts -> scan -> expand -> walk -> D2H of its hits, so that the locate kernels and the
+// hit copies of chunk k overlap the query upload of the later chunks.
+struct LocatePipe {
+    const gdx_index *idx;
+    Workspace *ws;
+    uint64_t *hit_offsets;  // caller's array, nq + 1 entries
+    void *pinned = nullptr; // library-owned pinned hit buffer (grows)
+    uint64_t pinned_cap = 0;
+    uint64_t total = 0;     // hits of all finished chunks
+    uint64_t walk_launches = 0;
+    struct Pending {
+        int slot;
+        uint64_t q0, cq;
+        bool valid = false;
+    } pending;
+
+    // after k_search(mode 2) of a chunk: widths, exclusive scan, totals to the host
+    gdx_status stage_counts(Slot &sl, int slot, uint64_t q0, uint64_t cq) {
+        CUDA_TRY(sl.counts.reserve((cq + 1) * 8));
+        CUDA_TRY(sl.local_off.reserve((cq + 1) * 8));
+        CUDA_TRY(cudaMemsetAsync(sl.d_words, 0, 4 * sizeof(uint64_t), sl.stream));
+        CUDA_TRY(cudaMemsetAsync(sl.counts.as<uint64_t>() + cq, 0, 8, sl.stream));
+        k_interval_counts<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(
+            sl.out_a.as<uint64_t>(), sl.out_b.as<uint64_t>(), cq, sl.counts.as<uint64_t>(),
+            reinterpret_cast<unsigned long long *>(sl.d_words));
+        size_t tmp = 0;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, sl.counts.as<uint64_t>(), sl.local_off.as<uint64_t>(),
+                                               cq + 1, sl.stream));
+        CUDA_TRY(sl.scan_tmp.reserve(tmp));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(sl.scan_tmp.p, tmp, sl.counts.as<uint64_t>(),
+                                               sl.local_off.as<uint64_t>(), cq + 1, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.h_words, sl.local_off.as<uint64_t>() + cq, 8, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaMemcpyAsync(sl.h_words + 1, sl.d_words, 8, cudaMemcpyDeviceToHost, sl.stream));
+        CUDA_TRY(cudaEventRecord(sl.ev_total, sl.stream));
+        pending = Pending{slot, q0, cq, true};
+        t_stats.kernel_launches += 2;
+        return GDX_OK;
+    }
+
+    Pending take_pending() {
+        Pending p = pending;
+        pending.valid = false;
+        return p;
+    }
+
+    // once the chunk's number of hits is known: expand, walk, copy hits + global offsets out
+    gdx_status finish(const Pending &p) {
+        if (!p.valid) return GDX_OK;
+        Slot &sl = ws->slot[p.slot];
+        const uint64_t cq = p.cq, q0 = p.q0;
+        CUDA_TRY(cudaEventSynchronize(sl.ev_total));
+        const uint64_t n_hits = sl.h_words[0], nbig = sl.h_words[1], base = total;
+        if (n_hits) {
+            if ((base + n_hits) * sizeof(gdx_hit) > pinned_cap) {  // grow the pinned result buffer (rare)
+                for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(ws->slot[s2].stream));
+                void *bigger = nullptr;
+                uint64_t cap = 0;
+                GDX_TRY(acquire_pinned_hits(idx, 2 * (base + n_hits) * sizeof(gdx_hit), &bigger, &cap));
+                if (pinned) {
+                    memcpy(bigger, pinned, base * sizeof(gdx_hit));
+                    release_pinned_hits(idx, pinned);
+                }
+                pinned = bigger;
+                pinned_cap = cap;
+            }
+            size_t free_b = 0, total_b = 0;
+            if (n_hits * 24 > sl.rows.cap + sl.hits.cap) {
+                CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+                if (n_hits * 24 > free_b + sl.rows.cap + sl.hits.cap)
+                    return fail(GDX_ERR_OOM, "%llu hits of one chunk do not fit into device memory; split the batch",
+                                (unsigned long long)n_hits);
+            }
+            CUDA_TRY(sl.rows.reserve(n_hits * 8));
+            CUDA_TRY(sl.hits.reserve(n_hits * 16));
+            CUDA_TRY(sl.big.reserve((nbig + 1) * 8));
+            k_expand_rows<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(
+                sl.out_a.as<uint64_t>(), sl.out_b.as<uint64_t>(), sl.local_off.as<uint64_t>(), cq,
+                sl.rows.as<uint64_t>(), sl.big.as<uint64_t>(), reinterpret_cast<unsigned long long *>(sl.d_words + 1));
+            if (nbig) {
+                dim3 grid((unsigned)nbig, 32);
+                k_expand_big_rows<<<grid, 256, 0, sl.stream>>>(sl.out_a.as<uint64_t>(), sl.out_b.as<uint64_t>(),
+                                                               sl.local_off.as<uint64_t>(), sl.big.as<uint64_t>(),
+                                                               sl.rows.as<uint64_t>());
+            }
+            unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 5);
+            GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+                k_locate_walk<decltype(L)><<<(unsigned)div_up(n_hits, 256), 256, 0, sl.stream>>>(
+                    idx->dev, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk);
+                return GDX_OK;
+            }));
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync((gdx_hit *)pinned + base, sl.hits.p, n_hits * sizeof(gdx_hit),
+                                     cudaMemcpyDeviceToHost, sl.stream));
+            t_stats.kernel_launches += 2 + (nbig ? 1 : 0);
+        }
+        k_add_base<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.local_off.as<uint64_t>(), cq, base);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(hit_offsets + q0, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+        t_stats.kernel_launches += 1;
+        total += n_hits;
+        return GDX_OK;
+    }
+};
+
 // Chunked pipeline over kSlots streams: H2D(query bytes) -> k_search -> D2H(results) per chunk.
 // If dev_a/dev_b are given the results stay on the device (locate path) and nothing is copied back.
 gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *qs, uint64_t *out_a,
-                       uint64_t *out_b, int mode, uint64_t *dev_a, uint64_t *dev_b) {
+                       uint64_t *out_b, int mode, uint64_t *dev_a, uint64_t *dev_b, LocatePipe *lp = nullptr) {
     const uint64_t nq = qs->nq;
     for (int s = 0; s < kSlots; ++s) ws->slot[s].ev_used = 0;
     CUDA_TRY(cudaMemset(ws->small.d, 0xff, 4 * sizeof(uint64_t)));
@@ -998,7 +1119,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         // growing a slot buffer frees the old one: only safe once the slot's stream has drained
         const SortPlan sp = plan_sort(idx, cq);
         if (sl.bytes.cap < byte1 - byte0 + 16 || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
-            (!dev_a && (sl.out_a.cap < cq * 8 || (mode == 0 && sl.out_b.cap < cq * 8))) ||
+            (!dev_a && (sl.out_a.cap < cq * 8 || ((mode == 0 || lp) && sl.out_b.cap < cq * 8))) ||
             (sp.use && sl.sort.cap < sp.total_bytes))
             CUDA_TRY(cudaStreamSynchronize(sl.stream));
         CUDA_TRY(sl.bytes.reserve(byte1 - byte0 + 16));
@@ -1031,7 +1152,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             CUDA_TRY(sl.out_a.reserve(cq * 8));
             a = sl.out_a.as<uint64_t>();
             b = nullptr;
-            if (mode == 0) {
+            if (mode == 0 || lp) {
                 CUDA_TRY(sl.out_b.reserve(cq * 8));
                 b = sl.out_b.as<uint64_t>();
             }
@@ -1052,7 +1173,11 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         GDX_TRY(st);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(e1, sl.stream));
-        if (!dev_a) {
+        if (lp) {  // locate continues per chunk; the previous chunk is finished while this one runs
+            const LocatePipe::Pending prev = lp->take_pending();
+            GDX_TRY(lp->stage_counts(sl, k % kSlots, q0, cq));
+            GDX_TRY(lp->finish(prev));
+        } else if (!dev_a) {
             CUDA_TRY(cudaMemcpyAsync(out_a + q0, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
             if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
@@ -1064,6 +1189,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         q0 = q1;
         ++k;
     }
+    if (lp) GDX_TRY(lp->finish(lp->take_pending()));
     const double t_issue = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count() : 0;
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(ws->slot[s].stream));
     if (trace && !trace_rows.empty()) {
@@ -1172,7 +1298,13 @@ gdx_status locate_device_intervals(const gdx_index *idx, Workspace *ws, const ui
     return GDX_OK;
 }
 
-gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out) {
+void release_pinned_hits(const gdx_index *idx, void *p) {
+    std::lock_guard<std::mutex> lk(idx->mu);
+    for (auto &b : idx->pinned)
+        if (b.p == p) b.in_use = false;
+}
+
+gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out, uint64_t *cap_out = nullptr) {
     std::lock_guard<std::mutex> lk(idx->mu);
     PinnedHits *best = nullptr;
     for (auto &p : idx->pinned)
@@ -1199,6 +1331,7 @@ gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out)
     }
     best->in_use = true;
     *out = best->p;
+    if (cap_out) *cap_out = best->cap;
     return GDX_OK;
 }
 
@@ -1256,6 +1389,23 @@ extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *q
     Workspace *ws = lease.w;
     if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
     const uint64_t n = queries->nq;
+    static const bool pipelined = !(getenv("GDX_LOCATE_PIPELINE") && atoi(getenv("GDX_LOCATE_PIPELINE")) == 0);
+    if (pipelined) {
+        // every chunk of the search pipeline carries on with counts -> scan -> expand -> walk -> D2H
+        LocatePipe lp{idx, ws, hit_offsets};
+        GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * sizeof(gdx_hit), &lp.pinned, &lp.pinned_cap));
+        gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 2, nullptr, nullptr, &lp);
+        if (st != GDX_OK) {
+            for (int s2 = 0; s2 < kSlots; ++s2) cudaStreamSynchronize(ws->slot[s2].stream);
+            release_pinned_hits(idx, lp.pinned);
+            return st;
+        }
+        hit_offsets[n] = lp.total;
+        t_stats.hits = lp.total;
+        *hits = (gdx_hit *)lp.pinned;
+        *num_hits = lp.total;
+        return GDX_OK;
+    }
     // a buffer may only be replaced once nothing in flight uses it: every call ends synchronized
     CUDA_TRY(ws->starts.reserve((n + 1) * 8));
     CUDA_TRY(ws->ends.reserve((n + 1) * 8));

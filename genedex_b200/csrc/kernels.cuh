@@ -459,6 +459,12 @@ __global__ void k_expand_rows(const uint64_t *__restrict__ starts, const uint64_
     for (uint64_t j = 0; j < cnt; ++j) rows[off + j] = s + j;
 }
 
+// chunk-local CSR offsets -> global ones (pipelined locate)
+__global__ void k_add_base(uint64_t *__restrict__ offsets, uint64_t n, uint64_t base) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) offsets[q] += base;
+}
+
 // one CTA per wide interval, coalesced fill
 __global__ void k_expand_big_rows(const uint64_t *__restrict__ starts, const uint64_t *__restrict__ ends,
                                   const uint64_t *__restrict__ hit_offsets,
