@@ -107,47 +107,62 @@ def sample_queries_on_device(text, nq, m, seed, device):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every 5 ms in a thread; falls
+    back to `nvidia-smi -lms` when pynvml is unavailable)."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.samples = []
-        self.proc = None
+        self.samples = []  # (time, sm_mhz, reasons bitmask)
         self.gpu_index = gpu_index
+        self.stop_flag = False
+        self.thread = None
+        self.sm_max = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[0].isdigit() else self.gpu_index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.samples.append((time.time(), line.strip()))
+            def pump():
+                while not self.stop_flag:
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.time(), float(mhz), int(reasons)))
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self.thread = threading.Thread(target=pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.thread = None
 
     def stop(self, t0, t1):
-        if self.proc:
-            self.proc.terminate()
-        sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.samples:
-            if not (t0 - 0.15 <= t <= t1 + 0.15):
-                continue
-            parts = [p.strip() for p in line.split(",")]
-            try:
-                sm.append(float(parts[0]))
-                smax = max(smax, float(parts[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, parts[3:7]):
-                if v == "Active":
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        sel = [(m, r) for t, m, r in self.samples if t0 <= t <= t1]
+        reasons = sorted(name for name, bit in self.BAD.items() if any(r & bit for _, r in sel))
+        return {"sm_mhz": statistics.median([m for m, _ in sel]) if sel else None, "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(sel)}
+
+
+def ncu_traffic_bytes(args, verified):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch from the committed ncu --set full
+    capture (profiles/r1_k_search*.txt); only meaningful for the default workload it was taken on."""
+    default = (args.text_len == 3_100_000_000 and args.queries == 7_500_000 and args.query_len == 50
+               and args.lookup_depth == 0 and args.sampling_rate == 4)
+    if not default:
+        return None
+    return 12.336579e9 + 0.235466e9 if verified else 37.914386e9 + 0.241442e9
 
 
 def measured_peak_gbs():
@@ -410,7 +425,7 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches_per_step": int(st.kernel_launches)},
         "gpu_launches": 2 * args.steps,  # k_query_keys + k_search per step (+ 6 cub radix-sort kernels)
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_kind": peak_kind, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
+                     "traffic": ncu_traffic_bytes(args, st.verified_queries > 0), "peak_kind": peak_kind, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "rank_queries_per_s": 2 * steps_exec / (kernel_ms * 1e-3)},
         "cpu_baseline": cpu,

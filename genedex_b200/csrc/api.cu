@@ -960,6 +960,8 @@ gdx_status sort_queries(const gdx_index *idx, const DevQueries &dq, const SortPl
 
 gdx_status check_queries(const gdx_queries *q) {
     if (!q) return fail(GDX_ERR_BAD_ARG, "queries is NULL");
+    if (q->offsets && q->nq && q->offsets[q->nq] < q->offsets[0])
+        return fail(GDX_ERR_BAD_ARG, "queries->offsets must be non-decreasing");
     if (q->nq && !q->offsets && q->fixed_len && !q->bytes) return fail(GDX_ERR_BAD_ARG, "queries->bytes is NULL");
     return GDX_OK;
 }
