@@ -341,13 +341,32 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         uint64_t s = 0, e = 0;
         if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
 
-        // K2: batch_computed_cursors.rs:62-70.  A lane whose interval has narrowed to one row leaves the
-        // loop early and idles until the warp reconverges behind it: the verification below then runs
-        // once per warp with all such lanes active instead of once per lane.
-        bool direct = false, verify = false;
+        // K2: batch_computed_cursors.rs:62-70.  The verification runs inline, as soon as a lane's interval
+        // has one row: its dependent DRAM fetches then overlap the LF steps of the other lanes of the warp
+        // (deferring it behind the loop so that it runs once per warp was measured 22 % slower).
+        bool direct = false;
         while (!bad && pos > 0 && s != e) {
             if (VERIFY && e - s == 1 && pos >= kVerifyMinRemaining) {
-                verify = true;
+                // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
+                const uint64_t at = resolve_row<L>(ix, s, vsteps);
+                vrows = 1;
+                bool match = true;
+                for (uint64_t j = pos; match && j-- > 0;) {
+                    const uint32_t c = GDX_SYMBOL_AT(j);
+                    if (c == 0) {  // the reference reaches this symbol with a non-empty interval
+                        bad = true;
+                        break;
+                    }
+                    const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
+                    match = back <= at && text_symbol(ix, at - back) == c;
+                }
+                if (match && !bad) {
+                    direct = true;
+                    s = at - pos;  // text position of the whole query
+                    e = s + 1;
+                } else {
+                    s = e = 0;
+                }
                 break;
             }
             const uint32_t c = GDX_SYMBOL_AT(pos - 1);
@@ -358,28 +377,6 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             lf_pair<L>(ix, c, s, e);
             --pos;
             ++steps;
-        }
-        if (VERIFY && verify) {
-            // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos) with the text
-            const uint64_t at = resolve_row<L>(ix, s, vsteps);
-            vrows = 1;
-            bool match = true;
-            for (uint64_t j = pos; match && j-- > 0;) {
-                const uint32_t c = GDX_SYMBOL_AT(j);
-                if (c == 0) {  // the reference reaches this symbol with a non-empty interval
-                    bad = true;
-                    break;
-                }
-                const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
-                match = back <= at && text_symbol(ix, at - back) == c;
-            }
-            if (match && !bad) {
-                direct = true;
-                s = at - pos;  // text position of the whole query
-                e = s + 1;
-            } else {
-                s = e = 0;
-            }
         }
         if (bad) {
             report_error(err, q_index_base + q);
