@@ -194,3 +194,32 @@ def test_cpp_mirror_compiles_and_links(tmp_path):
     # include/genedex_b200.hpp mirrors the crate's interface for C++ hosts; it must compile against
     # the header and link against the library (running it needs a GPU: tests/test_gpu_parity.py)
     assert os.path.exists(build_cpp_api_test(tmp_path))
+
+
+def test_c_abi_argument_errors_never_crash(gdx):
+    """Return codes instead of unwinding across the FFI: argument errors are reported before
+    any device work, so they can be checked without a GPU."""
+    L = gdx._lib
+    lib = L.load()
+    h = C.c_void_p()
+    alph = gdx.index._alphabet_struct(gdx.alphabet.ascii_dna())
+    cfg = L.gdx_config(L.GDX_I32, 4, 0, 1, L.GDX_CONSTRUCT_HOST, -1, 0)
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)
+    offs = np.array([0, 4], dtype=np.uint64)
+    assert lib.gdx_index_build(text.ctypes.data, offs.ctypes.data, 1, C.byref(alph), C.byref(cfg), None) == L.GDX_ERR_BAD_ARG
+    assert lib.gdx_index_build(text.ctypes.data, offs.ctypes.data, 0, C.byref(alph), C.byref(cfg), C.byref(h)) == L.GDX_ERR_BAD_ARG
+    assert b"at least one text" in lib.gdx_last_error_message()
+    cfg0 = L.gdx_config(L.GDX_I32, 0, 0, 1, L.GDX_CONSTRUCT_HOST, -1, 0)  # config.rs:28
+    assert lib.gdx_index_build(text.ctypes.data, offs.ctypes.data, 1, C.byref(alph), C.byref(cfg0), C.byref(h)) == L.GDX_ERR_BAD_ARG
+    bad = L.gdx_alphabet()
+    bad.num_dense_symbols, bad.num_searchable_dense_symbols = 1, 1  # alphabet.rs:166-170
+    assert lib.gdx_index_build(text.ctypes.data, offs.ctypes.data, 1, C.byref(bad), C.byref(cfg), C.byref(h)) == L.GDX_ERR_BAD_ARG
+    q = L.gdx_queries(text.ctypes.data, None, 2, 2)
+    out = np.zeros(2, dtype=np.uint64)
+    assert lib.gdx_count_many(None, C.byref(q), out.ctypes.data) == L.GDX_ERR_BAD_ARG
+    assert lib.gdx_get_stats(None) == L.GDX_ERR_BAD_ARG
+    assert lib.gdx_index_get_info(None, None) == L.GDX_ERR_BAD_ARG
+    hdr = (C.c_uint8 * lib.gdx_index_header_bytes())()
+    assert lib.gdx_index_adopt_image(hdr, C.c_void_p(4096), -1, 0, C.byref(h)) == L.GDX_ERR_BAD_ARG  # bad magic
+    lib.gdx_index_destroy(None)  # no-op
+    lib.gdx_free_hits(None, None)
