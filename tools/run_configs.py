@@ -149,7 +149,7 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
         assert int(counts[:n_orig].min()) >= 1, f"{name}: a query sampled from the text has count 0"
 
     if locate:
-        hit_off = np.empty(nq + 1, dtype=np.uint64)
+        hit_off = torch.empty(nq + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
         for _ in range(2):
             _, hits, release = pidx.locate_many_view(q_np, None, m, nq, hit_offsets=hit_off)
             release()
