@@ -83,6 +83,8 @@ PROTOTYPES = {
     "gdx_index_download_text_borders": (C.c_int, [_vp, _vp, _vp]),
     "gdx_index_destroy": (None, [_vp]),
     "gdx_index_get_info": (C.c_int, [_vp, _P(gdx_index_info)]),
+    "gdx_index_save_to_file": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
+    "gdx_index_load_from_file": (C.c_int, [C.c_char_p, _i32, _P(_vp), _vp, _u64, _P(_u64)]),
     "gdx_index_header_bytes": (_u64, []),
     "gdx_index_export": (C.c_int, [_vp, _vp, _P(_vp), _P(_u64)]),
     "gdx_index_adopt_image": (C.c_int, [_vp, _vp, _i32, _i32, _P(_vp)]),

@@ -824,6 +824,89 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
 }
 
 // ================================================================================================
+// index files
+// ================================================================================================
+namespace {
+constexpr char kFileMagic[8] = {'G', 'D', 'X', 'F', 'I', 'L', 'E', '1'};
+struct FilePrefix {
+    char magic[8];
+    uint64_t header_bytes, image_bytes, user_bytes;
+};
+struct FileCloser {
+    FILE *f;
+    ~FileCloser() {
+        if (f) fclose(f);
+    }
+};
+}  // namespace
+
+extern "C" gdx_status gdx_index_save_to_file(const gdx_index *idx, const char *path, const void *user_data,
+                                             uint64_t user_bytes) {
+    if (!idx || !path || (user_bytes && !user_data)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    FileCloser fc{fopen(path, "wb")};
+    if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s for writing", path);
+    FilePrefix p;
+    memcpy(p.magic, kFileMagic, 8);
+    p.header_bytes = sizeof(ImageHeader);
+    p.image_bytes = idx->h.image_bytes;
+    p.user_bytes = user_bytes;
+    if (fwrite(&p, sizeof p, 1, fc.f) != 1 || fwrite(&idx->h, sizeof(ImageHeader), 1, fc.f) != 1 ||
+        (user_bytes && fwrite(user_data, user_bytes, 1, fc.f) != 1))
+        return fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
+    const uint64_t chunk = 64ull << 20;
+    void *stage = nullptr;
+    CUDA_TRY(cudaMallocHost(&stage, chunk));
+    gdx_status st = GDX_OK;
+    for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
+        const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
+        cudaError_t e = cudaMemcpy(stage, (const uint8_t *)idx->image + off, nb, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) st = fail(GDX_ERR_CUDA, "image download failed: %s", cudaGetErrorString(e));
+        else if (fwrite(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
+    }
+    cudaFreeHost(stage);
+    return st;
+}
+
+extern "C" gdx_status gdx_index_load_from_file(const char *path, int32_t device_req, gdx_index **out,
+                                               void *user_data_out, uint64_t user_capacity, uint64_t *user_bytes_out) {
+    if (!path || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    *out = nullptr;
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s", path);
+    FilePrefix p;
+    ImageHeader h;
+    if (fread(&p, sizeof p, 1, fc.f) != 1 || memcmp(p.magic, kFileMagic, 8) != 0 || p.header_bytes != sizeof(ImageHeader) ||
+        fread(&h, sizeof h, 1, fc.f) != 1 || h.magic != kImageMagic || h.version != GDX_ABI_VERSION ||
+        h.image_bytes != p.image_bytes)
+        return fail(GDX_ERR_BAD_ARG, "%s is not a genedex_b200 index file of this version", path);
+    if (user_bytes_out) *user_bytes_out = p.user_bytes;
+    if (p.user_bytes) {
+        std::vector<uint8_t> blob(p.user_bytes);
+        if (fread(blob.data(), p.user_bytes, 1, fc.f) != 1) return fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
+        if (user_data_out) memcpy(user_data_out, blob.data(), std::min<uint64_t>(p.user_bytes, user_capacity));
+    }
+    int device;
+    GDX_TRY(resolve_device(device_req, &device));
+    DeviceGuard guard(device);
+    void *image = nullptr, *stage = nullptr;
+    CUDA_TRY(cudaMalloc(&image, p.image_bytes ? p.image_bytes : 1));
+    const uint64_t chunk = 64ull << 20;
+    cudaError_t e = cudaMallocHost(&stage, chunk);
+    gdx_status st = e == cudaSuccess ? GDX_OK : fail(GDX_ERR_OOM, "pinned staging allocation failed");
+    for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
+        const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
+        if (fread(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
+        else if ((e = cudaMemcpy((uint8_t *)image + off, stage, nb, cudaMemcpyHostToDevice)) != cudaSuccess)
+            st = fail(GDX_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+    }
+    if (stage) cudaFreeHost(stage);
+    if (st == GDX_OK) st = gdx_index_adopt_image(&h, image, device, 1, out);
+    if (st != GDX_OK) cudaFree(image);
+    return st;
+}
+
+// ================================================================================================
 // replication
 // ================================================================================================
 extern "C" uint64_t gdx_index_header_bytes(void) { return sizeof(ImageHeader); }

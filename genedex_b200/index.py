@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import os
 from dataclasses import dataclass
 from typing import Iterable, Sequence
 
@@ -171,6 +172,26 @@ class FmIndex:
 
     def total_text_len(self) -> int:
         return int(self.info().text_len)
+
+    # -- index files, lib.rs:296-327 (own container format, not savefile-compatible: DESIGN.md)
+    def save_to_file(self, filepath) -> None:
+        a = self._alphabet
+        blob = bytes([a._not_searchable]) + a._dense_to_io
+        _check(self._lib.gdx_index_save_to_file(self._h, os.fsencode(filepath), blob, len(blob)))
+
+    @classmethod
+    def load_from_file(cls, filepath, device: int = -1) -> "FmIndex":
+        lib = _lib.load()
+        h, nbytes = C.c_void_p(), C.c_uint64()
+        blob = (C.c_uint8 * 512)()
+        _check(lib.gdx_index_load_from_file(os.fsencode(filepath), device, C.byref(h), blob, 512, C.byref(nbytes)))
+        idx = cls(h, None)
+        hdr = (C.c_uint8 * lib.gdx_index_header_bytes())()
+        _check(lib.gdx_index_export(h, hdr, None, None))
+        raw = bytes(blob[: nbytes.value])
+        io_to_dense = bytes(hdr)[-256:]  # last field of the image header
+        idx._alphabet = Alphabet(io_to_dense, raw[1:], raw[0])
+        return idx
 
     # -- packed (numpy) forms: the zero-copy entry points the list forms are built on
     def cursors_many_packed(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,

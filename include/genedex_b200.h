@@ -185,6 +185,16 @@ gdx_status gdx_index_download_text_borders(const gdx_index *idx, uint64_t *rows_
 void gdx_index_destroy(gdx_index *idx);
 gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);
 
+/* ---- index files: FmIndex::save_to_file / load_from_file (src/lib.rs:296-327) -------------------------
+ * The crate serialises its host structs with the `savefile` crate (schema version 0); that byte format
+ * is owned by an un-vendored dependency and no reference test pins it, so this is an own versioned
+ * container (magic "GDXFILE1" + image header + device image + caller blob), NOT savefile-compatible.
+ * `user_data` is an opaque blob of the host language binding (e.g. the alphabet's dense->io table). */
+gdx_status gdx_index_save_to_file(const gdx_index *idx, const char *path, const void *user_data,
+                                  uint64_t user_bytes);
+gdx_status gdx_index_load_from_file(const char *path, int32_t device, gdx_index **out, void *user_data_out,
+                                    uint64_t user_capacity, uint64_t *user_bytes_out);
+
 /* ---- replication (no counterpart in the reference) ----------------------------------
  * The device image is one contiguous allocation described by an opaque POD header.  A replica on
  * another GPU (or in another process) is made by copying header + image bytes, e.g. with one

@@ -491,3 +491,26 @@ def test_text_verification_shortcut_semantics(gdx):
                 continue
             assert pidx.count_many([q]) == want
             assert [[(h.text_id, h.position) for h in hs] for hs in pidx.locate_many([q])] == oidx.locate_many([q])
+
+
+def test_save_and_load_index_file(gdx, tmp_path):
+    # FmIndex::save_to_file / load_from_file (lib.rs:296-327); own container, round trip must be lossless
+    rng = random.Random(21)
+    oa = util.oracle_alphabet("ascii_dna_iupac_as_dna_with_n")
+    texts = util.random_texts(rng, oa, 3, 5000)
+    oidx, pidx = util.build_pair(gdx, texts, "ascii_dna_iupac_as_dna_with_n", "u32", 4, 3)
+    path = tmp_path / "index.gdx"
+    pidx.save_to_file(path)
+    loaded = gdx.FmIndex.load_from_file(path)
+    assert loaded.alphabet() == pidx.alphabet()
+    assert loaded.total_text_len() == pidx.total_text_len() and loaded.num_texts() == 3
+    qs = util.random_queries(rng, oa, texts, 200, 100, 40, searchable_only=True)
+    util.assert_same_results(oidx, loaded, qs)
+    bad = tmp_path / "bad.gdx"
+    bad.write_bytes(b"NOTANIDX" + path.read_bytes()[8:4096])
+    with pytest.raises(gdx.GenedexError):
+        gdx.FmIndex.load_from_file(bad)
+    trunc = tmp_path / "trunc.gdx"
+    trunc.write_bytes(path.read_bytes()[:-100])
+    with pytest.raises(gdx.GenedexError):
+        gdx.FmIndex.load_from_file(trunc)
