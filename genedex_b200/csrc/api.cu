@@ -360,6 +360,20 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     return GDX_OK;
 }
 
+// L2 eviction policy values for the kernels (GDX_L2_HINTS=0 disables them)
+gdx_status init_policies(gdx_index *idx) {
+    const char *e = getenv("GDX_L2_HINTS");
+    if (e && atoi(e) == 0) return GDX_OK;
+    uint64_t *d = nullptr, h = 0;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    k_make_policies<<<1, 1>>>(d);
+    cudaError_t ce = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (ce != cudaSuccess) return fail(GDX_ERR_CUDA, "createpolicy failed: %s", cudaGetErrorString(ce));
+    idx->dev.pol_evict_first = h;
+    return GDX_OK;
+}
+
 gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
     std::unique_ptr<gdx_index> idx(new gdx_index());
     GDX_TRY(plan_header(src, idx->h));
@@ -440,6 +454,10 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
     }
 
     idx->dev = make_dev_index(h, idx->image);
+    {
+        gdx_status ps = init_policies(idx.get());
+        if (ps != GDX_OK) return cleanup(ps);
+    }
 
     // lookup tables: level 0 = [(0, n)] (lookup_table.rs:205-209), level d from level d-1
     {
@@ -936,6 +954,14 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
     idx->own_image = own_image != 0;
     idx->device = device;
     idx->dev = make_dev_index(h, device_image);
+    {
+        DeviceGuard guard(device);
+        gdx_status st = init_policies(idx);
+        if (st != GDX_OK) {
+            delete idx;
+            return st;
+        }
+    }
     *out = idx;
     return GDX_OK;
 }

@@ -63,6 +63,10 @@ struct DevIndex {
     uint32_t wide, noff, stride, derived_symbol;
     uint32_t sampling_shift;  // log2(sampling_rate) if it is a power of two, else 0xffffffff
     uint32_t text_bits;
+    // L2 eviction policies (createpolicy values made once per index on the device; 0 = no hints):
+    // records of one-row intervals, SA samples and text are touched once -> evict_first, so that they do
+    // not push the shared top of the search trie out of L2
+    uint64_t pol_evict_first;
     uint64_t lut_level_off[kMaxLookupDepth + 1];
     uint64_t lut_pow[kMaxLookupDepth + 1];
     uint8_t io_to_dense[256];
@@ -93,6 +97,7 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.stride = h.layout.stride;
     d.derived_symbol = h.layout.derived_symbol;
     d.sampling_shift = 0xffffffffu;
+    d.pol_evict_first = 0;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {
         uint32_t s = 0;
         while ((1u << s) < h.sampling_rate) ++s;

@@ -45,6 +45,28 @@ __device__ __forceinline__ void ldg256_na(const void *p, uint64_t w[4]) {
         : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
         : "l"(p));
 }
+// same with an L2 eviction policy (createpolicy value)
+__device__ __forceinline__ void ldg256_na_hint(const void *p, uint64_t w[4], uint64_t policy) {
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+        : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+        : "l"(p), "l"(policy));
+}
+__device__ __forceinline__ uint32_t ldg_u8_hint(const uint8_t *p, uint64_t policy) {
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+    return v;
+}
+__global__ void k_make_policies(uint64_t *out) {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    out[0] = p;
+}
+
 __device__ __forceinline__ void ldg128_na(const void *p, uint64_t &lo, uint64_t &hi) {
     asm("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
 }
@@ -67,6 +89,19 @@ struct K32 {
     static __device__ __forceinline__ Rec load(const DevIndex &ix, uint64_t i, uint32_t) {
         Rec r;
         ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        return r;
+    }
+    // a record that will not be needed again (one-row interval, locate walk)
+    static __device__ __forceinline__ Rec load_once(const DevIndex &ix, uint64_t i, uint32_t) {
+        Rec r;
+        if (ix.pol_evict_first) ldg256_na_hint(ix.records + ((i >> 6) << 5), r.w, ix.pol_evict_first);
+        else ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        return r;
+    }
+    static __device__ __forceinline__ Planes load_planes_once(const DevIndex &ix, uint64_t i) {
+        Planes r;
+        if (ix.pol_evict_first) ldg256_na_hint(ix.records + ((i >> 6) << 5), r.w, ix.pol_evict_first);
+        else ldg256_na(ix.records + ((i >> 6) << 5), r.w);
         return r;
     }
     static __device__ __forceinline__ Rec with_offset(const DevIndex &, const Planes &p, uint64_t,
@@ -124,6 +159,8 @@ struct KG {
         r.off = __ldg(reinterpret_cast<const uint16_t *>(p + 16 * B) + (c - 1));
         return r;
     }
+    static __device__ __forceinline__ Rec load_once(const DevIndex &ix, uint64_t i, uint32_t c) { return load(ix, i, c); }
+    static __device__ __forceinline__ Planes load_planes_once(const DevIndex &ix, uint64_t i) { return load_planes(ix, i); }
     static __device__ __forceinline__ Rec with_offset(const DevIndex &ix, const Planes &pl, uint64_t i,
                                                       uint32_t c) {
         Rec r;
@@ -158,7 +195,8 @@ __device__ __forceinline__ void lf_pair(const DevIndex &ix, uint32_t c, uint64_t
         return;
     }
     const bool same_block = (s >> L::kLog2P) == (e >> L::kLog2P);
-    typename L::Rec rs = L::load(ix, s, c);
+    // narrow intervals are private to this query: their records are streamed through L2 (evict first)
+    typename L::Rec rs = (same_block && e - s <= 2) ? L::load_once(ix, s, c) : L::load(ix, s, c);
     const uint64_t bs = sbc_load(ix, s, c);
     if (same_block) {
         const uint64_t ns = bs + L::local_rank(rs, c, s);
@@ -203,11 +241,11 @@ __device__ __forceinline__ uint64_t resolve_row(const DevIndex &ix, uint64_t i, 
                                                               : (i % ix.sampling_rate) == 0;
         if (sampled) {
             const uint64_t k = ix.sampling_shift != 0xffffffffu ? i >> ix.sampling_shift : i / ix.sampling_rate;
-            return (ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k)
-                            : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.samples) + k)) +
-                   steps;
+            if (ix.wide) return __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k) + steps;
+            const uint32_t *sp = reinterpret_cast<const uint32_t *>(ix.samples) + k;
+            return (uint64_t)(ix.pol_evict_first ? ldg_u32_hint(sp, ix.pol_evict_first) : __ldg(sp)) + steps;
         }
-        typename L::Planes pl = L::load_planes(ix, i);
+        typename L::Planes pl = L::load_planes_once(ix, i);
         const uint32_t c = L::symbol_at(pl, i);
         if (c == 0) {  // :121-126 text_border_lookup[&i]
             const uint64_t k = lower_bound_u64(ix.border_rows, ix.n_border, i);
@@ -226,7 +264,7 @@ __device__ __forceinline__ uint64_t resolve_row(const DevIndex &ix, uint64_t i, 
 // dense symbol at concatenated-text position p (text section of the image)
 __device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) {
     if (ix.text_bits == 4) return (__ldg(ix.text + (p >> 1)) >> ((p & 1) * 4)) & 15u;
-    return __ldg(ix.text + p);
+    return __ldg(ix.text + p);  // L1-allocating on purpose: the comparison walks consecutive bytes
 }
 
 // interval flag of the locate plumbing: start = resolved text position, end = kDirectHit
