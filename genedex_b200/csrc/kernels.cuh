@@ -1,22 +1,30 @@
 // kernels.cuh -- hand-written sm_100a kernels of the search path.
 //
+//   k_query_keys    sort key (last 16 symbols) of every query; cub radix sort then gives the order in
+//                   which threads pick queries, so that the top of the search trie is shared in L2
 //   k_search        K1+K2: lookup-table seed + backward search, one thread per query, both interval
 //                   borders' records in flight together      (batch_computed_cursors.rs:36-172,
 //                                                              lookup_table.rs:68-161, condensed.rs:137-341)
+//                   <.., VERIFY>: one-row intervals are finished by resolving SA[row] and comparing the
+//                   rest of the query with the text section (count / locate only, identical results)
 //   k_extend        one LF pair per cursor                   (cursor.rs:34-51)
-//   k_interval_counts / k_expand_rows / k_expand_big_rows    rows of every hit (CSR)
+//   k_interval_counts / k_expand_rows / k_expand_big_rows / k_add_base    rows of every hit (CSR)
 //   k_locate_walk   K3+K4: LF-walk to the next SA sample + text-id mapping, one thread per hit
 //                                                             (sampled_suffix_array.rs:110-138,
 //                                                              text_id_search_tree.rs:35-64)
 //   k_pack_*        BWT -> rank records (+ per-superblock totals)        (condensed.rs:59-124,365-415)
+//   k_pack_text     dense text -> 4/8-bit text section
 //   k_lut_fill      lookup level d from level d-1            (lookup_table.rs:163-258)
 //   k_planes_to_bwt reference bit planes -> dense BWT        (condensed.rs:343-362)
+//   k_records_to_bwt device records -> dense BWT (export)
 //   k_gather        random-gather ceiling microbenchmark     
 //
 // All hot loads are random sector accesses into HBM: there is no reuse to stage through shared
 // memory or TMA, so the design levers are (1) one aligned record per rank, fetched with a single
-// 256-bit LDG.NA (no L1 allocation, keeps L1 for the query bytes and the superblock table),
-// (2) both borders issued back to back, (3) enough resident warps to cover DRAM latency.
+// 256-bit LDG.NA (no L1 allocation, keeps L1 for the superblock table and the text comparison),
+// (2) both borders issued back to back, one fetch when they share a block, (3) enough resident warps
+// to keep the DRAM random-access rate saturated, (4) fewer random fetches per query: suffix-sorted
+// query order (L2 serves the first ~10 steps) and text verification (~16 LF steps instead of 50).
 #ifndef GDX_KERNELS_CUH
 #define GDX_KERNELS_CUH
 
@@ -208,13 +216,6 @@ __device__ __forceinline__ void lf_pair(const DevIndex &ix, uint32_t c, uint64_t
     const uint64_t be = sbc_load(ix, e, c);
     s = bs + L::local_rank(rs, c, s);
     e = be + L::local_rank(re, c, e);
-}
-
-template <class L>
-__device__ __forceinline__ uint64_t lf_one(const DevIndex &ix, uint32_t c, uint64_t i) {
-    if (c > ix.noff) return L::lf_derived(ix, i);
-    typename L::Rec r = L::load(ix, i, c);
-    return sbc_load(ix, i, c) + L::local_rank(r, c, i);
 }
 
 __device__ __forceinline__ void lut_load(const DevIndex &ix, uint64_t entry, uint64_t &s, uint64_t &e) {
