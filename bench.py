@@ -165,6 +165,30 @@ def ncu_traffic_bytes(args, verified):
     return 12.336579e9 + 0.235466e9 if verified else 37.914386e9 + 0.241442e9
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's host threads (and with them its pinned staging memory) to the NUMA node its GPU
+    hangs off: with 8 ranks streaming 375 MB batches concurrently, remote-socket host memory halves the
+    per-GPU PCIe rate.  Best effort; returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b2 = part.partition("-")
+            cpus.update(range(int(a), int(b2 or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak_gbs():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
@@ -252,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
     import genedex_b200 as gdx
     lib = gdx._lib.load()
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(dev)
     m, nq = args.query_len, args.queries
 
@@ -335,7 +360,13 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         pidx.count_many_packed(q_np, None, m, nq, out=counts_np)
     barrier()
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps)
+    e2e_ms_local = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max_over_ranks(e2e_ms_local)
+    e2e_ms_ranks = [e2e_ms_local]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (e2e_ms_local, numa_node))
+        e2e_ms_ranks = gathered
     t_region1 = time.time()
     st = pidx.stats()
     assert np.array_equal(counts_np, counts_device_path), "device-resident and host-buffer paths disagree"
@@ -421,7 +452,7 @@ def run_ours(args, rank, world, local_rank):
                                                                  "replicate": round(t_bcast, 2)}},
         "clocks": clock_info,
         "e2e": {"value": world * nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * m,
-                "d2h_bytes_per_step": nq * 8, "ms_per_step": e2e_ms, "kernel_ms_inside": st.kernel_ms_search,
+                "d2h_bytes_per_step": nq * 8, "ms_per_step": e2e_ms, "kernel_ms_inside": st.kernel_ms_search, "ms_per_step_by_rank_and_numa_node": e2e_ms_ranks,
                 "gpu_launches_per_step": int(st.kernel_launches)},
         "gpu_launches": 2 * args.steps,  # k_query_keys + k_search per step (+ 6 cub radix-sort kernels)
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
