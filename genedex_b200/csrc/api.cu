@@ -1040,7 +1040,7 @@ SortPlan plan_sort(const gdx_index *idx, uint64_t nq) {
     uint32_t bits = 1;
     while ((1u << bits) < idx->h.ns) ++bits;
     p.key_bits = bits;
-    p.key_syms = std::min<uint32_t>(32 / bits, 16);
+    p.key_syms = std::min<uint32_t>(32 / bits, 12);  // DNA: 24-bit keys = 3 radix passes, 4^12 > any batch
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     if (cub::DeviceRadixSort::SortPairs(nullptr, p.tmp_bytes, dk, dv, (int64_t)nq, 0, (int)(p.key_bits * p.key_syms)) !=
         cudaSuccess)

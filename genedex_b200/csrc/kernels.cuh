@@ -1,6 +1,6 @@
 // kernels.cuh -- hand-written sm_100a kernels of the search path.
 //
-//   k_query_keys    sort key (last 16 symbols) of every query; cub radix sort then gives the order in
+//   k_query_keys    sort key (last 12 symbols) of every query; cub radix sort then gives the order in
 //                   which threads pick queries, so that the top of the search trie is shared in L2
 //   k_search        K1+K2: lookup-table seed + backward search, one thread per query, both interval
 //                   borders' records in flight together      (batch_computed_cursors.rs:36-172,

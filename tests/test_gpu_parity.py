@@ -514,3 +514,29 @@ def test_save_and_load_index_file(gdx, tmp_path):
     trunc.write_bytes(path.read_bytes()[:-100])
     with pytest.raises(gdx.GenedexError):
         gdx.FmIndex.load_from_file(trunc)
+
+
+def test_pipelined_locate_with_many_hits_per_query(gdx):
+    # several pipeline chunks, ~15 hits per query: the pinned result buffer has to grow while earlier
+    # chunks are still being copied out, and every chunk-local CSR offset has to be rebased
+    rng = np.random.default_rng(12)
+    n, nq, m = 1_000_000, 1_200_000, 8
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+    oa = util.oracle_alphabet("ascii_dna")
+    oidx = O.OracleIndex.build([text.tobytes()], oa, "u32", sampling_rate=4, lookup_depth=2)
+    pidx = gdx.FmIndexConfig("u32").lookup_table_depth(2).construct_on_device(True).construct_index(
+        [text.tobytes()], gdx.alphabet.ascii_dna())
+    starts = rng.integers(0, n - m, nq)
+    q = np.ascontiguousarray(text[starts[:, None] + np.arange(m)[None, :]].reshape(-1))
+    off = np.arange(nq + 1, dtype=np.uint64) * m
+    for _ in range(2):  # second call reuses the grown buffers
+        poff, phits, release = pidx.locate_many_view(q, None, m, nq)
+        assert int(poff[-1]) == phits.shape[0] > 10 * nq
+        sel = rng.integers(0, nq, 20_000)
+        qsel = np.ascontiguousarray(q.reshape(nq, m)[sel].reshape(-1))
+        ooff, ohits = oidx.locate_many_packed(qsel, np.arange(sel.size + 1, dtype=np.uint64) * m, nthreads=0)
+        for j, i in enumerate(sel):
+            assert np.array_equal(ohits[int(ooff[j]):int(ooff[j + 1])], phits[int(poff[i]):int(poff[i + 1])])
+        counts = pidx.count_many_packed(q, None, m, nq)
+        assert np.array_equal(counts, poff[1:] - poff[:-1])
+        release()
