@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgenedex_b200.so")
 GDX_OK, GDX_ERR_INVALID_SYMBOL, GDX_ERR_BAD_ARG, GDX_ERR_CUDA, GDX_ERR_OOM, GDX_ERR_TEXT_TOO_LONG, \
     GDX_ERR_UNSUPPORTED = range(7)
 GDX_I32, GDX_U32, GDX_I64 = 0, 1, 2
-GDX_CONSTRUCT_HOST, GDX_CONSTRUCT_DEVICE = 0, 1
+GDX_CONSTRUCT_HOST, GDX_CONSTRUCT_DEVICE, GDX_CONSTRUCT_AUTO = 0, 1, 2
 GDX_FLAG_VERIFY_SUFFIX_ARRAY = 1
 GDX_FLAG_NO_TEXT = 2
 

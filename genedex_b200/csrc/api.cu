@@ -75,6 +75,8 @@ void apply_device_settings(int dev) {
     if (want > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)want);
     // the device-resident entry points take their scratch from the stream-ordered pool: keep freed
     // blocks cached across synchronisation points instead of returning them to the driver
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 16ull << 20);  // room for the superblock tables
+    cudaGetLastError();
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         uint64_t keep = ~0ull;
@@ -239,6 +241,21 @@ Workspace *acquire_ws(const gdx_index *idx) {
         w->destroy();
         delete w;
         return nullptr;
+    }
+    // The superblock table (count[c] + per-superblock ranks, ~1.5 MB for a 3.1 Gbp text) is read by
+    // every LF step: keep it in the persisting part of L2 for the kernels on the workspace's streams.
+    // Best effort (GDX_L2_PERSIST=0 disables it).
+    static const bool persist = !(getenv("GDX_L2_PERSIST") && atoi(getenv("GDX_L2_PERSIST")) == 0);
+    const uint64_t sbc_bytes = idx->h.n_superblocks * idx->h.layout.noff * 8;
+    if (persist && sbc_bytes && sbc_bytes <= (16ull << 20)) {
+        cudaStreamAttrValue attr = {};
+        attr.accessPolicyWindow.base_ptr = const_cast<uint64_t *>(idx->dev.sbc);
+        attr.accessPolicyWindow.num_bytes = sbc_bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        for (auto &sl : w->slot) cudaStreamSetAttribute(sl.stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
     }
     return w;
 }
@@ -489,6 +506,7 @@ gdx_status check_config(const gdx_config &c) {
     if (c.suffix_array_sampling_rate == 0)
         return fail(GDX_ERR_BAD_ARG, "suffix array sampling rate must be > 0 (config.rs:28)");
     if (c.storage > GDX_I64) return fail(GDX_ERR_BAD_ARG, "unknown index storage %u", c.storage);
+    if (c.construction > GDX_CONSTRUCT_AUTO) return fail(GDX_ERR_BAD_ARG, "unknown construction mode %u", c.construction);
     return GDX_OK;
 }
 
@@ -581,13 +599,20 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
             if (p) cudaFree(p);
         }
     } d_text;
-    if (keep_text || config->construction == GDX_CONSTRUCT_DEVICE) {
+    uint32_t construction = config->construction;
+    if (construction == GDX_CONSTRUCT_AUTO) {  // device suffix sort when the text and its scratch fit
+        size_t free_b = 0, total_b = 0;
+        construction = GDX_CONSTRUCT_HOST;
+        if (n < 0xffffffffull && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 36 * n + (1ull << 30))
+            construction = GDX_CONSTRUCT_DEVICE;
+    }
+    if (keep_text || construction == GDX_CONSTRUCT_DEVICE) {
         CUDA_TRY(cudaMalloc(&d_text.p, n ? n : 1));
         CUDA_TRY(cudaMemcpy(d_text.p, ct.text.data(), n, cudaMemcpyHostToDevice));
         if (keep_text) src.d_text = d_text.p;
     }
 
-    if (config->construction == GDX_CONSTRUCT_DEVICE) {
+    if (construction == GDX_CONSTRUCT_DEVICE) {
         DeviceBuildResult r;
         const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
         st = device_build_from_text(nullptr, d_text.p, n, alphabet->num_dense_symbols,
@@ -609,11 +634,8 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         return st;
     }
 
-    std::vector<int64_t> sa;
-    suffix_array_sais(ct.text.data(), n, alphabet->num_dense_symbols, sa);
     HostParts hp;
-    parts_from_suffix_array(ct.text.data(), n, sa.data(), config->suffix_array_sampling_rate, hp);
-    std::vector<int64_t>().swap(sa);
+    host_parts_from_text(ct.text.data(), n, alphabet->num_dense_symbols, config->suffix_array_sampling_rate, hp);
     uint8_t *d_bwt = nullptr;
     CUDA_TRY(cudaMalloc(&d_bwt, n ? n : 1));
     cudaError_t e = cudaMemcpy(d_bwt, hp.bwt.data(), n, cudaMemcpyHostToDevice);

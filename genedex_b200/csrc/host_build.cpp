@@ -151,20 +151,47 @@ struct Sais {
     }
 };
 
-template <class S>
-void sais_shifted(const uint8_t *text, uint64_t n, uint32_t sigma, std::vector<int64_t> &sa) {
-    // symbols + 1 and a unique terminator 0: "end of text < every symbol"
+// suffix array of (text + 1) followed by a unique terminator 0 ("end of text < every symbol");
+// full[0] is the terminator, full[1..] the suffix array of the text
+template <class I, class S>
+void sais_shifted_full(const uint8_t *text, uint64_t n, uint32_t sigma, std::vector<I> &full) {
     std::vector<S> t(n + 1);
     for (uint64_t i = 0; i < n; ++i) t[i] = (S)(text[i] + 1);
     t[n] = 0;
-    std::vector<int64_t> full(n + 1);
-    Sais<int64_t, S> s;
+    full.assign(n + 1, 0);
+    Sais<I, S> s;
     s.T = t.data();
     s.SA = full.data();
-    s.n = (int64_t)n + 1;
-    s.K = (int64_t)sigma + 1;
+    s.n = (I)(n + 1);
+    s.K = (I)(sigma + 1);
     s.run();
-    sa.assign(full.begin() + 1, full.end());  // full[0] is the terminator
+}
+
+template <class S>
+void sais_shifted(const uint8_t *text, uint64_t n, uint32_t sigma, std::vector<int64_t> &sa) {
+    std::vector<int64_t> full;
+    sais_shifted_full<int64_t, S>(text, n, sigma, full);
+    sa.assign(full.begin() + 1, full.end());
+}
+
+template <class I>
+void parts_from_sa(const uint8_t *text, uint64_t n, const I *sa, uint32_t sampling_rate, HostParts &out) {
+    out.n = n;
+    out.bwt.resize(n);
+    out.samples.clear();
+    out.samples.reserve(n / sampling_rate + 1);
+    out.border_rows.clear();
+    out.border_pos.clear();
+    for (uint64_t i = 0; i < n; ++i) {
+        const uint64_t p = (uint64_t)sa[i];
+        const uint8_t b = text[(p > 0 ? p : n) - 1];  // bwt.rs:96-105
+        out.bwt[i] = b;
+        if (b == 0) {  // bwt.rs:108-116
+            out.border_rows.push_back(i);
+            out.border_pos.push_back(p);
+        }
+        if (i % sampling_rate == 0) out.samples.push_back(p);  // sampled_suffix_array.rs:38-44
+    }
 }
 
 }  // namespace
@@ -182,21 +209,24 @@ void suffix_array_sais(const uint8_t *text, uint64_t n, uint32_t sigma, std::vec
 
 void parts_from_suffix_array(const uint8_t *text, uint64_t n, const int64_t *sa,
                              uint32_t sampling_rate, HostParts &out) {
-    out.n = n;
-    out.bwt.resize(n);
-    out.samples.clear();
-    out.samples.reserve(n / sampling_rate + 1);
-    out.border_rows.clear();
-    out.border_pos.clear();
-    for (uint64_t i = 0; i < n; ++i) {
-        const uint64_t p = (uint64_t)sa[i];
-        const uint8_t b = text[(p > 0 ? p : n) - 1];  // bwt.rs:96-105
-        out.bwt[i] = b;
-        if (b == 0) {  // bwt.rs:108-116
-            out.border_rows.push_back(i);
-            out.border_pos.push_back(p);
-        }
-        if (i % sampling_rate == 0) out.samples.push_back(p);  // sampled_suffix_array.rs:38-44
+    parts_from_sa<int64_t>(text, n, sa, sampling_rate, out);
+}
+
+void host_parts_from_text(const uint8_t *text, uint64_t n, uint32_t sigma, uint32_t sampling_rate, HostParts &out) {
+    if (n == 0) {
+        out = HostParts();
+        return;
+    }
+    if (n + 1 < (1ull << 31)) {
+        std::vector<int32_t> full;
+        if (sigma <= 255) sais_shifted_full<int32_t, uint8_t>(text, n, sigma, full);
+        else sais_shifted_full<int32_t, uint16_t>(text, n, sigma, full);
+        parts_from_sa<int32_t>(text, n, full.data() + 1, sampling_rate, out);
+    } else {
+        std::vector<int64_t> full;
+        if (sigma <= 255) sais_shifted_full<int64_t, uint8_t>(text, n, sigma, full);
+        else sais_shifted_full<int64_t, uint16_t>(text, n, sigma, full);
+        parts_from_sa<int64_t>(text, n, full.data() + 1, sampling_rate, out);
     }
 }
 

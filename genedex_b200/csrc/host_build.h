@@ -45,5 +45,9 @@ void suffix_array_sais(const uint8_t *text, uint64_t n, uint32_t sigma, std::vec
 void parts_from_suffix_array(const uint8_t *text, uint64_t n, const int64_t *sa,
                              uint32_t sampling_rate, HostParts &out);
 
+// suffix array + parts in one go; uses 32-bit suffix array entries when the text is shorter than 2^31
+// (half the memory of the 64-bit path, like the reference's i32 index storage)
+void host_parts_from_text(const uint8_t *text, uint64_t n, uint32_t sigma, uint32_t sampling_rate, HostParts &out);
+
 }  // namespace gdx
 #endif

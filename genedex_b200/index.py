@@ -81,7 +81,7 @@ class FmIndexConfig:
         self._sampling_rate = 4          # config.rs:75
         self._lookup_depth = 0           # config.rs:76
         self._priority = PerformancePriority.Balanced  # config.rs:77
-        self._construction = _lib.GDX_CONSTRUCT_HOST
+        self._construction = _lib.GDX_CONSTRUCT_AUTO  # all construction routes give the same index
         self._device = -1
         self._flags = 0
 

@@ -49,7 +49,8 @@ typedef enum gdx_storage { GDX_I32 = 0, GDX_U32 = 1, GDX_I64 = 2 } gdx_storage;
 /* where the suffix array is built (construction is not part of the search path) */
 typedef enum gdx_construction {
     GDX_CONSTRUCT_HOST = 0,  /* SA-IS on the host (the reference: libsais on the host)          */
-    GDX_CONSTRUCT_DEVICE = 1 /* prefix-doubling radix sort on the GPU (n < 2^32 - 1)            */
+    GDX_CONSTRUCT_DEVICE = 1,/* prefix-doubling radix sort on the GPU (n < 2^32 - 1)            */
+    GDX_CONSTRUCT_AUTO = 2   /* device when the text and the sort scratch (~36 B/symbol) fit    */
 } gdx_construction;
 
 /* src/alphabet.rs:24-28: 256-entry IO->dense table (0 = not in the alphabet; dense 0 is the

@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <string>
 #include <string_view>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -285,7 +286,7 @@ public:
 
 private:
     // config.rs:72-82 defaults: sampling rate 4, lookup depth 0, Balanced
-    gdx_config cfg_{I::storage, 4, 0, (uint32_t)PerformancePriority::Balanced, GDX_CONSTRUCT_HOST, -1, 0};
+    gdx_config cfg_{I::storage, 4, 0, (uint32_t)PerformancePriority::Balanced, GDX_CONSTRUCT_AUTO, -1, 0};
 };
 
 }  // namespace gdx

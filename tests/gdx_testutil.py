@@ -62,8 +62,7 @@ def build_pair(gdx, texts, alph_name, storage="u32", s=4, depth=0, on_device=Fal
     oa = oracle_alphabet(alph_name)
     oidx = O.OracleIndex.build(texts, oa, storage, sampling_rate=s, lookup_depth=depth)
     cfg = gdx.FmIndexConfig(storage).suffix_array_sampling_rate(s).lookup_table_depth(depth)
-    if on_device:
-        cfg = cfg.construct_on_device(True, verify=True)
+    cfg = cfg.construct_on_device(on_device, verify=on_device)  # the default would be "auto"
     pidx = cfg.construct_index(texts, product_alphabet(gdx, alph_name))
     return oidx, pidx
 
