@@ -331,7 +331,10 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     h.storage = src.storage;
     h.sampling_rate = src.sampling_rate;
     h.lookup_depth = src.lookup_depth;
-    h.wide = src.n > 0xffffffffull ? 1 : 0;
+    // 64-bit samples / lookup entries are only needed beyond 2^32 - 1 symbols; GDX_FORCE_WIDE=1 selects them
+    // for any text so that this path can be tested without a 4.3 G symbol index
+    const char *fw = getenv("GDX_FORCE_WIDE");
+    h.wide = (src.n > 0xffffffffull || (fw && atoi(fw) != 0)) ? 1 : 0;
     h.layout = choose_layout(h.sigma);
     memcpy(h.io_to_dense, src.alphabet->io_to_dense, 256);
     if (src.lookup_depth > kMaxLookupDepth)

@@ -540,3 +540,19 @@ def test_pipelined_locate_with_many_hits_per_query(gdx):
         counts = pidx.count_many_packed(q, None, m, nq)
         assert np.array_equal(counts, poff[1:] - poff[:-1])
         release()
+
+
+def test_wide_index_entries(gdx, monkeypatch):
+    # texts beyond 2^32 - 1 symbols store 64-bit SA samples and lookup entries; GDX_FORCE_WIDE selects that
+    # representation for a small index so that the path is exercised without a 4.3 G symbol text
+    monkeypatch.setenv("GDX_FORCE_WIDE", "1")
+    rng = random.Random(31)
+    for alph, depth in (("ascii_dna_with_n", 4), ("protein20", 2)):
+        oa = util.oracle_alphabet(alph)
+        texts = util.random_texts(rng, oa, 3, 6000)
+        for on_device in (False, True):
+            oidx, pidx = util.build_pair(gdx, texts, alph, "i64", 4, depth, on_device)
+            assert pidx.info().sample_bytes >= 8 * pidx.info().num_samples
+            qs = util.random_queries(rng, oa, texts, 300, 200, 40, searchable_only=True)
+            util.assert_same_results(oidx, pidx, qs)
+            assert np.array_equal(pidx.download_samples(), oidx.samples())
