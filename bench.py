@@ -32,6 +32,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("GDX_ORACLE_NATIVE", "1")  # CPU baseline: oracle rebuilt with -march=native on this box
 
 TEXT_SEED = 0x5EED0001
 QUERY_SEED = 0x5EED0002

@@ -36,10 +36,18 @@ class OraclePanic(RuntimeError):
 
 
 def build_library(force: bool = False) -> str:
+    """Portable build by default (the .so travels between machines).  With GDX_ORACLE_NATIVE=1 (set by
+    bench.py for the CPU-baseline legs) a -march=native library is built on the machine it runs on."""
     src = os.path.join(_HERE, "gdx_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "gdx_oracle.h"))
-    ):
+    newest = max(os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "gdx_oracle.h")))
+    if os.environ.get("GDX_ORACLE_NATIVE") == "1":
+        native = os.path.join(_HERE, "_build", "libgdx_oracle_native.so")
+        try:
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+            return native
+        except Exception:
+            pass  # no compiler on this machine: fall back to the portable build
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
@@ -50,8 +58,7 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        build_library()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(build_library())
         u8p, u16p, u64p, i64p = (C.POINTER(t) for t in (C.c_uint8, C.c_uint16, C.c_uint64, C.c_int64))
         vp = C.c_void_p
         L.gdxo_build.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
