@@ -556,3 +556,19 @@ def test_wide_index_entries(gdx, monkeypatch):
             qs = util.random_queries(rng, oa, texts, 300, 200, 40, searchable_only=True)
             util.assert_same_results(oidx, pidx, qs)
             assert np.array_equal(pidx.download_samples(), oidx.samples())
+
+
+def test_many_short_texts(gdx):
+    # a read-set shaped index: 20 000 texts of 0..120 symbols (many sentinels, many text borders)
+    rng = random.Random(44)
+    texts = [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(0, 121))) for _ in range(20_000)]
+    oa = util.oracle_alphabet("ascii_dna")
+    for on_device in (False, True):
+        oidx, pidx = util.build_pair(gdx, texts, "ascii_dna", "u32", 4, 4, on_device)
+        assert pidx.num_texts() == 20_000 and pidx.info().num_text_borders == 20_000
+        qs = util.random_queries(rng, oa, texts, 3000, 1000, 30)
+        util.assert_same_results(oidx, pidx, qs)
+        # every text start/end is reachable: locate the whole first and last text
+        for t in (0, 19_999):
+            if texts[t]:
+                assert (t, 0) in {(h.text_id, h.position) for h in pidx.locate(texts[t])}
