@@ -566,8 +566,8 @@ def test_many_short_texts(gdx):
     for on_device in (False, True):
         oidx, pidx = util.build_pair(gdx, texts, "ascii_dna", "u32", 4, 4, on_device)
         assert pidx.num_texts() == 20_000 and pidx.info().num_text_borders == 20_000
-        qs = util.random_queries(rng, oa, texts, 3000, 1000, 30)
-        util.assert_same_results(oidx, pidx, qs)
+        qs = [q for q in util.random_queries(rng, oa, texts, 3000, 1000, 30) if len(q) >= 5] + [b"", b"ACG"]
+        util.assert_same_results(oidx, pidx, qs)  # (short queries hit 10^5..10^6 rows each: keep them few)
         # every text start/end is reachable: locate the whole first and last text
         for t in (0, 19_999):
             if texts[t]:
