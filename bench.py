@@ -438,6 +438,16 @@ def run_ours(args, rank, world, local_rank):
                  + R * int(st.walk_steps) + 64 * int(st.verified_queries))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     value = world * nq / (kernel_ms * 1e-3)
+    traffic = ncu_traffic_bytes(args, st.verified_queries > 0)
+    random_access = None
+    if traffic:
+        # the path is bound by the device's random-access rate, not by streaming bandwidth: every missing
+        # 32 B sector is a 64 B DRAM fetch (ncu), and tools/gather_bench.py measures 42.7 G random fetches/s
+        # (profiles/r1_gather_ceiling.json).  Sorted queries give the shallow steps row locality, so the
+        # kernel can exceed the fully random figure.
+        random_access = {"dram_fetches_per_launch": traffic / 64, "fetches_per_s": traffic / 64 / (kernel_ms * 1e-3),
+                         "measured_random_fetch_ceiling_per_s": 42.7e9,
+                         "frac_of_ceiling": traffic / 64 / (kernel_ms * 1e-3) / 42.7e9}
     out = {
         "metric": "len-50 count queries/s on 3.1 Gbp DNA index",
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -458,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
                 "gpu_launches_per_step": int(st.kernel_launches)},
         "gpu_launches": 2 * args.steps,  # k_query_keys + k_search per step (+ 6 cub radix-sort kernels)
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic_bytes(args, st.verified_queries > 0), "peak_kind": peak_kind, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
+                     "traffic": traffic, "peak_kind": peak_kind, "random_access": random_access, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "rank_queries_per_s": 2 * steps_exec / (kernel_ms * 1e-3)},
         "cpu_baseline": cpu,
