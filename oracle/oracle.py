@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -43,12 +44,12 @@ def build_library(force: bool = False) -> str:
     if os.environ.get("GDX_ORACLE_NATIVE") == "1":
         native = os.path.join(_HERE, "_build", "libgdx_oracle_native.so")
         try:
-            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"], stdout=sys.stderr)
             return native
         except Exception:
             pass  # no compiler on this machine: fall back to the portable build
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < newest:
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=sys.stderr)
     return _LIB_PATH
 
 
