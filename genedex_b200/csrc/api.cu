@@ -1057,7 +1057,16 @@ struct SortPlan {
     size_t tmp_bytes = 0;
     uint64_t total_bytes = 0;  // keys a/b + idx a/b + cub temp, 256 B aligned pieces
     bool use = false;
+    bool bucket = false;       // one-pass bucket grouping instead of the radix sort
 };
+
+bool bucket_mode() {
+    static const bool on = [] {
+        const char *e = getenv("GDX_SORT_MODE");
+        return e && strcmp(e, "bucket") == 0;
+    }();
+    return on;
+}
 
 SortPlan plan_sort(const gdx_index *idx, uint64_t nq) {
     SortPlan p;
@@ -1065,6 +1074,13 @@ SortPlan plan_sort(const gdx_index *idx, uint64_t nq) {
     uint32_t bits = 1;
     while ((1u << bits) < idx->h.ns) ++bits;
     p.key_bits = bits;
+    if (bucket_mode() && bits <= kBucketBits) {
+        p.key_syms = kBucketBits / bits;
+        p.bucket = true;
+        p.total_bytes = 2 * align_up(nq * 4, 256) + align_up(kNumBuckets * 4, 256);  // keys, perm, histogram
+        p.use = true;
+        return p;
+    }
     p.key_syms = std::min<uint32_t>(32 / bits, 12);  // DNA: 24-bit keys = 3 radix passes, 4^12 > any batch
     cub::DoubleBuffer<uint32_t> dk(nullptr, nullptr), dv(nullptr, nullptr);
     if (cub::DeviceRadixSort::SortPairs(nullptr, p.tmp_bytes, dk, dv, (int64_t)nq, 0, (int)(p.key_bits * p.key_syms)) !=
@@ -1080,6 +1096,17 @@ gdx_status sort_queries(const gdx_index *idx, const DevQueries &dq, const SortPl
                         cudaStream_t stream, const uint32_t **perm) {
     uint8_t *base = (uint8_t *)scratch;
     const uint64_t piece = align_up(dq.nq * 4, 256);
+    if (p.bucket) {
+        uint32_t *keys = (uint32_t *)base, *out = (uint32_t *)(base + piece), *hist = (uint32_t *)(base + 2 * piece);
+        const unsigned grid = (unsigned)div_up(dq.nq, 256);
+        CUDA_TRY(cudaMemsetAsync(hist, 0, kNumBuckets * 4, stream));
+        k_bucket_count<<<grid, 256, 0, stream>>>(idx->dev, dq, p.key_bits, p.key_syms, keys, hist);
+        k_bucket_scan<<<1, 1024, 0, stream>>>(hist);
+        k_bucket_scatter<<<grid, 256, 0, stream>>>(keys, dq.nq, hist, out);
+        CUDA_TRY(cudaGetLastError());
+        *perm = out;
+        return GDX_OK;
+    }
     uint32_t *ka = (uint32_t *)base, *kb = (uint32_t *)(base + piece), *ia = (uint32_t *)(base + 2 * piece),
              *ib = (uint32_t *)(base + 3 * piece);
     void *tmp = base + 4 * piece;

@@ -307,6 +307,68 @@ k_query_keys(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_t 
     idx[q] = (uint32_t)q;
 }
 
+// ---- one-pass bucket grouping (alternative to the full radix sort) -----------------------------------
+// For L2 sharing it is enough that queries with the same suffix are searched at about the same time:
+// group the batch by a 16-bit key (the last 8 symbols of a DNA query) with one counting-sort pass --
+// histogram, scan over the 65 536 buckets, unordered scatter -- instead of three radix passes.
+constexpr uint32_t kBucketBits = 16;
+constexpr uint32_t kNumBuckets = 1u << kBucketBits;
+
+__global__ void __launch_bounds__(256)
+k_bucket_count(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_t key_bits, uint32_t key_syms,
+               uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= qs.nq) return;
+    uint64_t begin, len;
+    if (qs.offsets) {
+        begin = __ldg(qs.offsets + q) - qs.base;
+        len = __ldg(qs.offsets + q + 1) - qs.base - begin;
+    } else {
+        begin = q * qs.fixed_len;
+        len = qs.fixed_len;
+    }
+    const uint8_t *p = qs.bytes + begin;
+    uint32_t key = 0;
+    for (uint32_t j = 0; j < key_syms; ++j) {
+        uint32_t code = 0;
+        if (j < len) {
+            const uint32_t c = ix.io_to_dense[__ldg(p + len - 1 - j)];
+            code = (c >= 1 && c <= ix.ns) ? c - 1 : 0;
+        }
+        key = (key << key_bits) | code;
+    }
+    keys[q] = key;
+    atomicAdd(hist + key, 1u);
+}
+
+// exclusive scan of the 65 536 bucket counts: one CTA of 1024 threads, 64 buckets per thread
+__global__ void __launch_bounds__(1024) k_bucket_scan(uint32_t *__restrict__ hist) {
+    using Scan = cub::BlockScan<uint32_t, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    constexpr uint32_t per = kNumBuckets / 1024;
+    uint32_t local[per], sum = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < per; ++j) {
+        local[j] = hist[threadIdx.x * per + j];
+        sum += local[j];
+    }
+    uint32_t base;
+    Scan(tmp).ExclusiveSum(sum, base);
+#pragma unroll
+    for (uint32_t j = 0; j < per; ++j) {
+        hist[threadIdx.x * per + j] = base;
+        base += local[j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_bucket_scatter(const uint32_t *__restrict__ keys, uint64_t nq, uint32_t *__restrict__ cursor,
+                 uint32_t *__restrict__ perm) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    perm[atomicAdd(cursor + keys[q], 1u)] = (uint32_t)q;
+}
+
 // ---- K1 + K2: seed + backward search ----------------------------------------------------------------
 // mode 0: out_a = starts, out_b = ends; mode 1: out_a = counts.
 // Follows the batched path of the reference: a symbol is translated only when the search reaches
