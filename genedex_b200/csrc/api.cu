@@ -382,6 +382,8 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
 
 // L2 eviction policy values for the kernels (GDX_L2_HINTS=0 disables them)
 gdx_status init_policies(gdx_index *idx) {
+    if (const char *vm = getenv("GDX_VERIFY_MIN"))
+        if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
     const char *e = getenv("GDX_L2_HINTS");
     if (e && atoi(e) == 0) return GDX_OK;
     uint64_t *d = nullptr, h = 0;

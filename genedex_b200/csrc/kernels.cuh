@@ -270,9 +270,9 @@ __device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) 
 
 // interval flag of the locate plumbing: start = resolved text position, end = kDirectHit
 constexpr uint64_t kDirectHit = ~0ull;
-// switch from LF steps to "resolve the row + compare against the text" when the interval has one row
-// and at least this many symbols are left (a walk + sample + text read costs about 5 random sectors)
-constexpr uint32_t kVerifyMinRemaining = 8;
+// k_search switches from LF steps to "resolve the row + compare against the text" when the interval has
+// one row and at least DevIndex::verify_min_remaining symbols are left (a walk + sample + text read costs
+// about 5 random sectors; default 8, GDX_VERIFY_MIN overrides it for measurements)
 
 // ---- sort key of a query: its last symbols, last symbol most significant ---------------------------
 // Backward search consumes a query right to left, so queries that share a suffix walk the same
@@ -381,7 +381,7 @@ constexpr uint32_t kQueryStage = 64;                       // bytes staged per q
 constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, covers any misalignment
 
 // VERIFY (count / locate only, needs the text section): as soon as the interval holds exactly one row
-// and >= kVerifyMinRemaining symbols are left, SA[row] is resolved (LF-walk to a sample) and the rest
+// and >= verify_min_remaining symbols are left, SA[row] is resolved (LF-walk to a sample) and the rest
 // of the query is compared with the text right to left.  The reference would shrink that interval to
 // [x, x+1) or to empty by the same comparisons, one rank per symbol (cursor.rs:40-51): count and hit
 // are identical, the invalid-symbol panic fires at the same symbol, only the interval itself is not
@@ -447,7 +447,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         // (deferring it behind the loop so that it runs once per warp was measured 22 % slower).
         bool direct = false;
         while (!bad && pos > 0 && s != e) {
-            if (VERIFY && e - s == 1 && pos >= kVerifyMinRemaining) {
+            if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
                 const uint64_t at = resolve_row<L>(ix, s, vsteps);
                 vrows = 1;
