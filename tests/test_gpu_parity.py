@@ -572,3 +572,27 @@ def test_many_short_texts(gdx):
         for t in (0, 19_999):
             if texts[t]:
                 assert (t, 0) in {(h.text_id, h.position) for h in pidx.locate(texts[t])}
+
+
+def test_device_resident_locate_with_wide_intervals(gdx):
+    import torch
+    rng = random.Random(3)
+    texts = [bytes(rng.choice(b"AC") for _ in range(30_000)), b"AAAAAAAAAA" * 300]
+    oidx, pidx = util.build_pair(gdx, texts, "ascii_dna", "u32", 4, 2, True)
+    qs = [b"", b"A", b"AA", b"CA", b"ACAC", b"AAAAAAAAAA", b"G", b"CCCCCCCCCCCCCCCC"]
+    data, off = O.pack(qs)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
+    lib = gdx._lib.load()
+    stream = torch.cuda.current_stream().cuda_stream
+    d_s = torch.from_numpy(want_s.astype(np.int64)).cuda()
+    d_e = torch.from_numpy(want_e.astype(np.int64)).cuda()
+    counts = torch.from_numpy((want_e - want_s).astype(np.int64)).cuda()
+    hit_off = torch.zeros(len(qs) + 1, dtype=torch.int64, device="cuda")
+    hit_off[1:] = torch.cumsum(counts, 0)
+    total = int(hit_off[-1].item())
+    d_hits = torch.zeros((total, 2), dtype=torch.int64, device="cuda")
+    assert lib.gdx_locate_intervals_device(pidx.handle, d_s.data_ptr(), d_e.data_ptr(), len(qs), hit_off.data_ptr(),
+                                           total, d_hits.data_ptr(), stream) == 0
+    torch.cuda.synchronize()
+    _, ohits = oidx.locate_many_packed(data, off)
+    assert np.array_equal(d_hits.cpu().numpy().astype(np.uint64), ohits)
