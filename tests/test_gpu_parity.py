@@ -3,6 +3,7 @@
 Bit-exact bar: intervals, counts, and hits (text_id, position) in the reference's SA-row order.
 """
 import ctypes as C
+import os
 import random
 import threading
 
@@ -596,3 +597,16 @@ def test_device_resident_locate_with_wide_intervals(gdx):
     torch.cuda.synchronize()
     _, ohits = oidx.locate_many_packed(data, off)
     assert np.array_equal(d_hits.cpu().numpy().astype(np.uint64), ohits)
+
+
+def test_c_example_runs(gdx, tmp_path):
+    import subprocess
+    libdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "genedex_b200", "csrc")
+    root = os.path.dirname(libdir.rstrip("/").rsplit("/genedex_b200", 1)[0] + "/x")
+    exe = str(tmp_path / "basic_usage")
+    subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "basic_usage.c"), "-L", libdir, "-lgenedex_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "query 3: count 1" in out.stdout

@@ -223,3 +223,13 @@ def test_c_abi_argument_errors_never_crash(gdx):
     assert lib.gdx_index_adopt_image(hdr, C.c_void_p(4096), -1, 0, C.byref(h)) == L.GDX_ERR_BAD_ARG  # bad magic
     lib.gdx_index_destroy(None)  # no-op
     lib.gdx_free_hits(None, None)
+
+
+def test_c_example_compiles(tmp_path):
+    # examples/basic_usage.c: the crate's basic_usage example in plain C against the header
+    libdir = os.path.join(ROOT, "genedex_b200", "csrc")
+    exe = str(tmp_path / "basic_usage")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "basic_usage.c"), "-L", libdir, "-lgenedex_b200",
+                           f"-Wl,-rpath,{libdir}", "-o", exe])
+    assert os.path.exists(exe)
