@@ -601,8 +601,8 @@ def test_device_resident_locate_with_wide_intervals(gdx):
 
 def test_c_example_runs(gdx, tmp_path):
     import subprocess
-    libdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "genedex_b200", "csrc")
-    root = os.path.dirname(libdir.rstrip("/").rsplit("/genedex_b200", 1)[0] + "/x")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "genedex_b200", "csrc")
     exe = str(tmp_path / "basic_usage")
     subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(root, "include"),
                            os.path.join(root, "examples", "basic_usage.c"), "-L", libdir, "-lgenedex_b200",
