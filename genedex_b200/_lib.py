@@ -77,6 +77,7 @@ PROTOTYPES = {
     "gdx_index_create_from_parts": (C.c_int, [_P(gdx_parts), _i32, _P(_vp)]),
     "gdx_index_create_from_bwt": (C.c_int, [_vp, _P(gdx_parts), _i32, _P(_vp)]),
     "gdx_suffix_array": (C.c_int, [_vp, _u64, _u32, _u32, _i32, _vp]),
+    "gdx_concat_texts": (C.c_int, [_vp, _vp, _u64, _P(gdx_alphabet), _vp, _vp, _vp]),
     "gdx_index_download_bwt": (C.c_int, [_vp, _vp]),
     "gdx_index_get_count": (C.c_int, [_vp, _vp]),
     "gdx_index_download_samples": (C.c_int, [_vp, _vp]),

@@ -749,6 +749,26 @@ extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_
     return st;
 }
 
+extern "C" gdx_status gdx_concat_texts(const uint8_t *texts, const uint64_t *text_offsets, uint64_t num_texts,
+                                       const gdx_alphabet *alphabet, uint8_t *dense_out, uint64_t *sentinels_out,
+                                       uint64_t *count_out) {
+    if (!text_offsets || !alphabet || !dense_out || !sentinels_out || !count_out || num_texts == 0)
+        return fail(GDX_ERR_BAD_ARG, "NULL argument or no texts");
+    GDX_TRY(validate_alphabet(*alphabet));
+    ConcatText ct;
+    uint64_t bad = 0;
+    gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
+    if (st != GDX_OK) {
+        t_error_query = bad;
+        return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
+                    (unsigned long long)bad);
+    }
+    memcpy(dense_out, ct.text.data(), ct.text.size());
+    memcpy(sentinels_out, ct.sentinels.data(), ct.sentinels.size() * 8);
+    memcpy(count_out, ct.count.data(), ct.count.size() * 8);
+    return GDX_OK;
+}
+
 extern "C" gdx_status gdx_suffix_array(const uint8_t *dense_text, uint64_t n, uint32_t sigma, uint32_t where,
                                        int32_t device_req, uint64_t *sa_out) {
     if (n == 0) return GDX_OK;

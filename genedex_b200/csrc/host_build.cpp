@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 namespace gdx {
 
@@ -20,21 +21,54 @@ gdx_status concat_texts(const uint8_t *texts, const uint64_t *text_offsets, uint
     const uint64_t total = text_offsets[num_texts] - text_offsets[0];
     out.text.assign(total + num_texts, 0);
     out.sentinels.resize(num_texts);
-    std::vector<uint64_t> freq(257, 0);
+    // sentinel positions first (construction/mod.rs:267-274), then the symbols are translated in parallel
+    // slices of the concatenated output (the reference does this with rayon, construction/mod.rs:289-303)
     uint64_t w = 0;
     for (uint64_t t = 0; t < num_texts; ++t) {
-        for (uint64_t p = text_offsets[t]; p < text_offsets[t + 1]; ++p) {
-            const uint8_t d = alphabet.io_to_dense[texts[p]];
-            if (d == 0) {  // alphabet.rs:195-198
-                if (bad_text) *bad_text = t;
-                return GDX_ERR_INVALID_SYMBOL;
-            }
-            out.text[w++] = d;
-            freq[d]++;
-        }
-        out.sentinels[t] = w;  // construction/mod.rs:267-274
-        out.text[w++] = 0;
+        w += text_offsets[t + 1] - text_offsets[t];
+        out.sentinels[t] = w++;
     }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const unsigned nthreads = total < (1u << 22) ? 1 : hw;
+    std::vector<std::vector<uint64_t>> freqs(nthreads, std::vector<uint64_t>(257, 0));
+    std::vector<uint64_t> bad(nthreads, ~0ull);
+    auto work = [&](unsigned tid) {
+        // texts are split by their index range so that a slice never straddles a thread boundary mid-copy
+        const uint64_t lo = total * tid / nthreads, hi = total * (tid + 1) / nthreads;  // input byte range
+        // first text that contains input byte `lo`
+        uint64_t t = std::upper_bound(text_offsets, text_offsets + num_texts + 1, text_offsets[0] + lo) - text_offsets - 1;
+        std::vector<uint64_t> &freq = freqs[tid];
+        for (uint64_t p = text_offsets[0] + lo; p < text_offsets[0] + hi;) {
+            while (t + 1 <= num_texts && p >= text_offsets[t + 1]) ++t;  // skips empty texts
+            const uint64_t end = std::min(text_offsets[0] + hi, text_offsets[t + 1]);
+            uint8_t *dst = out.text.data() + (p - text_offsets[0]) + t;  // t sentinels precede text t
+            for (; p < end; ++p) {
+                const uint8_t d = alphabet.io_to_dense[texts[p]];
+                if (d == 0) {  // alphabet.rs:195-198
+                    bad[tid] = std::min(bad[tid], t);
+                    return;
+                }
+                *dst++ = d;
+                freq[d]++;
+            }
+        }
+    };
+    if (nthreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned i = 0; i < nthreads; ++i) th.emplace_back(work, i);
+        for (auto &x : th) x.join();
+    }
+    uint64_t first_bad = ~0ull;
+    for (uint64_t b : bad) first_bad = std::min(first_bad, b);
+    if (first_bad != ~0ull) {
+        if (bad_text) *bad_text = first_bad;
+        return GDX_ERR_INVALID_SYMBOL;
+    }
+    std::vector<uint64_t> freq(257, 0);
+    for (auto &f : freqs)
+        for (int i = 0; i < 257; ++i) freq[i] += f[i];
     freq[0] = num_texts;  // construction/mod.rs:302
     out.count.assign(sigma + 1, 0);  // construction/mod.rs:318-336
     uint64_t sum = 0;

@@ -183,6 +183,13 @@ gdx_status gdx_index_get_count(const gdx_index *idx, uint64_t *count_out /* num_
 gdx_status gdx_index_download_samples(const gdx_index *idx, uint64_t *samples_out);
 gdx_status gdx_index_download_text_borders(const gdx_index *idx, uint64_t *rows_out, uint64_t *positions_out);
 
+/* Construction utility: concatenate + densely encode the texts with one 0 sentinel after each text
+ * (src/construction/mod.rs:255-308), sentinel positions and count[] (src/construction/mod.rs:318-336).
+ * dense_out: total text length + num_texts bytes; sentinels_out: num_texts; count_out: sigma + 1. */
+gdx_status gdx_concat_texts(const uint8_t *texts, const uint64_t *text_offsets, uint64_t num_texts,
+                            const gdx_alphabet *alphabet, uint8_t *dense_out, uint64_t *sentinels_out,
+                            uint64_t *count_out);
+
 void gdx_index_destroy(gdx_index *idx);
 gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);
 

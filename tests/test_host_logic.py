@@ -233,3 +233,44 @@ def test_c_example_compiles(tmp_path):
                            os.path.join(ROOT, "examples", "basic_usage.c"), "-L", libdir, "-lgenedex_b200",
                            f"-Wl,-rpath,{libdir}", "-o", exe])
     assert os.path.exists(exe)
+
+
+def test_concat_texts_equals_oracle_also_multithreaded(gdx):
+    # construction/mod.rs:255-336; above 4 M symbols the translation runs on several host threads
+    lib = gdx._lib.load()
+    rng = np.random.default_rng(8)
+    for total, ntexts in ((1000, 7), (6_000_000, 40)):
+        cuts = np.sort(rng.integers(0, total, ntexts - 1))
+        cuts[:3] = cuts[3]  # a few empty texts
+        cuts = np.sort(cuts)
+        io = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)[rng.integers(0, 10, total)]
+        offs = np.concatenate([[0], cuts, [total]]).astype(np.uint64)
+        texts = [io[int(a):int(b)].tobytes() for a, b in zip(offs[:-1], offs[1:])]
+        oa = O.ALPHABETS["ascii_dna_with_n"]()
+        alph = gdx.index._alphabet_struct(gdx.alphabet.ascii_dna_with_n())
+        dense = np.zeros(total + ntexts, dtype=np.uint8)
+        sent = np.zeros(ntexts, dtype=np.uint64)
+        count = np.zeros(7, dtype=np.uint64)
+        assert lib.gdx_concat_texts(io.ctypes.data, offs.ctypes.data, ntexts, C.byref(alph), dense.ctypes.data,
+                                    sent.ctypes.data, count.ctypes.data) == 0
+        # independent restatement with numpy
+        want = np.zeros(total + ntexts, dtype=np.uint8)
+        table = oa.io_to_dense
+        pos = 0
+        want_sent = []
+        for t in texts:
+            want[pos:pos + len(t)] = table[np.frombuffer(t, dtype=np.uint8)]
+            pos += len(t)
+            want_sent.append(pos)
+            pos += 1
+        assert np.array_equal(dense, want) and sent.tolist() == want_sent
+        freq = np.bincount(want, minlength=7).astype(np.uint64)
+        assert count.tolist() == np.concatenate([[0], np.cumsum(freq[:6])]).tolist()
+        if total <= 1000:  # and the oracle agrees (small case only: the oracle also builds a suffix array)
+            oidx = O.OracleIndex.build(texts, oa, "u32")
+            assert np.array_equal(oidx.dense_text(), dense) and oidx.count_array().tolist() == count.tolist()
+    bad = np.frombuffer(b"ACGTXACGT", dtype=np.uint8)
+    offs = np.array([0, 4, 9], dtype=np.uint64)
+    assert lib.gdx_concat_texts(bad.ctypes.data, offs.ctypes.data, 2, C.byref(alph), dense.ctypes.data, sent.ctypes.data,
+                                count.ctypes.data) == gdx._lib.GDX_ERR_INVALID_SYMBOL
+    assert lib.gdx_last_error_query() == 1
