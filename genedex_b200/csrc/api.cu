@@ -198,8 +198,8 @@ struct Workspace {
     }
     cudaEvent_t next_event(Slot &s) {
         if (s.ev_used == s.ev.size()) {
-            cudaEvent_t e;
-            cudaEventCreate(&e);
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;  // recording on nullptr fails loudly later
             s.ev.push_back(e);
         }
         return s.ev[s.ev_used++];
@@ -1166,7 +1166,6 @@ struct LocatePipe {
     void *pinned = nullptr; // library-owned pinned hit buffer (grows)
     uint64_t pinned_cap = 0;
     uint64_t total = 0;     // hits of all finished chunks
-    uint64_t walk_launches = 0;
     struct Pending {
         int slot;
         uint64_t q0, cq;
