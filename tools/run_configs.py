@@ -148,6 +148,21 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
     if n_orig:
         assert int(counts[:n_orig].min()) >= 1, f"{name}: a query sampled from the text has count 0"
 
+    # the other entry points of the path: cursors (every LF step, no text verification) and batched extend
+    for _ in range(2):
+        cs, ce = pidx.cursors_many_packed(q_np, None, m, nq)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cs, ce = pidx.cursors_many_packed(q_np, None, m, nq)
+    cur_ms = (time.perf_counter() - t0) * 1e3 / 3
+    assert np.array_equal(ce - cs, counts), f"{name}: cursor widths differ from counts"
+    sym = np.full(nq, q_np[0], dtype=np.uint8)
+    t0 = time.perf_counter()
+    es, ee = pidx.extend_many_packed(cs, ce, sym)
+    ext_ms = (time.perf_counter() - t0) * 1e3
+    res.update({"cursors_e2e_ms": round(cur_ms, 3), "cursors_e2e_queries_per_s": nq / (cur_ms * 1e-3),
+                "extend_many_e2e_ms": round(ext_ms, 3), "extend_many_cursors_per_s": nq / (ext_ms * 1e-3)})
+
     if locate:
         hit_off = torch.empty(nq + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
         for _ in range(2):
