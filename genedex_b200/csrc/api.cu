@@ -3,7 +3,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +130,116 @@ struct DBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// grow-only pinned host buffer (staging for callers that pass ordinary pageable memory)
+struct HBuf {
+    void *p = nullptr;
+    uint64_t cap = 0;
+    cudaError_t reserve(uint64_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const uint64_t want = align_up(bytes + bytes / 8, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// true for cudaMallocHost / cudaHostRegister'ed / managed memory, false for ordinary (pageable) host memory
+bool is_pinned(const void *p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+// A few host threads that copy between pageable caller memory and the pinned staging buffers: one thread
+// moves ~10 GB/s, a PCIe Gen5 link 52 GB/s.  One job at a time; the calling thread works too.
+class HostPool {
+public:
+    static HostPool &get() {
+        static HostPool pool;
+        return pool;
+    }
+    void copy(void *dst, const void *src, uint64_t bytes) {
+        constexpr uint64_t kPiece = 2ull << 20;
+        if (bytes <= 2 * kPiece || workers_.empty()) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        std::lock_guard<std::mutex> one_job(job_mu_);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = (uint8_t *)dst;
+            src_ = (const uint8_t *)src;
+            bytes_ = bytes;
+            pieces_ = (bytes + kPiece - 1) / kPiece;
+            next_.store(0);
+            done_ = 0;
+            ++generation_;
+        }
+        cv_.notify_all();
+        work(kPiece);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return done_ == pieces_; });
+    }
+
+private:
+    HostPool() {
+        unsigned n = std::thread::hardware_concurrency();
+        n = n > 2 ? std::min(7u, n / 2) : 0;  // plus the caller
+        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void work(uint64_t piece) {
+        for (;;) {
+            const uint64_t k = next_.fetch_add(1);
+            if (k >= pieces_) break;
+            const uint64_t off = k * piece, nb = std::min(piece, bytes_ - off);
+            memcpy(dst_ + off, src_ + off, nb);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (++done_ == pieces_) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+            }
+            work(2ull << 20);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, job_mu_;
+    std::condition_variable cv_, done_cv_;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    uint64_t bytes_ = 0, pieces_ = 0, done_ = 0, generation_ = 0;
+    std::atomic<uint64_t> next_{0};
+    bool stop_ = false;
+};
+
+constexpr uint64_t kStageMinBytes = 4ull << 20;  // smaller transfers go through the driver's own staging
+
 constexpr int kSlots = 3;
 // Pipeline chunking: the byte budget of successive chunks doubles from kChunkFirst to kChunkMax
 // (fast pipeline fill, then few large launches: less launch overhead and deeper shared suffixes for the
@@ -148,6 +261,10 @@ struct Slot {
     uint64_t *d_words = nullptr;  // device: [0] number of wide intervals, [1] worklist cursor
     uint64_t *h_words = nullptr;  // pinned: [0] hits of the chunk, [1] number of wide intervals
     cudaEvent_t ev_total = nullptr;
+    // staging for pageable caller buffers
+    HBuf h_in, h_off, h_out_a, h_out_b;
+    cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
+    bool h2d_pending = false;
     std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
     size_t ev_used = 0;
 };
@@ -169,6 +286,8 @@ struct Workspace {
             if (cudaMalloc(&s.d_words, 4 * sizeof(uint64_t)) != cudaSuccess) return false;
             if (cudaMallocHost(&s.h_words, 4 * sizeof(uint64_t)) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&s.ev_total, cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming) != cudaSuccess) return false;
         }
         if (cudaMallocHost(&small.h, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
         if (cudaMalloc(&small.d, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
@@ -187,6 +306,9 @@ struct Workspace {
             if (s.d_words) cudaFree(s.d_words);
             if (s.h_words) cudaFreeHost(s.h_words);
             if (s.ev_total) cudaEventDestroy(s.ev_total);
+            if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+            if (s.ev_out) cudaEventDestroy(s.ev_out);
+            for (HBuf *b : {&s.h_in, &s.h_off, &s.h_out_a, &s.h_out_b}) b->release();
             for (auto e : s.ev) cudaEventDestroy(e);
         }
         if (small.h) cudaFreeHost(small.h);
@@ -1170,7 +1292,18 @@ struct LocatePipe {
         int slot;
         uint64_t q0, cq;
         bool valid = false;
-    } pending;
+    } pending, pending_offsets;
+    bool stage_offsets = false;  // the caller's hit_offsets array is pageable
+
+    // hand the previous chunk's CSR offsets from the slot's pinned staging to the caller
+    gdx_status flush_offsets() {
+        if (!pending_offsets.valid) return GDX_OK;
+        pending_offsets.valid = false;
+        Slot &ps = ws->slot[pending_offsets.slot];
+        CUDA_TRY(cudaEventSynchronize(ps.ev_out));
+        HostPool::get().copy(hit_offsets + pending_offsets.q0, ps.h_out_a.p, pending_offsets.cq * 8);
+        return GDX_OK;
+    }
 
     // after k_search(mode 2) of a chunk: widths, exclusive scan, totals to the host
     gdx_status stage_counts(Slot &sl, int slot, uint64_t q0, uint64_t cq) {
@@ -1253,7 +1386,15 @@ struct LocatePipe {
         }
         k_add_base<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.local_off.as<uint64_t>(), cq, base);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(hit_offsets + q0, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+        if (stage_offsets) {
+            GDX_TRY(flush_offsets());  // frees the staging of the chunk before
+            CUDA_TRY(sl.h_out_a.reserve(cq * 8));
+            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            CUDA_TRY(cudaEventRecord(sl.ev_out, sl.stream));
+            pending_offsets = Pending{p.slot, q0, cq, true};
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(hit_offsets + q0, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+        }
         t_stats.kernel_launches += 1;
         total += n_hits;
         return GDX_OK;
@@ -1278,6 +1419,28 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     std::vector<TraceRow> trace_rows;
     const auto t_host0 = std::chrono::steady_clock::now();
     const uint64_t byte_end = query_bytes_end(qs, nq);
+    // Ordinary (pageable) caller memory would make every cudaMemcpyAsync a blocking, driver-staged copy at
+    // 8-14 GB/s.  Large batches are staged through the slots' own pinned buffers instead, copied by a few
+    // host threads (HostPool); pinned caller buffers take the direct path.
+    const uint64_t total_in = byte_end - query_bytes_end(qs, 0);
+    const bool stage_in = nq && total_in >= kStageMinBytes && !is_pinned(qs->bytes);
+    const bool stage_off = nq && qs->offsets && nq * 8 >= kStageMinBytes && !is_pinned(qs->offsets);
+    const bool stage_out = nq && !dev_a && !lp && nq * 8 >= kStageMinBytes && !is_pinned(out_a);
+    struct PendingOut {
+        int slot = 0;
+        uint64_t q0 = 0, cq = 0;
+        bool valid = false;
+    } pend_out;
+    auto finish_out = [&](PendingOut &p) -> gdx_status {
+        if (!p.valid) return GDX_OK;
+        p.valid = false;
+        Slot &ps = ws->slot[p.slot];
+        CUDA_TRY(cudaEventSynchronize(ps.ev_out));
+        HostPool::get().copy(out_a + p.q0, ps.h_out_a.p, p.cq * 8);
+        if (mode == 0) HostPool::get().copy(out_b + p.q0, ps.h_out_b.p, p.cq * 8);
+        return GDX_OK;
+    };
+    for (int s2 = 0; s2 < kSlots; ++s2) ws->slot[s2].h2d_pending = false;
     uint64_t budget = kChunkFirst;
     uint64_t q0 = 0;
     int k = 0;
@@ -1312,9 +1475,19 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             cudaEventCreate(&ev_h2d);
             cudaEventRecord(ev_h2d, sl.stream);
         }
-        if (byte1 > byte0)
-            CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, qs->bytes + (byte0 - 0), byte1 - byte0, cudaMemcpyHostToDevice,
-                                     sl.stream));
+        if ((stage_in || stage_off) && sl.h2d_pending) {  // the slot's staging buffers are free again
+            CUDA_TRY(cudaEventSynchronize(sl.ev_h2d));
+            sl.h2d_pending = false;
+        }
+        if (byte1 > byte0) {
+            const uint8_t *src = qs->bytes + byte0;
+            if (stage_in) {
+                CUDA_TRY(sl.h_in.reserve(byte1 - byte0));
+                HostPool::get().copy(sl.h_in.p, src, byte1 - byte0);
+                src = (const uint8_t *)sl.h_in.p;
+            }
+            CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, src, byte1 - byte0, cudaMemcpyHostToDevice, sl.stream));
+        }
         DevQueries dq;
         dq.bytes = sl.bytes.as<uint8_t>();
         dq.offsets = nullptr;
@@ -1323,8 +1496,13 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         dq.base = 0;
         if (qs->offsets) {
             CUDA_TRY(sl.offsets.reserve((cq + 1) * 8));
-            CUDA_TRY(cudaMemcpyAsync(sl.offsets.p, qs->offsets + q0, (cq + 1) * 8, cudaMemcpyHostToDevice,
-                                     sl.stream));
+            const uint64_t *osrc = qs->offsets + q0;
+            if (stage_off) {
+                CUDA_TRY(sl.h_off.reserve((cq + 1) * 8));
+                HostPool::get().copy(sl.h_off.p, osrc, (cq + 1) * 8);
+                osrc = (const uint64_t *)sl.h_off.p;
+            }
+            CUDA_TRY(cudaMemcpyAsync(sl.offsets.p, osrc, (cq + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
             dq.offsets = sl.offsets.as<uint64_t>();
             dq.base = byte0;
         }
@@ -1340,6 +1518,10 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
                 CUDA_TRY(sl.out_b.reserve(cq * 8));
                 b = sl.out_b.as<uint64_t>();
             }
+        }
+        if (stage_in || stage_off) {
+            CUDA_TRY(cudaEventRecord(sl.ev_h2d, sl.stream));
+            sl.h2d_pending = true;
         }
         cudaEvent_t e0 = ws->next_event(sl), e1 = ws->next_event(sl);
         CUDA_TRY(cudaEventRecord(e0, sl.stream));
@@ -1361,6 +1543,17 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             const LocatePipe::Pending prev = lp->take_pending();
             GDX_TRY(lp->stage_counts(sl, k % kSlots, q0, cq));
             GDX_TRY(lp->finish(prev));
+        } else if (stage_out) {  // results go to pinned staging; the previous chunk's are handed over meanwhile
+            PendingOut prev = pend_out;
+            CUDA_TRY(sl.h_out_a.reserve(cq * 8));
+            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            if (mode == 0) {
+                CUDA_TRY(sl.h_out_b.reserve(cq * 8));
+                CUDA_TRY(cudaMemcpyAsync(sl.h_out_b.p, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            }
+            CUDA_TRY(cudaEventRecord(sl.ev_out, sl.stream));
+            pend_out = PendingOut{k % kSlots, q0, cq, true};
+            GDX_TRY(finish_out(prev));
         } else if (!dev_a) {
             CUDA_TRY(cudaMemcpyAsync(out_a + q0, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
             if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
@@ -1374,6 +1567,8 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         ++k;
     }
     if (lp) GDX_TRY(lp->finish(lp->take_pending()));
+    if (lp) GDX_TRY(lp->flush_offsets());
+    GDX_TRY(finish_out(pend_out));
     const double t_issue = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count() : 0;
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(ws->slot[s].stream));
     if (trace && !trace_rows.empty()) {
@@ -1577,6 +1772,7 @@ extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *q
     if (pipelined) {
         // every chunk of the search pipeline carries on with counts -> scan -> expand -> walk -> D2H
         LocatePipe lp{idx, ws, hit_offsets};
+        lp.stage_offsets = n * 8 >= kStageMinBytes && !is_pinned(hit_offsets);
         GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * sizeof(gdx_hit), &lp.pinned, &lp.pinned_cap));
         gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 2, nullptr, nullptr, &lp);
         if (st != GDX_OK) {
