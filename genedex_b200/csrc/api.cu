@@ -1832,9 +1832,6 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
     GDX_TRY(begin_call(idx, "gdx_extend_many"));
     if (n == 0) return GDX_OK;
     if (!starts || !ends || !io_symbols) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    for (uint64_t i = 0; i < n; ++i)  // text_with_rank_support/mod.rs:106-110 bounds assert
-        if (starts[i] > idx->h.n || ends[i] > idx->h.n)
-            return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)i);
     DeviceGuard guard(idx->device);
     WsLease lease(idx);
     Workspace *ws = lease.w;
@@ -1843,9 +1840,21 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
     CUDA_TRY(ws->starts.reserve(n * 8));
     CUDA_TRY(ws->ends.reserve(n * 8));
     CUDA_TRY(ws->symbols.reserve(n));
-    CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 8, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->starts.p, starts, n * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 16, st));  // [0] invalid symbol, [1] cursor out of bounds
+    // large pageable cursor arrays go through pinned staging (see search_host)
+    Slot &sl = ws->slot[0];
+    const bool stage = n * 8 >= kStageMinBytes && !(is_pinned(starts) && is_pinned(ends));
+    const uint64_t *src_s = starts, *src_e = ends;
+    if (stage) {
+        CUDA_TRY(sl.h_out_a.reserve(n * 8));
+        CUDA_TRY(sl.h_out_b.reserve(n * 8));
+        HostPool::get().copy(sl.h_out_a.p, starts, n * 8);
+        HostPool::get().copy(sl.h_out_b.p, ends, n * 8);
+        src_s = (const uint64_t *)sl.h_out_a.p;
+        src_e = (const uint64_t *)sl.h_out_b.p;
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws->starts.p, src_s, n * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->ends.p, src_e, n * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ws->symbols.p, io_symbols, n, cudaMemcpyHostToDevice, st));
     GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
         k_extend<decltype(L)><<<(unsigned)div_up(n, 256), 256, 0, st>>>(
@@ -1853,16 +1862,28 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
         return GDX_OK;
     }));
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16, cudaMemcpyDeviceToHost, st));
+    if (stage) {  // optimistic copy-out into the staging buffers; handed to the caller only on success
+        CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, ws->starts.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(sl.h_out_b.p, ws->ends.p, n * 8, cudaMemcpyDeviceToHost, st));
+    }
     CUDA_TRY(cudaStreamSynchronize(st));
     t_stats.kernel_launches = 1;
+    if (ws->small.h[1] != kNoError)  // checked on the device: text_with_rank_support/mod.rs:106-110
+        return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)ws->small.h[1]);
     if (ws->small.h[0] != kNoError) {
         t_error_query = ws->small.h[0];
         return fail(GDX_ERR_INVALID_SYMBOL, "cursor %llu: symbol in io representation should be valid (alphabet.rs:195-198)",
                     (unsigned long long)ws->small.h[0]);
     }
-    CUDA_TRY(cudaMemcpy(starts, ws->starts.p, n * 8, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(ends, ws->ends.p, n * 8, cudaMemcpyDeviceToHost));
+    if (stage) {
+        HostPool::get().copy(starts, sl.h_out_a.p, n * 8);
+        HostPool::get().copy(ends, sl.h_out_b.p, n * 8);
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(starts, ws->starts.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ends, ws->ends.p, n * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     return GDX_OK;
 }
 

@@ -520,6 +520,10 @@ k_extend(const __grid_constant__ DevIndex ix, uint64_t *__restrict__ starts, uin
         return;
     }
     uint64_t s = starts[q], e = ends[q];
+    if (s > ix.n || e > ix.n) {  // text_with_rank_support/mod.rs:106-110 bounds assert
+        report_error(err + 1, q);
+        return;
+    }
     if (s != e) {
         lf_pair<L>(ix, c, s, e);
         starts[q] = s;

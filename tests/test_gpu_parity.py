@@ -610,3 +610,25 @@ def test_c_example_runs(gdx, tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "query 3: count 1" in out.stdout
+
+
+def test_extend_many_large_and_bounds(gdx):
+    # large pageable cursor arrays take the staged path; out-of-range cursors are rejected (mod.rs:106-110)
+    rng = np.random.default_rng(2)
+    n = 400_000
+    text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+    oidx = O.OracleIndex.build([text.tobytes()], util.oracle_alphabet("ascii_dna"), "u32", 4, 0)
+    pidx = gdx.FmIndexConfig("u32").construct_index([text.tobytes()], gdx.alphabet.ascii_dna())
+    nc = 1_000_000
+    a = rng.integers(0, n + 1, nc).astype(np.uint64)
+    b = rng.integers(0, n + 1, nc).astype(np.uint64)
+    starts, ends = np.minimum(a, b), np.maximum(a, b)
+    syms = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, nc)]
+    gs, ge = pidx.extend_many_packed(starts, ends, syms)
+    for i in rng.integers(0, nc, 3000):
+        assert (int(gs[i]), int(ge[i])) == oidx.extend_query_front((int(starts[i]), int(ends[i])), int(syms[i]))
+    bad = starts.copy()
+    bad[123456] = n + 5
+    with pytest.raises(gdx.GenedexError) as e:
+        pidx.extend_many_packed(bad, np.maximum(bad, ends), syms)
+    assert "123456" in str(e.value)
