@@ -259,8 +259,8 @@ class FmIndex:
         return hit_offsets, self._take_hits(hp, nh.value)
 
     def extend_many_packed(self, starts: np.ndarray, ends: np.ndarray, io_symbols: np.ndarray):
-        starts = np.ascontiguousarray(starts, dtype=np.uint64).copy()
-        ends = np.ascontiguousarray(ends, dtype=np.uint64).copy()
+        starts = np.array(starts, dtype=np.uint64, order="C")  # one copy: the C call extends in place
+        ends = np.array(ends, dtype=np.uint64, order="C")
         sym = np.ascontiguousarray(io_symbols, dtype=np.uint8)
         _check(self._lib.gdx_extend_many(self._h, starts.ctypes.data, ends.ctypes.data, sym.ctypes.data, starts.size))
         return starts, ends
