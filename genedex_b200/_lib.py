@@ -17,6 +17,7 @@ GDX_I32, GDX_U32, GDX_I64 = 0, 1, 2
 GDX_CONSTRUCT_HOST, GDX_CONSTRUCT_DEVICE, GDX_CONSTRUCT_AUTO = 0, 1, 2
 GDX_FLAG_VERIFY_SUFFIX_ARRAY = 1
 GDX_FLAG_NO_TEXT = 2
+GDX_FLAG_NO_INVERSE_SAMPLES = 4
 
 
 class gdx_alphabet(C.Structure):
@@ -55,7 +56,8 @@ class gdx_index_info(C.Structure):
                 ("rank_record_bytes", C.c_uint32), ("rank_positions_per_record", C.c_uint32),
                 ("device", C.c_int32), ("image_bytes", C.c_uint64), ("rank_bytes", C.c_uint64),
                 ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64), ("num_samples", C.c_uint64),
-                ("num_text_borders", C.c_uint64), ("text_bytes", C.c_uint64)]
+                ("num_text_borders", C.c_uint64), ("text_bytes", C.c_uint64),
+                ("inverse_sample_bytes", C.c_uint64)]
 
 
 class gdx_stats(C.Structure):

@@ -428,6 +428,9 @@ struct ImageSources {
     const uint64_t *h_samples64 = nullptr;  // host
     const void *d_samples = nullptr;        // device, element width given by d_samples_wide
     bool d_samples_wide = false;
+    // optional sampled inverse suffix array (one of them, only together with d_text)
+    const uint64_t *h_isa64 = nullptr;      // host
+    const uint32_t *d_isa32 = nullptr;      // device
 };
 
 gdx_status validate_alphabet(const gdx_alphabet &a) {
@@ -497,6 +500,12 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     if (src.d_text) {
         h.text_bits = h.sigma <= 16 ? 4 : 8;
         h.off_text = place(h.text_bits == 4 ? (src.n + 1) / 2 : src.n);
+    }
+    h.has_isa = 0;
+    h.off_isa = off;
+    if (h.text_bits && (src.h_isa64 || src.d_isa32)) {
+        h.has_isa = 1;
+        h.off_isa = place(h.n_samples * esz);
     }
     h.image_bytes = off;
     return GDX_OK;
@@ -591,6 +600,23 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
         }
     }
 
+    if (h.has_isa && h.n_samples) {  // same element width as the SA samples
+        void *dst = base + h.off_isa;
+        if (src.h_isa64) {
+            if (h.wide) {
+                IMG_TRY(cudaMemcpy(dst, src.h_isa64, h.n_samples * 8, cudaMemcpyHostToDevice));
+            } else {
+                std::vector<uint32_t> narrow(h.n_samples);
+                for (uint64_t i = 0; i < h.n_samples; ++i) narrow[i] = (uint32_t)src.h_isa64[i];
+                IMG_TRY(cudaMemcpy(dst, narrow.data(), h.n_samples * 4, cudaMemcpyHostToDevice));
+            }
+        } else if (h.wide) {
+            k_widen_u32<<<(unsigned)div_up(h.n_samples, 256), 256>>>(src.d_isa32, h.n_samples, (uint64_t *)dst);
+            IMG_TRY(cudaGetLastError());
+        } else {
+            IMG_TRY(cudaMemcpy(dst, src.d_isa32, h.n_samples * 4, cudaMemcpyDeviceToDevice));
+        }
+    }
     if (h.text_bits && h.n) {
         const uint64_t items = h.text_bits == 4 ? (h.n + 1) / 2 : h.n;
         k_pack_text<<<(unsigned)div_up(items, 256), 256>>>(src.d_text, h.n, h.text_bits, base + h.off_text);
@@ -720,6 +746,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     // the dense text goes to the device once: input of the device suffix sort and source of the
     // optional text section of the image
     const bool keep_text = (config->flags & GDX_FLAG_NO_TEXT) == 0;
+    const bool keep_isa = keep_text && (config->flags & GDX_FLAG_NO_INVERSE_SAMPLES) == 0;
     struct DevText {
         uint8_t *p = nullptr;
         ~DevText() {
@@ -743,7 +770,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         DeviceBuildResult r;
         const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
         st = device_build_from_text(nullptr, d_text.p, n, alphabet->num_dense_symbols,
-                                    config->suffix_array_sampling_rate, r, t_error, false, verify);
+                                    config->suffix_array_sampling_rate, r, t_error, false, verify, keep_isa);
         if (st != GDX_OK) return st;
         if (verify && r.verify_violations) {
             r.release();
@@ -756,6 +783,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         src.d_bwt = r.d_bwt;
         src.d_samples = r.d_samples;
         src.d_samples_wide = false;
+        src.d_isa32 = r.d_isa_samples;
         st = build_image(src, device, out);
         r.release();
         return st;
@@ -775,6 +803,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     src.n_border = hp.border_rows.size();
     src.d_bwt = d_bwt;
     src.h_samples64 = hp.samples.data();
+    if (keep_isa) src.h_isa64 = hp.isa_samples.data();
     st = build_image(src, device, out);
     cudaFree(d_bwt);
     return st;
@@ -1006,7 +1035,8 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->lookup_bytes = h.off_border_rows - h.off_lookup;
     out->num_samples = h.n_samples;
     out->num_text_borders = h.n_border;
-    out->text_bytes = h.text_bits ? h.image_bytes - h.off_text : 0;
+    out->text_bytes = h.text_bits ? h.off_isa - h.off_text : 0;
+    out->inverse_sample_bytes = h.has_isa ? h.image_bytes - h.off_isa : 0;
     return GDX_OK;
 }
 
@@ -1179,7 +1209,7 @@ void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint
                    cudaStream_t stream) {
     if (dq.nq == 0) return;
     const unsigned grid = (unsigned)div_up(dq.nq, 256);
-    if (mode != 0 && idx->dev.text && verify_enabled())
+    if (idx->dev.text && verify_enabled() && (mode != 0 || idx->dev.isa))
         k_search<L, true><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
     else
         k_search<L, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);

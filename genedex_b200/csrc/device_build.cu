@@ -18,6 +18,8 @@ void DeviceBuildResult::release() {
     if (d_bwt) cudaFree(d_bwt);
     if (d_samples) cudaFree(d_samples);
     if (d_sa) cudaFree(d_sa);
+    if (d_isa_samples) cudaFree(d_isa_samples);
+    d_isa_samples = nullptr;
     d_bwt = nullptr;
     d_samples = nullptr;
     d_sa = nullptr;
@@ -144,6 +146,15 @@ __global__ void k_bwt_and_samples(const uint8_t *__restrict__ text, const uint32
     }
 }
 
+// inverse suffix array at every s-th text position: out[SA[i] / s] = i for SA[i] % s == 0
+__global__ void k_sample_isa(const uint32_t *__restrict__ sa, uint64_t n, uint32_t sampling_rate,
+                             uint32_t *__restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = sa[i];
+    if (p % sampling_rate == 0) out[p / sampling_rate] = (uint32_t)i;
+}
+
 __global__ void k_count_zeros(const uint8_t *__restrict__ text, uint64_t n, unsigned long long *out) {
     uint64_t local = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
@@ -199,7 +210,7 @@ unsigned grid_for(uint64_t n, unsigned block = 256) { return (unsigned)((n + blo
 
 gdx_status device_build_from_text(const uint8_t *h_text, const uint8_t *d_text_in, uint64_t n, uint32_t sigma,
                                   uint32_t sampling_rate, DeviceBuildResult &out, std::string &err, bool keep_sa,
-                                  bool verify) {
+                                  bool verify, bool want_isa) {
     if (n >= 0xffffffffull) {
         err = "device construction supports text lengths below 2^32 - 1";
         return GDX_ERR_UNSUPPORTED;
@@ -401,6 +412,13 @@ gdx_status device_build_from_text(const uint8_t *h_text, const uint8_t *d_text_i
     for (uint64_t i = 0; i < nborder; ++i) {
         out.border_rows[i] = rows[order[i]];
         out.border_pos[i] = pos[order[i]];
+    }
+    if (want_isa) {
+        Dev isa_s;
+        DB_TRY(isa_s.alloc(nsamp * 4));
+        k_sample_isa<<<grid_for(n), 256>>>(sa.as<uint32_t>(), n, sampling_rate, isa_s.as<uint32_t>());
+        DB_TRY(cudaGetLastError());
+        out.d_isa_samples = (uint32_t *)isa_s.take();
     }
     out.d_bwt = (uint8_t *)bwt.take();
     out.d_samples = (uint32_t *)samples.take();

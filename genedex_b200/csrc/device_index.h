@@ -13,6 +13,8 @@
 //   text         (optional) the concatenated dense text, 4 bits per symbol (sigma <= 16) or 8: lets
 //                count/locate finish a query whose interval has narrowed to one row by one text
 //                comparison instead of one random rank record per remaining symbol
+//   isa          (optional, with text) ISA[0], ISA[s], ISA[2s], ...: the SA row of every s-th text position;
+//                lets cursors_for_many_queries turn a verified text position back into its interval
 #ifndef GDX_DEVICE_INDEX_H
 #define GDX_DEVICE_INDEX_H
 
@@ -40,7 +42,8 @@ struct ImageHeader {
     uint64_t off_records, off_sbc, off_samples, off_lookup, off_border_rows, off_border_pos,
         off_sentinels, off_count, off_text;
     uint32_t text_bits;  // 0 = no text section, 4 or 8
-    uint32_t pad1;
+    uint32_t has_isa;    // sampled inverse suffix array present
+    uint64_t off_isa;
     uint64_t image_bytes;
     uint64_t lut_level_off[kMaxLookupDepth + 1];  // entry offset of level d
     uint64_t lut_pow[kMaxLookupDepth + 1];        // ns^d
@@ -58,6 +61,7 @@ struct DevIndex {
     const uint64_t *sentinels;
     const uint64_t *count;
     const uint8_t *text;
+    const void *isa;  // sampled inverse suffix array (same element width as samples) or nullptr
     uint64_t n, ntexts, n_border;
     uint32_t sigma, ns, sampling_rate, lookup_depth;
     uint32_t wide, noff, stride, derived_symbol;
@@ -87,6 +91,7 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.count = (const uint64_t *)(base + h.off_count);
     d.text = h.text_bits ? base + h.off_text : nullptr;
     d.text_bits = h.text_bits;
+    d.isa = h.has_isa ? base + h.off_isa : nullptr;
     d.n = h.n;
     d.ntexts = h.ntexts;
     d.n_border = h.n_border;

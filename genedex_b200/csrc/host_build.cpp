@@ -216,8 +216,10 @@ void parts_from_sa(const uint8_t *text, uint64_t n, const I *sa, uint32_t sampli
     out.samples.reserve(n / sampling_rate + 1);
     out.border_rows.clear();
     out.border_pos.clear();
+    out.isa_samples.assign((n + sampling_rate - 1) / sampling_rate, 0);
     for (uint64_t i = 0; i < n; ++i) {
         const uint64_t p = (uint64_t)sa[i];
+        if (p % sampling_rate == 0) out.isa_samples[p / sampling_rate] = i;
         const uint8_t b = text[(p > 0 ? p : n) - 1];  // bwt.rs:96-105
         out.bwt[i] = b;
         if (b == 0) {  // bwt.rs:108-116

@@ -27,6 +27,7 @@ struct HostParts {
     uint64_t n = 0;
     std::vector<uint8_t> bwt;
     std::vector<uint64_t> samples;       // SA[0], SA[s], ...
+    std::vector<uint64_t> isa_samples;   // ISA[0], ISA[s], ... (row of every s-th text position)
     std::vector<uint64_t> border_rows;   // ascending
     std::vector<uint64_t> border_pos;
 };

@@ -262,6 +262,40 @@ __device__ __forceinline__ uint64_t resolve_row(const DevIndex &ix, uint64_t i, 
     }
 }
 
+// one LF step from an SA row: row of the suffix that starts one text position earlier (the BWT symbol of
+// the row must not be the sentinel -- callers stay inside a region that matched query symbols)
+template <class L>
+__device__ __forceinline__ uint64_t lf_row(const DevIndex &ix, uint64_t row) {
+    typename L::Planes pl = L::load_planes_once(ix, row);
+    const uint32_t c = L::symbol_at(pl, row);
+    if (c == 0) return row;
+    if (c > ix.noff) return L::lf_derived(ix, row);
+    typename L::Rec r = L::with_offset(ix, pl, row, c);
+    return sbc_load(ix, row, c) + L::local_rank(r, c, row);
+}
+
+template <class L>
+__device__ __forceinline__ uint64_t lf_one(const DevIndex &ix, uint32_t c, uint64_t i) {
+    if (c > ix.noff) return L::lf_derived(ix, i);
+    typename L::Rec r = L::load_once(ix, i, c);
+    return sbc_load(ix, i, c) + L::local_rank(r, c, i);
+}
+
+// ISA[t] = SA row of the suffix starting at text position t, from the sampled inverse suffix array:
+// start at the next sampled position q >= t and walk q - t LF steps back.  Every text position in [t, q)
+// must hold a non-sentinel symbol (callers guarantee q lies inside a matched region).
+template <class L>
+__device__ __forceinline__ uint64_t isa_row(const DevIndex &ix, uint64_t t, uint32_t &steps) {
+    const uint64_t k = (t + ix.sampling_rate - 1) / ix.sampling_rate;
+    uint64_t row = ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.isa) + k)
+                           : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.isa) + k);
+    for (uint64_t q = k * ix.sampling_rate; q > t; --q) {
+        row = lf_row<L>(ix, row);
+        ++steps;
+    }
+    return row;
+}
+
 // dense symbol at concatenated-text position p (text section of the image)
 __device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) {
     if (ix.text_bits == 4) return (__ldg(ix.text + (p >> 1)) >> ((p & 1) * 4)) & 15u;
@@ -447,11 +481,16 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         // (deferring it behind the loop so that it runs once per warp was measured 22 % slower).
         bool direct = false;
         while (!bad && pos > 0 && s != e) {
-            if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining) {
+            // mode 0 (cursors) must also produce the interval: possible with the sampled inverse suffix
+            // array once at least sampling_rate symbols have matched (the ISA walk stays inside them)
+            if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining &&
+                (mode != 0 || (ix.isa != nullptr && len - pos >= ix.sampling_rate))) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
                 const uint64_t at = resolve_row<L>(ix, s, vsteps);
                 vrows = 1;
                 bool match = true;
+                uint64_t jm = 0;     // query position of the first mismatch (from the right)
+                uint32_t cm = 0;     // its dense symbol
                 for (uint64_t j = pos; match && j-- > 0;) {
                     const uint32_t c = GDX_SYMBOL_AT(j);
                     if (c == 0) {  // the reference reaches this symbol with a non-empty interval
@@ -460,13 +499,30 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                     }
                     const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
                     match = back <= at && text_symbol(ix, at - back) == c;
+                    if (!match) {
+                        jm = j;
+                        cm = c;
+                    }
                 }
-                if (match && !bad) {
-                    direct = true;
-                    s = at - pos;  // text position of the whole query
+                if (bad) {
+                    s = e = 0;
+                } else if (mode != 0) {
+                    if (match) {
+                        direct = true;
+                        s = at - pos;  // text position of the whole query
+                        e = s + 1;
+                    } else {
+                        s = e = 0;
+                    }
+                } else if (match) {
+                    // the reference ends on [y, y + 1), y = row of the suffix at the query's text position
+                    s = isa_row<L>(ix, at - pos, vsteps);
                     e = s + 1;
                 } else {
-                    s = e = 0;
+                    // the reference's interval became empty at query[jm]: both borders of the one-row
+                    // interval [r, r + 1) of query[jm+1..] map to count[c] + rank(c, r)  (lib.rs:273-275)
+                    const uint64_t r = isa_row<L>(ix, at - (pos - jm - 1), vsteps);
+                    s = e = lf_one<L>(ix, cm, r);
                 }
                 break;
             }

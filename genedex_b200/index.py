@@ -111,6 +111,13 @@ class FmIndexConfig:
         self._flags = (self._flags & ~_lib.GDX_FLAG_NO_TEXT) | (0 if keep else _lib.GDX_FLAG_NO_TEXT)
         return self
 
+    def keep_inverse_samples(self, keep: bool = True) -> "FmIndexConfig":
+        """Keep the sampled inverse suffix array (default, needs the text): cursors_for_many_queries then
+        finishes one-row intervals through the text as well.  Results are identical either way."""
+        self._flags = (self._flags & ~_lib.GDX_FLAG_NO_INVERSE_SAMPLES) | (
+            0 if keep else _lib.GDX_FLAG_NO_INVERSE_SAMPLES)
+        return self
+
     def device(self, ordinal: int) -> "FmIndexConfig":
         self._device = ordinal
         return self

@@ -78,6 +78,9 @@ typedef struct gdx_config {
  * count/locate then run every LF step instead of finishing one-row intervals by a text comparison.
  * Results are identical either way. */
 #define GDX_FLAG_NO_TEXT 2u
+/* do not keep the sampled inverse suffix array (n / rate entries, only kept together with the text):
+ * cursors_for_many_queries then runs every LF step. Results are identical either way. */
+#define GDX_FLAG_NO_INVERSE_SAMPLES 4u
 
 /* src/lib.rs:331-335 Hit { text_id, position } */
 typedef struct gdx_hit {
@@ -136,6 +139,7 @@ typedef struct gdx_index_info {
     uint64_t rank_bytes, sample_bytes, lookup_bytes;
     uint64_t num_samples, num_text_borders;
     uint64_t text_bytes;           /* packed text section, 0 if absent */
+    uint64_t inverse_sample_bytes; /* sampled inverse suffix array, 0 if absent */
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */

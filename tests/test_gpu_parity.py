@@ -632,3 +632,40 @@ def test_extend_many_large_and_bounds(gdx):
     with pytest.raises(gdx.GenedexError) as e:
         pidx.extend_many_packed(bad, np.maximum(bad, ends), syms)
     assert "123456" in str(e.value)
+
+
+def test_cursor_shortcut_uses_inverse_samples(gdx):
+    # with text + sampled inverse suffix array, cursors_for_many_queries finishes one-row intervals through
+    # the text too and must still return the reference's intervals bit for bit -- also the value of an
+    # empty interval (start == end == count[c] + rank(c, row) of the failing step)
+    rng = random.Random(5)
+    texts = [bytes(rng.choice(b"ACGT") for _ in range(30_000)), bytes(rng.choice(b"ACGTN") for _ in range(5_000)), b"ACGT"]
+    for s_rate, depth in ((4, 0), (3, 2), (16, 0), (64, 1)):
+        oidx, pidx = util.build_pair(gdx, texts, "ascii_dna_with_n", "u32", s_rate, depth, True)
+        assert pidx.info().inverse_sample_bytes > 0
+        qs = []
+        for _ in range(2000):
+            t = rng.choice(texts[:2])
+            m = rng.randrange(10, 100)
+            p = rng.randrange(0, len(t) - m)
+            q = bytearray(t[p:p + m])
+            if rng.random() < 0.5:
+                q[rng.randrange(m)] = rng.choice(b"ACGT")
+            if rng.random() < 0.1:
+                q = bytearray(bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(1, 9))) + t[:m])
+            if depth > 0 and b"N" in q:
+                continue
+            qs.append(bytes(q))
+        data, off = O.pack(qs)
+        os_, oe_ = oidx.cursors_many_packed(data, off)
+        ps_, pe_ = pidx.cursors_many_packed(data, off)
+        assert np.array_equal(os_, ps_) and np.array_equal(oe_, pe_)
+        st = pidx.stats()
+        if s_rate <= 16:
+            assert st.verified_queries > 500  # the shortcut ran for cursors
+        no_isa = gdx.FmIndexConfig("u32").suffix_array_sampling_rate(s_rate).lookup_table_depth(depth) \\
+            .keep_inverse_samples(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        assert no_isa.info().inverse_sample_bytes == 0 and no_isa.info().text_bytes > 0
+        ns_, ne_ = no_isa.cursors_many_packed(data, off)
+        assert np.array_equal(os_, ns_) and np.array_equal(oe_, ne_)
+        assert no_isa.stats().verified_queries == 0
