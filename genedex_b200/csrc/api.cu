@@ -1209,10 +1209,13 @@ void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint
                    cudaStream_t stream) {
     if (dq.nq == 0) return;
     const unsigned grid = (unsigned)div_up(dq.nq, 256);
-    if (idx->dev.text && verify_enabled() && (mode != 0 || idx->dev.isa))
-        k_search<L, true><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+    const bool verify = idx->dev.text && verify_enabled();
+    if (verify && mode != 0)
+        k_search<L, true, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+    else if (verify && idx->dev.isa)
+        k_search<L, true, true><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
     else
-        k_search<L, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+        k_search<L, false, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
 }
 
 // ---- suffix sort of a query batch (locality of the first search steps, see k_query_keys) -------------

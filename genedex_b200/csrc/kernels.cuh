@@ -35,6 +35,10 @@
 
 #include "device_index.h"
 
+#ifndef GDX_K32_VERIFY_MIN_BLOCKS
+#define GDX_K32_VERIFY_MIN_BLOCKS 6
+#endif
+
 namespace gdx {
 
 struct DevQueries {
@@ -83,6 +87,7 @@ __device__ __forceinline__ void ldg128_na(const void *p, uint64_t &lo, uint64_t 
 struct K32 {
     static constexpr uint32_t kLog2P = 6;
     static constexpr int kSearchMinBlocks = 6;  // 40 registers: 1536 threads per SM
+    static constexpr int kVerifyMinBlocks = GDX_K32_VERIFY_MIN_BLOCKS;
     struct Planes {
         uint64_t w[4];
     };
@@ -142,6 +147,7 @@ template <int B>
 struct KG {
     static constexpr uint32_t kLog2P = 7;
     static constexpr int kSearchMinBlocks = B <= 3 ? 5 : (B <= 5 ? 4 : 3);
+    static constexpr int kVerifyMinBlocks = kSearchMinBlocks;
     struct Planes {
         uint64_t lo[B], hi[B];
     };
@@ -421,8 +427,9 @@ constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, co
 // are identical, the invalid-symbol panic fires at the same symbol, only the interval itself is not
 // produced -- so mode 0 (cursors) never uses it.  mode 2 = locate: out_a/out_b carry either the
 // interval or (text position, kDirectHit).
-template <class L, bool VERIFY>
-__global__ void __launch_bounds__(256, L::kSearchMinBlocks)
+// CURSORS (mode 0 with VERIFY): compile the inverse-sample path only into the variant that needs it
+template <class L, bool VERIFY, bool CURSORS>
+__global__ void __launch_bounds__(256, VERIFY ? L::kVerifyMinBlocks : L::kSearchMinBlocks)
 k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__restrict__ out_a,
          uint64_t *__restrict__ out_b, int mode, uint64_t q_index_base, uint64_t *err,
          unsigned long long *stat_steps, const uint32_t *__restrict__ perm) {
@@ -484,7 +491,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             // mode 0 (cursors) must also produce the interval: possible with the sampled inverse suffix
             // array once at least sampling_rate symbols have matched (the ISA walk stays inside them)
             if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining &&
-                (mode != 0 || (ix.isa != nullptr && len - pos >= ix.sampling_rate))) {
+                (!CURSORS || len - pos >= ix.sampling_rate)) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
                 const uint64_t at = resolve_row<L>(ix, s, vsteps);
                 vrows = 1;
@@ -499,14 +506,14 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                     }
                     const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
                     match = back <= at && text_symbol(ix, at - back) == c;
-                    if (!match) {
+                    if (CURSORS && !match) {
                         jm = j;
                         cm = c;
                     }
                 }
                 if (bad) {
                     s = e = 0;
-                } else if (mode != 0) {
+                } else if (!CURSORS) {
                     if (match) {
                         direct = true;
                         s = at - pos;  // text position of the whole query

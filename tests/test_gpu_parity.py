@@ -663,8 +663,8 @@ def test_cursor_shortcut_uses_inverse_samples(gdx):
         st = pidx.stats()
         if s_rate <= 16:
             assert st.verified_queries > 500  # the shortcut ran for cursors
-        no_isa = gdx.FmIndexConfig("u32").suffix_array_sampling_rate(s_rate).lookup_table_depth(depth) \\
-            .keep_inverse_samples(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        no_isa = (gdx.FmIndexConfig("u32").suffix_array_sampling_rate(s_rate).lookup_table_depth(depth)
+                  .keep_inverse_samples(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n()))
         assert no_isa.info().inverse_sample_bytes == 0 and no_isa.info().text_bytes > 0
         ns_, ne_ = no_isa.cursors_many_packed(data, off)
         assert np.array_equal(os_, ns_) and np.array_equal(oe_, ne_)

@@ -113,6 +113,25 @@ def time_device_count(gdx, pidx, q_dev, m, nq, reps=5):
     return e0.elapsed_time(e1) / reps, d_counts.cpu().numpy().astype(np.uint64)
 
 
+def time_device_cursors(gdx, pidx, q_dev, m, nq, reps=5):
+    torch = _torch()
+    lib = gdx._lib.load()
+    d_s = torch.zeros(nq, dtype=torch.int64, device=q_dev.device)
+    d_e = torch.zeros(nq, dtype=torch.int64, device=q_dev.device)
+    qs = gdx._lib.gdx_queries(q_dev.data_ptr(), None, m, nq)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        assert lib.gdx_cursors_many_device(pidx.handle, C.byref(qs), d_s.data_ptr(), d_e.data_ptr(), None, stream) == 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        assert lib.gdx_cursors_many_device(pidx.handle, C.byref(qs), d_s.data_ptr(), d_e.data_ptr(), None, stream) == 0
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev, m, nq, depth, s,
              origin=None, oracle_sample=200_000, locate=True, verify_text=None):
     """texts_io: host uint8 array of all texts back to back; origin = (text ids, positions) of the first
@@ -162,7 +181,9 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
     for _ in range(3):
         es, ee = pidx.extend_many_packed(cs, ce, sym)
     ext_ms = (time.perf_counter() - t0) * 1e3 / 3
-    res.update({"cursors_e2e_ms": round(cur_ms, 3), "cursors_e2e_queries_per_s": nq / (cur_ms * 1e-3),
+    cur_kernel_ms = time_device_cursors(gdx, pidx, q_dev, m, nq)
+    res.update({"cursors_kernel_ms": round(cur_kernel_ms, 3), "cursors_queries_per_s": nq / (cur_kernel_ms * 1e-3),
+                "cursors_e2e_ms": round(cur_ms, 3), "cursors_e2e_queries_per_s": nq / (cur_ms * 1e-3),
                 "extend_many_e2e_ms": round(ext_ms, 3), "extend_many_cursors_per_s": nq / (ext_ms * 1e-3)})
 
     if locate:
