@@ -241,16 +241,17 @@ private:
 constexpr uint64_t kStageMinBytes = 4ull << 20;  // smaller transfers go through the driver's own staging
 
 constexpr int kSlots = 3;
-// Pipeline chunking: the byte budget of successive chunks doubles from kChunkFirst to kChunkMax
+// Pipeline chunking (defaults 4 / 32 / 4 MB, profiles/r1_ab_pipeline_chunks.txt): the byte budget of
+// successive chunks doubles from kChunkFirst to kChunkMax
 // (fast pipeline fill, then few large launches: less launch overhead and deeper shared suffixes for the
 // per-chunk query sort) and the batch ends with a chunk of about kChunkTail (short drain).
 uint64_t env_mb(const char *name, uint64_t dflt) {
     const char *e = getenv(name);
     return (uint64_t)(e && atoi(e) > 0 ? atoi(e) : dflt) << 20;
 }
-const uint64_t kChunkFirst = env_mb("GDX_CHUNK_FIRST_MB", 8);
-const uint64_t kChunkMax = env_mb("GDX_CHUNK_MAX_MB", 64);
-const uint64_t kChunkTail = env_mb("GDX_CHUNK_TAIL_MB", 8);
+const uint64_t kChunkFirst = env_mb("GDX_CHUNK_FIRST_MB", 4);
+const uint64_t kChunkMax = env_mb("GDX_CHUNK_MAX_MB", 32);
+const uint64_t kChunkTail = env_mb("GDX_CHUNK_TAIL_MB", 4);
 constexpr uint64_t kChunkMaxQueries = 64ull << 20;
 
 struct Slot {
