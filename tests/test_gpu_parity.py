@@ -475,10 +475,10 @@ def test_text_verification_shortcut_semantics(gdx):
             (invalid if b"X" in q else valid).append(bytes(q))
         util.assert_same_results(oidx, pidx, valid)
         util.assert_same_results(oidx, lf_only, valid)
-        assert pidx.stats().verified_queries > 0 or True
         data, offsets = O.pack(valid)
         pidx.count_many_packed(data, offsets)
-        assert pidx.stats().verified_queries > 100  # the shortcut really ran
+        if os.environ.get("GDX_VERIFY", "1") != "0":
+            assert pidx.stats().verified_queries > 100  # the shortcut really ran
         lf_only.count_many_packed(data, offsets)
         assert lf_only.stats().verified_queries == 0
         for q in invalid:  # one query per call: panic <=> exception, otherwise equal results
@@ -662,7 +662,8 @@ def test_cursor_shortcut_uses_inverse_samples(gdx):
         assert np.array_equal(os_, ps_) and np.array_equal(oe_, pe_)
         st = pidx.stats()
         if s_rate <= 16:
-            assert st.verified_queries > 500  # the shortcut ran for cursors
+            if os.environ.get("GDX_VERIFY", "1") != "0":
+                assert st.verified_queries > 500  # the shortcut ran for cursors
         no_isa = (gdx.FmIndexConfig("u32").suffix_array_sampling_rate(s_rate).lookup_table_depth(depth)
                   .keep_inverse_samples(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n()))
         assert no_isa.info().inverse_sample_bytes == 0 and no_isa.info().text_bytes > 0
