@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgenedex_b200.so")
+# GENEDEX_B200_LIB selects another build of the same library (kernel experiments); default: in-tree
+LIB_PATH = os.environ.get("GENEDEX_B200_LIB") or os.path.join(_HERE, "csrc", "libgenedex_b200.so")
 
 GDX_OK, GDX_ERR_INVALID_SYMBOL, GDX_ERR_BAD_ARG, GDX_ERR_CUDA, GDX_ERR_OOM, GDX_ERR_TEXT_TOO_LONG, \
     GDX_ERR_UNSUPPORTED = range(7)

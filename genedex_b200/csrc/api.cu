@@ -1,6 +1,7 @@
 // api.cu -- C ABI of genedex_b200 (include/genedex_b200.h): index handles, device image
 // construction from host parts, chunked H2D / kernel / D2H pipelines, locate CSR plumbing.
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include <algorithm>
 #include <atomic>
@@ -500,7 +501,8 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     h.off_text = off;
     if (src.d_text) {
         h.text_bits = h.sigma <= 16 ? 4 : 8;
-        h.off_text = place(h.text_bits == 4 ? (src.n + 1) / 2 : src.n);
+        // + 16: the comparison reads whole 64-bit words, one past the last (compare_with_text)
+        h.off_text = place((h.text_bits == 4 ? (src.n + 1) / 2 : src.n) + 16);
     }
     h.has_isa = 0;
     h.off_isa = off;

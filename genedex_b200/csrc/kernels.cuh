@@ -196,6 +196,9 @@ struct KG {
 };
 
 __device__ __forceinline__ uint64_t sbc_load(const DevIndex &ix, uint64_t i, uint32_t c) {
+#ifdef GDX_EXP_FAKE_SBC  // experiment only (wrong results): same access pattern without the superblock load
+    return (i >> kSuperblockLog2) << kSuperblockLog2;
+#endif
     return __ldg(ix.sbc + (i >> kSuperblockLog2) * ix.noff + (c - 1));
 }
 
@@ -306,6 +309,58 @@ __device__ __forceinline__ uint64_t isa_row(const DevIndex &ix, uint64_t t, uint
 __device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) {
     if (ix.text_bits == 4) return (__ldg(ix.text + (p >> 1)) >> ((p & 1) * 4)) & 15u;
     return __ldg(ix.text + p);  // L1-allocating on purpose: the comparison walks consecutive bytes
+}
+
+// Right-to-left comparison of query[0..pos) with the text in front of position `at` (query position j
+// <-> text position at - (pos - j)), a 64-bit word of packed symbols at a time.  Same outcome as the
+// reference's one-rank-per-symbol shrinking of a one-row interval (cursor.rs:40-51):
+//   0 = every symbol matched; 1 = first mismatch from the right at query position jm (symbol cm);
+//   2 = an invalid symbol (dense 0, alphabet.rs:195-198) is reached before any mismatch.
+// Positions before the start of the first text read as 0 = sentinel, which no valid symbol matches.
+// The text section is padded so that the word after the last one may be read.
+template <int BITS>
+__device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8_t *tab, const uint8_t *sbytes,
+                                                 uint64_t tail_begin, const uint8_t *p, uint64_t pos, uint64_t at,
+                                                 uint64_t &jm, uint32_t &cm) {
+    constexpr uint32_t SPW = 64 / BITS;  // symbols per word
+    constexpr uint64_t kLow = BITS == 4 ? 0x7777777777777777ull : 0x7f7f7f7f7f7f7f7full;
+    const uint64_t *text64 = reinterpret_cast<const uint64_t *>(ix.text);
+    uint64_t j_hi = pos;
+    while (j_hi > 0) {
+        const uint32_t cnt = j_hi < SPW ? (uint32_t)j_hi : SPW;
+        const uint64_t j0 = j_hi - cnt;
+        const uint64_t back0 = pos - j0;  // distance of query position j0 from `at`
+        uint64_t tw;
+        if (back0 <= at) {
+            const uint64_t t0 = at - back0;
+            const uint32_t sh = (uint32_t)(t0 % SPW) * BITS;
+            const uint64_t w0 = __ldg(text64 + t0 / SPW), w1 = __ldg(text64 + t0 / SPW + 1);
+            tw = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+        } else {  // the chunk starts before position 0 of the first text
+            const uint64_t missing = back0 - at;
+            tw = missing >= SPW ? 0 : __ldg(text64) << (missing * BITS);
+        }
+        uint64_t qw = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < SPW; ++k)
+            if (k < cnt) {
+                const uint64_t i = j0 + k;
+                const uint32_t c = tab[i >= tail_begin ? sbytes[i - tail_begin] : __ldg(p + i)];
+                qw |= (uint64_t)c << (k * BITS);
+            }
+        const uint64_t vm = cnt == SPW ? ~0ull : (1ull << (cnt * BITS)) - 1;
+        const uint64_t diff = (qw ^ tw) & vm;
+        const uint64_t zero = ~(((qw & kLow) + kLow) | qw | kLow) & vm;  // top bit of every symbol that is 0
+        if (diff | zero) {
+            const uint32_t km = diff ? (63u - (uint32_t)__clzll((long long)diff)) / BITS : 0;
+            if (zero && (!diff || (63u - (uint32_t)__clzll((long long)zero)) / BITS >= km)) return 2;
+            jm = j0 + km;
+            cm = (uint32_t)(qw >> (km * BITS)) & ((1u << BITS) - 1);
+            return 1;
+        }
+        j_hi = j0;
+    }
+    return 0;
 }
 
 // interval flag of the locate plumbing: start = resolved text position, end = kDirectHit
@@ -458,11 +513,14 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         uint32_t *slot = stage + threadIdx.x * kQuerySlotWords;
         const uint8_t *first = p + tail_begin;
         const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 3u);
-        if (tail) {
+        if (tail) {  // global -> shared without a register round trip: all words of the query are in flight at once
             const uint32_t *w = reinterpret_cast<const uint32_t *>(first - mis);
             const uint32_t nw = (mis + tail + 3u) >> 2;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot);
 #pragma unroll 1
-            for (uint32_t k = 0; k < nw; ++k) slot[k] = __ldg(w + k);
+            for (uint32_t k = 0; k < nw; ++k)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * k), "l"(w + k) : "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
         }
         const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(slot) + mis;
         // dense symbol of query position i
@@ -495,22 +553,13 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
                 const uint64_t at = resolve_row<L>(ix, s, vsteps);
                 vrows = 1;
-                bool match = true;
                 uint64_t jm = 0;     // query position of the first mismatch (from the right)
                 uint32_t cm = 0;     // its dense symbol
-                for (uint64_t j = pos; match && j-- > 0;) {
-                    const uint32_t c = GDX_SYMBOL_AT(j);
-                    if (c == 0) {  // the reference reaches this symbol with a non-empty interval
-                        bad = true;
-                        break;
-                    }
-                    const uint64_t back = pos - j;  // nothing precedes position 0 of the first text
-                    match = back <= at && text_symbol(ix, at - back) == c;
-                    if (CURSORS && !match) {
-                        jm = j;
-                        cm = c;
-                    }
-                }
+                const int cmp = ix.text_bits == 4
+                                  ? compare_with_text<4>(ix, tab, sbytes, tail_begin, p, pos, at, jm, cm)
+                                  : compare_with_text<8>(ix, tab, sbytes, tail_begin, p, pos, at, jm, cm);
+                const bool match = cmp == 0;
+                bad = cmp == 2;  // the reference reaches this symbol with a non-empty interval
                 if (bad) {
                     s = e = 0;
                 } else if (!CURSORS) {
