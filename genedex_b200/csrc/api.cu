@@ -514,19 +514,10 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     return GDX_OK;
 }
 
-// L2 eviction policy values for the kernels (GDX_L2_HINTS=0 disables them)
+// run-time overrides of kernel parameters (measurements only)
 gdx_status init_policies(gdx_index *idx) {
     if (const char *vm = getenv("GDX_VERIFY_MIN"))
         if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
-    const char *e = getenv("GDX_L2_HINTS");
-    if (e && atoi(e) == 0) return GDX_OK;
-    uint64_t *d = nullptr, h = 0;
-    CUDA_TRY(cudaMalloc(&d, 8));
-    k_make_policies<<<1, 1>>>(d);
-    cudaError_t ce = cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (ce != cudaSuccess) return fail(GDX_ERR_CUDA, "createpolicy failed: %s", cudaGetErrorString(ce));
-    idx->dev.pol_evict_first = h;
     return GDX_OK;
 }
 

@@ -70,7 +70,6 @@ struct DevIndex {
     // L2 eviction policies (createpolicy values made once per index on the device; 0 = no hints):
     // records of one-row intervals, SA samples and text are touched once -> evict_first, so that they do
     // not push the shared top of the search trie out of L2
-    uint64_t pol_evict_first;
     uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (default 8)
     uint32_t pad2;
     uint64_t lut_level_off[kMaxLookupDepth + 1];
@@ -104,7 +103,6 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.stride = h.layout.stride;
     d.derived_symbol = h.layout.derived_symbol;
     d.sampling_shift = 0xffffffffu;
-    d.pol_evict_first = 0;
     d.verify_min_remaining = 8;
     d.pad2 = 0;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {

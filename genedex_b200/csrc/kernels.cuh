@@ -57,28 +57,6 @@ __device__ __forceinline__ void ldg256_na(const void *p, uint64_t w[4]) {
         : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
         : "l"(p));
 }
-// same with an L2 eviction policy (createpolicy value)
-__device__ __forceinline__ void ldg256_na_hint(const void *p, uint64_t w[4], uint64_t policy) {
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
-        : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
-        : "l"(p), "l"(policy));
-}
-__device__ __forceinline__ uint32_t ldg_u8_hint(const uint8_t *p, uint64_t policy) {
-    uint32_t v;
-    asm("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldg_u32_hint(const uint32_t *p, uint64_t policy) {
-    uint32_t v;
-    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
-    return v;
-}
-__global__ void k_make_policies(uint64_t *out) {
-    uint64_t p;
-    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    out[0] = p;
-}
-
 __device__ __forceinline__ void ldg128_na(const void *p, uint64_t &lo, uint64_t &hi) {
     asm("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p));
 }
@@ -104,17 +82,16 @@ struct K32 {
         ldg256_na(ix.records + ((i >> 6) << 5), r.w);
         return r;
     }
-    // a record that will not be needed again (one-row interval, locate walk)
+    // a record that will not be needed again (one-row interval, locate walk).  An L2 evict_first policy on
+    // these loads was measured: no effect on B200 (profiles/README.md), so they are plain loads.
     static __device__ __forceinline__ Rec load_once(const DevIndex &ix, uint64_t i, uint32_t) {
         Rec r;
-        if (ix.pol_evict_first) ldg256_na_hint(ix.records + ((i >> 6) << 5), r.w, ix.pol_evict_first);
-        else ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        ldg256_na(ix.records + ((i >> 6) << 5), r.w);
         return r;
     }
     static __device__ __forceinline__ Planes load_planes_once(const DevIndex &ix, uint64_t i) {
         Planes r;
-        if (ix.pol_evict_first) ldg256_na_hint(ix.records + ((i >> 6) << 5), r.w, ix.pol_evict_first);
-        else ldg256_na(ix.records + ((i >> 6) << 5), r.w);
+        ldg256_na(ix.records + ((i >> 6) << 5), r.w);
         return r;
     }
     static __device__ __forceinline__ Rec with_offset(const DevIndex &, const Planes &p, uint64_t,
@@ -253,7 +230,7 @@ __device__ __forceinline__ uint64_t resolve_row(const DevIndex &ix, uint64_t i, 
             const uint64_t k = ix.sampling_shift != 0xffffffffu ? i >> ix.sampling_shift : i / ix.sampling_rate;
             if (ix.wide) return __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k) + steps;
             const uint32_t *sp = reinterpret_cast<const uint32_t *>(ix.samples) + k;
-            return (uint64_t)(ix.pol_evict_first ? ldg_u32_hint(sp, ix.pol_evict_first) : __ldg(sp)) + steps;
+            return (uint64_t)__ldg(sp) + steps;
         }
         typename L::Planes pl = L::load_planes_once(ix, i);
         const uint32_t c = L::symbol_at(pl, i);
@@ -341,13 +318,23 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8
             tw = missing >= SPW ? 0 : __ldg(text64) << (missing * BITS);
         }
         uint64_t qw = 0;
+        if (j0 >= tail_begin) {  // the whole chunk is staged: two 32-bit halves, no per-symbol branch
+            const uint8_t *sp = sbytes + (j0 - tail_begin);
+            uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (uint32_t k = 0; k < SPW; ++k)
-            if (k < cnt) {
+            for (uint32_t k = 0; k < SPW / 2; ++k) {
+                if (k < cnt) lo |= (uint32_t)tab[sp[k]] << (k * BITS);
+                if (k + SPW / 2 < cnt) hi |= (uint32_t)tab[sp[k + SPW / 2]] << (k * BITS);
+            }
+            qw = (uint64_t)lo | ((uint64_t)hi << 32);
+        } else {  // reaches in front of the staged tail of a long query
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; ++k) {
                 const uint64_t i = j0 + k;
                 const uint32_t c = tab[i >= tail_begin ? sbytes[i - tail_begin] : __ldg(p + i)];
                 qw |= (uint64_t)c << (k * BITS);
             }
+        }
         const uint64_t vm = cnt == SPW ? ~0ull : (1ull << (cnt * BITS)) - 1;
         const uint64_t diff = (qw ^ tw) & vm;
         const uint64_t zero = ~(((qw & kLow) + kLow) | qw | kLow) & vm;  // top bit of every symbol that is 0

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOGGLES = [
-    {"GDX_SORT_MODE": "bucket", "GDX_LOCATE_PIPELINE": "0", "GDX_L2_HINTS": "0", "GDX_L2_PERSIST": "0"},
+    {"GDX_SORT_MODE": "bucket", "GDX_LOCATE_PIPELINE": "0", "GDX_L2_PERSIST": "0"},
     {"GDX_VERIFY": "0", "GDX_SORT_QUERIES": "0", "GDX_CHUNK_FIRST_MB": "1", "GDX_CHUNK_MAX_MB": "2",
      "GDX_CHUNK_TAIL_MB": "1"},
     {"GDX_FORCE_WIDE": "1", "GDX_VERIFY_MIN": "2", "GDX_CHUNK_MAX_MB": "256", "GDX_L2_FETCH_GRANULARITY": "0"},
