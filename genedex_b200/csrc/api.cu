@@ -344,6 +344,9 @@ struct gdx_index {
     bool own_image = false;
     int device = 0;
     DevIndex dev;
+    void *dense_sa = nullptr;      // accelerator outside the image (gdx_index_set_dense_suffix_array)
+    uint64_t dense_sa_bytes = 0;
+    bool no_dense_sa = false;      // GDX_FLAG_NO_DENSE_SUFFIX_ARRAY
     mutable std::mutex mu;
     mutable std::vector<Workspace *> free_ws;
     mutable std::vector<PinnedHits> pinned;
@@ -519,6 +522,56 @@ gdx_status init_policies(gdx_index *idx) {
     if (const char *vm = getenv("GDX_VERIFY_MIN"))
         if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
     return GDX_OK;
+}
+
+// ---- dense suffix array accelerator (include/genedex_b200.h: gdx_index_set_dense_suffix_array) ----------
+gdx_status build_dense_sa(gdx_index *idx) {
+    if (idx->dense_sa || idx->h.n == 0) return GDX_OK;
+    const uint64_t n = idx->h.n, bytes = n * (idx->h.wide ? 8 : 4);
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GDX_ERR_OOM, "dense suffix array: %llu bytes of device memory not available", (unsigned long long)bytes);
+    }
+    gdx_status st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+        k_densify<decltype(L)><<<(unsigned)div_up(n, 256), 256>>>(idx->dev, d, n);
+        return GDX_OK;
+    });
+    cudaError_t e = st == GDX_OK ? cudaDeviceSynchronize() : cudaSuccess;
+    if (st != GDX_OK || e != cudaSuccess) {
+        cudaFree(d);
+        return st != GDX_OK ? st : fail(GDX_ERR_CUDA, "dense suffix array: %s", cudaGetErrorString(e));
+    }
+    idx->dense_sa = d;
+    idx->dense_sa_bytes = bytes;
+    idx->dev.samples = d;  // resolve_row / k_locate_walk now see a suffix array with sampling rate 1
+    idx->dev.sampling_rate = 1;
+    idx->dev.sampling_shift = 0;
+    return GDX_OK;
+}
+
+void drop_dense_sa(gdx_index *idx) {
+    if (!idx->dense_sa) return;
+    const DevIndex fresh = make_dev_index(idx->h, idx->image);
+    idx->dev.samples = fresh.samples;
+    idx->dev.sampling_rate = fresh.sampling_rate;
+    idx->dev.sampling_shift = fresh.sampling_shift;
+    cudaFree(idx->dense_sa);
+    idx->dense_sa = nullptr;
+    idx->dense_sa_bytes = 0;
+}
+
+// best effort after every way of creating a replica; the caller holds a DeviceGuard and has freed its temporaries
+void auto_dense_sa(gdx_index *idx) {
+    if (!idx || idx->no_dense_sa || idx->h.n == 0) return;
+    const char *e = getenv("GDX_DENSE_SA");
+    if (e && atoi(e) == 0) return;
+    if (!(e && atoi(e) != 0)) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+        if (idx->h.n * (idx->h.wide ? 8ull : 4ull) > free_b / 4) return;
+    }
+    if (build_dense_sa(idx) != GDX_OK) t_error.clear();  // optional: not an error of the call
 }
 
 gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
@@ -780,6 +833,10 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         src.d_isa32 = r.d_isa_samples;
         st = build_image(src, device, out);
         r.release();
+        if (st == GDX_OK) {
+            (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
+            auto_dense_sa(*out);
+        }
         return st;
     }
 
@@ -800,6 +857,10 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     if (keep_isa) src.h_isa64 = hp.isa_samples.data();
     st = build_image(src, device, out);
     cudaFree(d_bwt);
+    if (st == GDX_OK) {
+        (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
+        auto_dense_sa(*out);
+    }
     return st;
 }
 
@@ -858,6 +919,7 @@ extern "C" gdx_status gdx_index_create_from_bwt(const uint8_t *bwt, const gdx_pa
     src.d_bwt = d_bwt;
     gdx_status st = build_image(src, device, out);
     cudaFree(d_bwt);
+    if (st == GDX_OK) auto_dense_sa(*out);
     return st;
 }
 
@@ -891,6 +953,7 @@ extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_
     src.d_bwt = d_bwt;
     gdx_status st = build_image(src, device, out);
     cudaFree(d_bwt);
+    if (st == GDX_OK) auto_dense_sa(*out);
     return st;
 }
 
@@ -1005,6 +1068,7 @@ extern "C" void gdx_index_destroy(gdx_index *idx) {
     }
     for (auto &p : idx->pinned)
         if (p.p) cudaFreeHost(p.p);
+    if (idx->dense_sa) cudaFree(idx->dense_sa);
     if (idx->own_image && idx->image) cudaFree(idx->image);
     delete idx;
 }
@@ -1031,6 +1095,7 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->num_text_borders = h.n_border;
     out->text_bytes = h.text_bits ? h.off_isa - h.off_text : 0;
     out->inverse_sample_bytes = h.has_isa ? h.image_bytes - h.off_isa : 0;
+    out->dense_suffix_array_bytes = idx->dense_sa_bytes;
     return GDX_OK;
 }
 
@@ -1154,8 +1219,17 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
             delete idx;
             return st;
         }
+        auto_dense_sa(idx);
     }
     *out = idx;
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    if (on) return build_dense_sa(idx);
+    drop_dense_sa(idx);
     return GDX_OK;
 }
 

@@ -67,11 +67,10 @@ struct DevIndex {
     uint32_t wide, noff, stride, derived_symbol;
     uint32_t sampling_shift;  // log2(sampling_rate) if it is a power of two, else 0xffffffff
     uint32_t text_bits;
-    // L2 eviction policies (createpolicy values made once per index on the device; 0 = no hints):
-    // records of one-row intervals, SA samples and text are touched once -> evict_first, so that they do
-    // not push the shared top of the search trie out of L2
+    // samples / sampling_rate / sampling_shift describe what resolve_row reads: the image's sampled suffix
+    // array, or the dense accelerator (rate 1) once gdx_index_set_dense_suffix_array has built it
     uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (default 8)
-    uint32_t pad2;
+    uint32_t isa_rate;              // sampling rate of the inverse samples (= the configured rate)
     uint64_t lut_level_off[kMaxLookupDepth + 1];
     uint64_t lut_pow[kMaxLookupDepth + 1];
     uint8_t io_to_dense[256];
@@ -104,7 +103,7 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.derived_symbol = h.layout.derived_symbol;
     d.sampling_shift = 0xffffffffu;
     d.verify_min_remaining = 8;
-    d.pad2 = 0;
+    d.isa_rate = h.sampling_rate;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {
         uint32_t s = 0;
         while ((1u << s) < h.sampling_rate) ++s;

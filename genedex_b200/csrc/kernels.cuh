@@ -272,10 +272,10 @@ __device__ __forceinline__ uint64_t lf_one(const DevIndex &ix, uint32_t c, uint6
 // must hold a non-sentinel symbol (callers guarantee q lies inside a matched region).
 template <class L>
 __device__ __forceinline__ uint64_t isa_row(const DevIndex &ix, uint64_t t, uint32_t &steps) {
-    const uint64_t k = (t + ix.sampling_rate - 1) / ix.sampling_rate;
+    const uint64_t k = (t + ix.isa_rate - 1) / ix.isa_rate;
     uint64_t row = ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.isa) + k)
                            : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.isa) + k);
-    for (uint64_t q = k * ix.sampling_rate; q > t; --q) {
+    for (uint64_t q = k * ix.isa_rate; q > t; --q) {
         row = lf_row<L>(ix, row);
         ++steps;
     }
@@ -536,7 +536,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             // mode 0 (cursors) must also produce the interval: possible with the sampled inverse suffix
             // array once at least sampling_rate symbols have matched (the ISA walk stays inside them)
             if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining &&
-                (!CURSORS || len - pos >= ix.sampling_rate)) {
+                (!CURSORS || len - pos >= ix.isa_rate)) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
                 const uint64_t at = resolve_row<L>(ix, s, vsteps);
                 vrows = 1;
@@ -848,6 +848,18 @@ __global__ void k_widen_u32(const uint32_t *__restrict__ in, uint64_t n, uint64_
 __global__ void k_narrow_u64(const uint64_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint32_t)in[i];
+}
+
+// ---- dense suffix array accelerator: SA[row] for every row from the sampled one (one walk per row) -----
+template <class L>
+__global__ void __launch_bounds__(256)
+k_densify(const __grid_constant__ DevIndex ix, void *__restrict__ out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t steps = 0;
+    const uint64_t v = resolve_row<L>(ix, i, steps);
+    if (ix.wide) reinterpret_cast<uint64_t *>(out)[i] = v;
+    else reinterpret_cast<uint32_t *>(out)[i] = (uint32_t)v;
 }
 
 // ---- random-gather ceiling ----------------------------------------------------------------

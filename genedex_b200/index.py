@@ -118,6 +118,14 @@ class FmIndexConfig:
             0 if keep else _lib.GDX_FLAG_NO_INVERSE_SAMPLES)
         return self
 
+    def dense_suffix_array(self, allow: bool = True) -> "FmIndexConfig":
+        """Allow (default) or forbid the dense suffix array accelerator: SA[row] for every row, 4-8 bytes
+        per symbol on top of the image, built when device memory is ample (`FmIndex.set_dense_suffix_array`
+        forces it).  Resolving a row is then one load instead of an LF-walk; results are identical."""
+        self._flags = (self._flags & ~_lib.GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) | (
+            0 if allow else _lib.GDX_FLAG_NO_DENSE_SUFFIX_ARRAY)
+        return self
+
     def device(self, ordinal: int) -> "FmIndexConfig":
         self._device = ordinal
         return self
@@ -173,6 +181,10 @@ class FmIndex:
         out = _lib.gdx_index_info()
         _check(self._lib.gdx_index_get_info(self._h, C.byref(out)))
         return out
+
+    def set_dense_suffix_array(self, on: bool = True) -> None:
+        """Build now (raises if it does not fit) or free the dense suffix array accelerator."""
+        _check(self._lib.gdx_index_set_dense_suffix_array(self._h, 1 if on else 0))
 
     def num_texts(self) -> int:
         return int(self.info().num_texts)

@@ -81,6 +81,8 @@ typedef struct gdx_config {
 /* do not keep the sampled inverse suffix array (n / rate entries, only kept together with the text):
  * cursors_for_many_queries then runs every LF step. Results are identical either way. */
 #define GDX_FLAG_NO_INVERSE_SAMPLES 4u
+/* never build the dense suffix array accelerator (see gdx_index_set_dense_suffix_array) for this index */
+#define GDX_FLAG_NO_DENSE_SUFFIX_ARRAY 8u
 
 /* src/lib.rs:331-335 Hit { text_id, position } */
 typedef struct gdx_hit {
@@ -140,6 +142,7 @@ typedef struct gdx_index_info {
     uint64_t num_samples, num_text_borders;
     uint64_t text_bytes;           /* packed text section, 0 if absent */
     uint64_t inverse_sample_bytes; /* sampled inverse suffix array, 0 if absent */
+    uint64_t dense_suffix_array_bytes; /* device-only accelerator outside the image, 0 if absent */
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */
@@ -196,6 +199,18 @@ gdx_status gdx_concat_texts(const uint8_t *texts, const uint64_t *text_offsets, 
 
 void gdx_index_destroy(gdx_index *idx);
 gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);
+
+/* Dense suffix array accelerator (memory for speed, B200: 180 GB of HBM).  The index keeps the sampled
+ * suffix array the configuration asks for (sampled_suffix_array.rs:10-16) -- that is what is saved,
+ * exported and replicated.  On top of it a replica can hold SA[row] for EVERY row (4 B per symbol, 8 B
+ * beyond 2^32 - 1 symbols), derived on the device from the samples in a fraction of a second:
+ * resolving a row (locate, and the text verification of count/locate) is then one load instead of an
+ * LF-walk of up to rate - 1 steps plus a load.  Results are identical with and without it.
+ * It is built automatically after construction / load / adopt / replicate when it needs at most a
+ * quarter of the free device memory (GDX_DENSE_SA=0 never, =1 always; GDX_FLAG_NO_DENSE_SUFFIX_ARRAY
+ * per index).  on != 0 builds it now (GDX_ERR_OOM if it does not fit), on == 0 frees it.  Must not run
+ * concurrently with queries on the same handle. */
+gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
 
 /* ---- index files: FmIndex::save_to_file / load_from_file (src/lib.rs:296-327) -------------------------
  * The crate serialises its host structs with the `savefile` crate (schema version 0); that byte format

@@ -198,6 +198,8 @@ public:
         return i;
     }
     const gdx_index *handle() const { return h_->p; }
+    // build (true) or free (false) the dense suffix array accelerator; not while queries are running
+    void set_dense_suffix_array(bool on) { check(gdx_index_set_dense_suffix_array(h_->p, on ? 1 : 0)); }
 
 private:
     std::shared_ptr<detail::Handle> h_;  // FmIndex: Clone (lib.rs:92) shares the device image
@@ -269,9 +271,13 @@ public:
     // additions of this engine
     FmIndexConfig &construct_on_device(bool on = true, bool verify = false) {
         cfg_.construction = on ? GDX_CONSTRUCT_DEVICE : GDX_CONSTRUCT_HOST;
-        cfg_.flags = verify ? GDX_FLAG_VERIFY_SUFFIX_ARRAY : 0;
+        cfg_.flags = (cfg_.flags & ~GDX_FLAG_VERIFY_SUFFIX_ARRAY) | (verify ? GDX_FLAG_VERIFY_SUFFIX_ARRAY : 0);
         return *this;
     }
+    FmIndexConfig &keep_text(bool keep = true) { return flag(GDX_FLAG_NO_TEXT, !keep); }
+    FmIndexConfig &keep_inverse_samples(bool keep = true) { return flag(GDX_FLAG_NO_INVERSE_SAMPLES, !keep); }
+    // dense suffix array accelerator (gdx_index_set_dense_suffix_array): default = built when memory is ample
+    FmIndexConfig &dense_suffix_array(bool allow = true) { return flag(GDX_FLAG_NO_DENSE_SUFFIX_ARRAY, !allow); }
     FmIndexConfig &device(int ordinal) {
         cfg_.device = ordinal;
         return *this;
@@ -285,6 +291,10 @@ public:
     }
 
 private:
+    FmIndexConfig &flag(uint32_t bit, bool on) {
+        cfg_.flags = on ? (cfg_.flags | bit) : (cfg_.flags & ~bit);
+        return *this;
+    }
     // config.rs:72-82 defaults: sampling rate 4, lookup depth 0, Balanced
     gdx_config cfg_{I::storage, 4, 0, (uint32_t)PerformancePriority::Balanced, GDX_CONSTRUCT_AUTO, -1, 0};
 };

@@ -670,3 +670,40 @@ def test_cursor_shortcut_uses_inverse_samples(gdx):
         ns_, ne_ = no_isa.cursors_many_packed(data, off)
         assert np.array_equal(os_, ns_) and np.array_equal(oe_, ne_)
         assert no_isa.stats().verified_queries == 0
+
+
+def test_dense_suffix_array_accelerator_changes_no_result(gdx):
+    """gdx_index_set_dense_suffix_array: resolve_row / locate read SA[row] directly instead of walking to a
+    sample; counts, hits (order included) and cursors stay identical; the image keeps the sampled array."""
+    rng = random.Random(77)
+    texts = [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(2000, 9000))) for _ in range(5)]
+    texts.append(b"ACGT" * 500)  # repeats: many hits per query
+    for s_rate, storage in ((4, "u32"), (7, "i64"), (16, "i32")):
+        oidx = O.OracleIndex.build(texts, util.oracle_alphabet("ascii_dna_with_n"), storage, sampling_rate=s_rate,
+                                   lookup_depth=3)
+        cfg = gdx.FmIndexConfig(storage).suffix_array_sampling_rate(s_rate).lookup_table_depth(3)
+        pidx = cfg.construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        queries = []
+        for _ in range(600):
+            t = rng.choice(texts)
+            p = rng.randrange(len(t) - 60)
+            queries.append(t[p:p + rng.randrange(1, 60)])
+        queries += [b"ACGTACGT", b"CGTA" * 6, b"", b"T"]
+        n = pidx.total_text_len()
+        if os.environ.get("GDX_DENSE_SA") != "0":
+            assert pidx.info().dense_suffix_array_bytes in (n * 4, n * 8)  # automatic: memory is ample here
+        samples_before = pidx.download_samples()
+        util.assert_same_results(oidx, pidx, queries)
+        pidx.set_dense_suffix_array(False)
+        assert pidx.info().dense_suffix_array_bytes == 0
+        util.assert_same_results(oidx, pidx, queries)
+        pidx.set_dense_suffix_array(True)
+        pidx.set_dense_suffix_array(True)  # idempotent
+        assert pidx.info().dense_suffix_array_bytes in (n * 4, n * 8)
+        util.assert_same_results(oidx, pidx, queries)
+        assert np.array_equal(pidx.download_samples(), samples_before)
+        assert pidx.info().sampling_rate == s_rate
+        never = cfg.dense_suffix_array(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        assert never.info().dense_suffix_array_bytes == 0
+        util.assert_same_results(oidx, never, queries)
+        cfg.dense_suffix_array(True)

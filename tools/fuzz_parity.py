@@ -57,10 +57,11 @@ def one_case(seed):
     storage = rng.choice(["i32", "u32", "i64"])
     on_device = rng.random() < 0.5
     keep_text = rng.random() < 0.8
-    desc = f"seed={seed} alph={alph} texts={[len(t) for t in texts]} s={s} D={depth} {storage} dev={on_device} text={keep_text}"
+    dense = rng.random() < 0.6
+    desc = f"seed={seed} alph={alph} texts={[len(t) for t in texts]} s={s} D={depth} {storage} dev={on_device} text={keep_text} dense={dense}"
     oidx = O.OracleIndex.build(texts, oa, storage, sampling_rate=s, lookup_depth=depth)
     cfg = (gdx.FmIndexConfig(storage).suffix_array_sampling_rate(s).lookup_table_depth(depth)
-           .construct_on_device(on_device, verify=on_device).keep_text(keep_text))
+           .construct_on_device(on_device, verify=on_device).keep_text(keep_text).dense_suffix_array(dense))
     pidx = cfg.construct_index(texts, util.product_alphabet(gdx, alph))
 
     nonempty = [t for t in texts if t]
