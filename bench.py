@@ -156,14 +156,24 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sel)}
 
 
-def ncu_traffic_bytes(args, verified):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch from the committed ncu --set full
-    capture (profiles/r1_k_search*.txt); only meaningful for the default workload it was taken on."""
+def ncu_traffic_bytes(args, verified, dense):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch, read from the committed summary of
+    the ncu --set full capture of this very workload (profiles/r1_k_search*.txt); None for any other workload."""
     default = (args.text_len == 3_100_000_000 and args.queries == 7_500_000 and args.query_len == 50
                and args.lookup_depth == 0 and args.sampling_rate == 4)
     if not default:
         return None
-    return 12.336579e9 + 0.235466e9 if verified else 37.914386e9 + 0.241442e9
+    name = ("r1_k_search.txt" if dense else "r1_k_search_sampled_sa.txt") if verified else "r1_k_search_v1_lf_only_sorted.txt"
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total = 0.0
+    try:
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(f[1]) * unit[f[2]]
+    except Exception:
+        return None
+    return total or None
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -201,6 +211,7 @@ def workload_name(args):
     return (f"C2: hg38-shaped synthetic {args.text_len / 1e9:.2f} Gbp DNA single text (ascii_dna_with_n, "
             f"{args.n_fraction:.0%} N in runs<=10kbp, u32, s={args.sampling_rate}, D={args.lookup_depth}), "
             f"{args.queries / 1e6:.2f}M len-{args.query_len} queries sampled from the text, count")
+
 
 
 def build_oracle_from_product(pidx, args, nthreads=0):
@@ -438,16 +449,17 @@ def run_ours(args, rank, world, local_rank):
                  + R * int(st.walk_steps) + 64 * int(st.verified_queries))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     value = world * nq / (kernel_ms * 1e-3)
-    traffic = ncu_traffic_bytes(args, st.verified_queries > 0)
+    dense_bytes = int(info.dense_suffix_array_bytes)
+    traffic = ncu_traffic_bytes(args, st.verified_queries > 0, dense_bytes > 0)
     random_access = None
     if traffic:
-        # the path is bound by the device's random-access rate, not by streaming bandwidth: every missing
-        # 32 B sector is a 64 B DRAM fetch (ncu), and tools/gather_bench.py measures 42.7 G random fetches/s
-        # (profiles/r1_gather_ceiling.json).  Sorted queries give the shallow steps row locality, so the
-        # kernel can exceed the fully random figure.
-        random_access = {"dram_fetches_per_launch": traffic / 64, "fetches_per_s": traffic / 64 / (kernel_ms * 1e-3),
-                         "measured_random_fetch_ceiling_per_s": 42.7e9,
-                         "frac_of_ceiling": traffic / 64 / (kernel_ms * 1e-3) / 42.7e9}
+        # What bounds the kernel: DRAM serves a random access as a whole 128 B line on this part (ncu on
+        # tools/gather_bench.py: 126 B of dram__bytes_read per random 32 B load, profiles/r1_gather_dram.txt),
+        # and random line fetches saturate at ~43 G/s = 5.5 TB/s (profiles/r1_gather_ceiling.json).
+        random_access = {"dram_lines_per_launch": traffic / 128, "lines_per_s": traffic / 128 / (kernel_ms * 1e-3),
+                         "measured_random_line_ceiling_per_s": 43.0e9,
+                         "frac_of_ceiling": traffic / 128 / (kernel_ms * 1e-3) / 43.0e9,
+                         "note": "whole step (sort + k_search) in the denominator"}
     out = {
         "metric": "len-50 count queries/s on 3.1 Gbp DNA index",
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -455,7 +467,8 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "queries_per_gpu": nq,
                    "l2": "inputs larger than L2: 1.55 GB rank records accessed at random, 375 MB of queries",
-                   "index_image_bytes": int(info.image_bytes), "rank_record_bytes": R,
+                   "index_image_bytes": int(info.image_bytes), "dense_suffix_array_bytes": dense_bytes,
+                   "rank_record_bytes": R,
                    "lf_steps_per_step": steps_exec, "verified_queries_per_step": int(st.verified_queries),
                    "verify_walk_steps_per_step": int(st.walk_steps), "step_ms_min_median_max": [round(min(step_ms), 3),
                                                                             round(statistics.median(step_ms), 3),

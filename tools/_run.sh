@@ -1,5 +1,4 @@
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_toggles.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -5
-python tools/fuzz_parity.py --seconds 45 --seed 21 2>&1 | tail -2
-export LENS=16,24,50 REPS=3
-echo dense; python tools/dram_by_length.py
-echo nodense; GDX_DENSE_SA=0 python tools/dram_by_length.py
+python -m pytest tests -m gpu -q --timeout=1500 -p no:cacheprovider 2>&1 | tail -4
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; tail -c 600 gpurun_out/bench_r1_final.err
+GDX_DENSE_SA=0 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1_sampled_sa.json 2>/dev/null
+python tools/run_configs.py --out gpurun_out/configs_r1_final.jsonl > gpurun_out/configs_final.log 2>&1; tail -3 gpurun_out/configs_final.log
