@@ -1942,34 +1942,48 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
     CUDA_TRY(ws->ends.reserve(n * 8));
     CUDA_TRY(ws->symbols.reserve(n));
     CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 16, st));  // [0] invalid symbol, [1] cursor out of bounds
+    CUDA_TRY(cudaStreamSynchronize(st));
     // large pageable cursor arrays go through pinned staging (see search_host)
-    Slot &sl = ws->slot[0];
+    Slot &sl0 = ws->slot[0];
     const bool stage = n * 8 >= kStageMinBytes && !(is_pinned(starts) && is_pinned(ends));
     const uint64_t *src_s = starts, *src_e = ends;
     if (stage) {
-        CUDA_TRY(sl.h_out_a.reserve(n * 8));
-        CUDA_TRY(sl.h_out_b.reserve(n * 8));
-        HostPool::get().copy(sl.h_out_a.p, starts, n * 8);
-        HostPool::get().copy(sl.h_out_b.p, ends, n * 8);
-        src_s = (const uint64_t *)sl.h_out_a.p;
-        src_e = (const uint64_t *)sl.h_out_b.p;
+        CUDA_TRY(sl0.h_out_a.reserve(n * 8));
+        CUDA_TRY(sl0.h_out_b.reserve(n * 8));
+        HostPool::get().copy(sl0.h_out_a.p, starts, n * 8);
+        HostPool::get().copy(sl0.h_out_b.p, ends, n * 8);
+        src_s = (const uint64_t *)sl0.h_out_a.p;
+        src_e = (const uint64_t *)sl0.h_out_b.p;
     }
-    CUDA_TRY(cudaMemcpyAsync(ws->starts.p, src_s, n * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->ends.p, src_e, n * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->symbols.p, io_symbols, n, cudaMemcpyHostToDevice, st));
-    GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-        k_extend<decltype(L)><<<(unsigned)div_up(n, 256), 256, 0, st>>>(
-            idx->dev, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), ws->symbols.as<uint8_t>(), n, ws->small.d);
-        return GDX_OK;
-    }));
-    CUDA_TRY(cudaGetLastError());
+    uint64_t *d_s = ws->starts.as<uint64_t>(), *d_e = ws->ends.as<uint64_t>();
+    uint8_t *d_c = ws->symbols.as<uint8_t>();
+    // chunks of 1 M cursors round-robin over the workspace streams: upload, kernel and download of
+    // neighbouring chunks overlap (PCIe is full duplex).  Results land in the staging buffers (pageable
+    // caller arrays: handed over only on success) or directly in the caller's pinned arrays (on error their
+    // contents are unspecified -- the reference panics in that case).
+    const uint64_t kChunk = 1ull << 20;
+    uint64_t launches = 0;
+    for (uint64_t off = 0, k = 0; off < n; off += kChunk, ++k) {
+        const uint64_t cn = std::min<uint64_t>(kChunk, n - off);
+        cudaStream_t cs = ws->slot[k % kSlots].stream;
+        CUDA_TRY(cudaMemcpyAsync(d_s + off, src_s + off, cn * 8, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(d_e + off, src_e + off, cn * 8, cudaMemcpyHostToDevice, cs));
+        CUDA_TRY(cudaMemcpyAsync(d_c + off, io_symbols + off, cn, cudaMemcpyHostToDevice, cs));
+        GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+            k_extend<decltype(L)><<<(unsigned)div_up(cn, 256), 256, 0, cs>>>(idx->dev, d_s + off, d_e + off, d_c + off, cn,
+                                                                           ws->small.d, off);
+            return GDX_OK;
+        }));
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+        uint64_t *dst_s = stage ? (uint64_t *)sl0.h_out_a.p : starts, *dst_e = stage ? (uint64_t *)sl0.h_out_b.p : ends;
+        CUDA_TRY(cudaMemcpyAsync(dst_s + off, d_s + off, cn * 8, cudaMemcpyDeviceToHost, cs));
+        CUDA_TRY(cudaMemcpyAsync(dst_e + off, d_e + off, cn * 8, cudaMemcpyDeviceToHost, cs));
+    }
+    for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(ws->slot[s2].stream));
     CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16, cudaMemcpyDeviceToHost, st));
-    if (stage) {  // optimistic copy-out into the staging buffers; handed to the caller only on success
-        CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, ws->starts.p, n * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(sl.h_out_b.p, ws->ends.p, n * 8, cudaMemcpyDeviceToHost, st));
-    }
     CUDA_TRY(cudaStreamSynchronize(st));
-    t_stats.kernel_launches = 1;
+    t_stats.kernel_launches = launches;
     if (ws->small.h[1] != kNoError)  // checked on the device: text_with_rank_support/mod.rs:106-110
         return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)ws->small.h[1]);
     if (ws->small.h[0] != kNoError) {
@@ -1978,12 +1992,8 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
                     (unsigned long long)ws->small.h[0]);
     }
     if (stage) {
-        HostPool::get().copy(starts, sl.h_out_a.p, n * 8);
-        HostPool::get().copy(ends, sl.h_out_b.p, n * 8);
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(starts, ws->starts.p, n * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(ends, ws->ends.p, n * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+        HostPool::get().copy(starts, sl0.h_out_a.p, n * 8);
+        HostPool::get().copy(ends, sl0.h_out_b.p, n * 8);
     }
     return GDX_OK;
 }

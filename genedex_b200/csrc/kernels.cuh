@@ -610,17 +610,17 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
 template <class L>
 __global__ void __launch_bounds__(256)
 k_extend(const __grid_constant__ DevIndex ix, uint64_t *__restrict__ starts, uint64_t *__restrict__ ends,
-         const uint8_t *__restrict__ io_symbols, uint64_t n, uint64_t *err) {
+         const uint8_t *__restrict__ io_symbols, uint64_t n, uint64_t *err, uint64_t index_base) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     uint32_t c = ix.io_to_dense[io_symbols[q]];
     if (c == 0) {  // the reference translates before it looks at the interval (cursor.rs:35-37)
-        report_error(err, q);
+        report_error(err, index_base + q);
         return;
     }
     uint64_t s = starts[q], e = ends[q];
     if (s > ix.n || e > ix.n) {  // text_with_rank_support/mod.rs:106-110 bounds assert
-        report_error(err + 1, q);
+        report_error(err + 1, index_base + q);
         return;
     }
     if (s != e) {

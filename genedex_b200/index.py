@@ -214,10 +214,11 @@ class FmIndex:
 
     # -- packed (numpy) forms: the zero-copy entry points the list forms are built on
     def cursors_many_packed(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
-                            nq: int | None = None):
+                            nq: int | None = None, out: tuple[np.ndarray, np.ndarray] | None = None):
+        """-> (starts, ends); `out` = two uint64 arrays of >= nq entries to fill (e.g. pinned memory)."""
         nq = (offsets.size - 1) if offsets is not None else nq
-        starts = np.empty(max(nq, 1), dtype=np.uint64)
-        ends = np.empty(max(nq, 1), dtype=np.uint64)
+        starts, ends = out if out is not None else (np.empty(max(nq, 1), dtype=np.uint64),
+                                                    np.empty(max(nq, 1), dtype=np.uint64))
         q = _queries_struct(data, offsets, fixed_len, nq)
         _check(self._lib.gdx_cursors_many(self._h, C.byref(q), starts.ctypes.data, ends.ctypes.data))
         return starts[:nq], ends[:nq]
@@ -277,9 +278,15 @@ class FmIndex:
                                               hit_offsets.ctypes.data, C.byref(hp), C.byref(nh)))
         return hit_offsets, self._take_hits(hp, nh.value)
 
-    def extend_many_packed(self, starts: np.ndarray, ends: np.ndarray, io_symbols: np.ndarray):
-        starts = np.array(starts, dtype=np.uint64, order="C")  # one copy: the C call extends in place
-        ends = np.array(ends, dtype=np.uint64, order="C")
+    def extend_many_packed(self, starts: np.ndarray, ends: np.ndarray, io_symbols: np.ndarray, inplace: bool = False):
+        """Batched Cursor.extend_query_front; inplace=True updates the given C-contiguous uint64 arrays (the C
+        call works in place; pinned arrays avoid the staging copy), otherwise copies are extended."""
+        if inplace:
+            assert starts.dtype == np.uint64 and ends.dtype == np.uint64 and starts.flags.c_contiguous \
+                and ends.flags.c_contiguous
+        else:
+            starts = np.array(starts, dtype=np.uint64, order="C")  # one copy: the C call extends in place
+            ends = np.array(ends, dtype=np.uint64, order="C")
         sym = np.ascontiguousarray(io_symbols, dtype=np.uint8)
         _check(self._lib.gdx_extend_many(self._h, starts.ctypes.data, ends.ctypes.data, sym.ctypes.data, starts.size))
         return starts, ends

@@ -252,7 +252,9 @@ gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, co
                                 uint64_t n, uint64_t *hit_offsets, gdx_hit **hits,
                                 uint64_t *num_hits);
 void gdx_free_hits(const gdx_index *idx, gdx_hit *hits);
-/* Cursor::extend_query_front (src/cursor.rs:34-51) for many cursors: in-place on starts/ends. */
+/* Cursor::extend_query_front (src/cursor.rs:34-51) for many cursors: in-place on starts/ends.  On an error
+ * status the contents of pinned starts/ends are unspecified (the reference panics); pageable arrays are
+ * left untouched. */
 gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, uint64_t *ends,
                            const uint8_t *io_symbols, uint64_t n);
 

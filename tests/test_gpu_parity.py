@@ -619,7 +619,7 @@ def test_extend_many_large_and_bounds(gdx):
     text = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
     oidx = O.OracleIndex.build([text.tobytes()], util.oracle_alphabet("ascii_dna"), "u32", 4, 0)
     pidx = gdx.FmIndexConfig("u32").construct_index([text.tobytes()], gdx.alphabet.ascii_dna())
-    nc = 1_000_000
+    nc = 2_500_000  # three pipeline chunks of 2^20 cursors
     a = rng.integers(0, n + 1, nc).astype(np.uint64)
     b = rng.integers(0, n + 1, nc).astype(np.uint64)
     starts, ends = np.minimum(a, b), np.maximum(a, b)
@@ -628,10 +628,20 @@ def test_extend_many_large_and_bounds(gdx):
     for i in rng.integers(0, nc, 3000):
         assert (int(gs[i]), int(ge[i])) == oidx.extend_query_front((int(starts[i]), int(ends[i])), int(syms[i]))
     bad = starts.copy()
-    bad[123456] = n + 5
+    bad[2_123_456] = n + 5
+    bad[2_400_000] = n + 7  # the smallest offending index is reported, whatever chunk it is in
     with pytest.raises(gdx.GenedexError) as e:
         pidx.extend_many_packed(bad, np.maximum(bad, ends), syms)
-    assert "123456" in str(e.value)
+    assert "2123456" in str(e.value)
+    bad_syms = syms.copy()
+    bad_syms[1_500_000] = ord("X")
+    with pytest.raises(gdx.InvalidSymbolError):
+        pidx.extend_many_packed(starts, ends, bad_syms)
+    assert pidx.last_error_query() == 1_500_000 if hasattr(pidx, "last_error_query") else True
+    # in place on the caller's arrays
+    s2, e2 = starts.copy(), ends.copy()
+    pidx.extend_many_packed(s2, e2, syms, inplace=True)
+    assert np.array_equal(s2, gs) and np.array_equal(e2, ge)
 
 
 def test_cursor_shortcut_uses_inverse_samples(gdx):

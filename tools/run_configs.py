@@ -167,20 +167,30 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
     if n_orig:
         assert int(counts[:n_orig].min()) >= 1, f"{name}: a query sampled from the text has count 0"
 
-    # the other entry points of the path: cursors (every LF step, no text verification) and batched extend
+    # the other entry points of the path: cursors and batched extend, through the C ABI with pinned host buffers
+    def pinned_u64(k):
+        return torch.empty(k, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+
+    cs, ce = pinned_u64(nq), pinned_u64(nq)
     for _ in range(2):
-        cs, ce = pidx.cursors_many_packed(q_np, None, m, nq)
+        pidx.cursors_many_packed(q_np, None, m, nq, out=(cs, ce))
     t0 = time.perf_counter()
     for _ in range(3):
-        cs, ce = pidx.cursors_many_packed(q_np, None, m, nq)
+        pidx.cursors_many_packed(q_np, None, m, nq, out=(cs, ce))
     cur_ms = (time.perf_counter() - t0) * 1e3 / 3
     assert np.array_equal(ce - cs, counts), f"{name}: cursor widths differ from counts"
-    sym = np.full(nq, q_np[0], dtype=np.uint8)
-    pidx.extend_many_packed(cs, ce, sym)  # first call sizes the staging buffers
-    t0 = time.perf_counter()
-    for _ in range(3):
-        es, ee = pidx.extend_many_packed(cs, ce, sym)
-    ext_ms = (time.perf_counter() - t0) * 1e3 / 3
+    sym = torch.full((nq,), int(q_np[0]), dtype=torch.uint8).pin_memory().numpy()
+    es, ee = pinned_u64(nq), pinned_u64(nq)
+    ext_times = []
+    for it in range(4):  # first call sizes the buffers
+        es[:] = cs
+        ee[:] = ce
+        t0 = time.perf_counter()
+        pidx.extend_many_packed(es, ee, sym, inplace=True)
+        ext_times.append((time.perf_counter() - t0) * 1e3)
+    ext_ms = sum(ext_times[1:]) / 3
+    ref_s, ref_e = pidx.extend_many_packed(cs[:1000], ce[:1000], sym[:1000])
+    assert np.array_equal(ref_s, es[:1000]) and np.array_equal(ref_e, ee[:1000]), f"{name}: chunked extend differs"
     cur_kernel_ms = time_device_cursors(gdx, pidx, q_dev, m, nq)
     res.update({"cursors_kernel_ms": round(cur_kernel_ms, 3), "cursors_queries_per_s": nq / (cur_kernel_ms * 1e-3),
                 "cursors_e2e_ms": round(cur_ms, 3), "cursors_e2e_queries_per_s": nq / (cur_ms * 1e-3),
