@@ -11,11 +11,15 @@ pass of count_many over the whole query batch.  For N > 1 every rank holds a ful
 (built on rank 0, one NCCL broadcast of the device image) and its own 7.5 M queries: weak scaling,
 no collective on the query path.
 
-`value`   queries/s with the queries already resident in HBM (one k_search launch per step).
+`value`   queries/s with the queries already resident in HBM (k_query_keys + radix sort + one k_search
+          launch per step).  The index carries the library's default accelerators (packed text, dense
+          suffix array: config.dense_suffix_array_bytes); GDX_DENSE_SA=0 / GDX_VERIFY=0 switch them off.
 `e2e`     the same through the C ABI with pinned HOST buffers: H2D of the queries and D2H of the
           counts are inside the timed region (chunked 3-stream pipeline in libgenedex_b200).
-`roofline` the k_search launch: algorithmic bytes (m + 2*R*steps + 16 per query,
-          R = 32 B rank record) / CUDA-event duration, against the measured HBM copy peak.
+`roofline` the k_search launch: algorithmic bytes (m + 2*R*steps + 16 per query for the LF steps
+          executed, + R per walk step + 64 per text-verified query; R = 32 B rank record) / CUDA-event
+          duration of the whole step, against the measured HBM copy peak; `traffic` = DRAM bytes of the
+          launch from the committed ncu capture (profiles/r1_k_search*.txt).
 `cpu_baseline` the oracle's port of the reference's 64-query batched search on the host cores.
 """
 import argparse

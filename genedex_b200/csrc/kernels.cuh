@@ -17,6 +17,7 @@
 //   k_lut_fill      lookup level d from level d-1            (lookup_table.rs:163-258)
 //   k_planes_to_bwt reference bit planes -> dense BWT        (condensed.rs:343-362)
 //   k_records_to_bwt device records -> dense BWT (export)
+//   k_densify       SA[row] for every row from the sampled suffix array (accelerator)
 //   k_gather        random-gather ceiling microbenchmark     
 //
 // All hot loads are random sector accesses into HBM: there is no reuse to stage through shared
@@ -24,7 +25,10 @@
 // 256-bit LDG.NA (no L1 allocation, keeps L1 for the superblock table and the text comparison),
 // (2) both borders issued back to back, one fetch when they share a block, (3) enough resident warps
 // to keep the DRAM random-access rate saturated, (4) fewer random fetches per query: suffix-sorted
-// query order (L2 serves the first ~10 steps) and text verification (~16 LF steps instead of 50).
+// query order (L2 serves the first ~10 steps), text verification (~16 LF steps instead of 50, word-wise
+// comparison) and the dense suffix array (SA[row] in one load), (5) few instructions per step: at 12 warps
+// per scheduler an LF iteration takes about as long to issue as a DRAM round trip.  DRAM serves every
+// random access as a whole 128 B line (profiles/r1_gather_dram.txt); a record is one 32 B sector of it.
 #ifndef GDX_KERNELS_CUH
 #define GDX_KERNELS_CUH
 

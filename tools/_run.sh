@@ -1,4 +1,2 @@
-python -m pytest tests -m gpu -q --timeout=1500 -p no:cacheprovider 2>&1 | tail -4
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err; tail -c 600 gpurun_out/bench_r1_final.err
-GDX_DENSE_SA=0 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1_sampled_sa.json 2>/dev/null
-python tools/run_configs.py --out gpurun_out/configs_r1_final.jsonl > gpurun_out/configs_final.log 2>&1; tail -3 gpurun_out/configs_final.log
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "extend or cursor" 2>&1 | tail -4
+python tools/run_configs.py c3 c4d0 --out gpurun_out/configs_r1_x.jsonl > gpurun_out/configs_x.log 2>&1; tail -2 gpurun_out/configs_x.log | cut -c1-1200
