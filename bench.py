@@ -160,14 +160,18 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sel)}
 
 
-def ncu_traffic_bytes(args, verified, dense):
+def ncu_traffic_bytes(args, verified, dense, seeded):
     """dram__bytes_read.sum + dram__bytes_write.sum of one k_search launch, read from the committed summary of
     the ncu --set full capture of this very workload (profiles/r1_k_search*.txt); None for any other workload."""
     default = (args.text_len == 3_100_000_000 and args.queries == 7_500_000 and args.query_len == 50
                and args.lookup_depth == 0 and args.sampling_rate == 4)
     if not default:
         return None
-    name = ("r1_k_search.txt" if dense else "r1_k_search_sampled_sa.txt") if verified else "r1_k_search_v1_lf_only_sorted.txt"
+    name = {(True, True, True): "r1_k_search.txt", (True, True, False): "r1_k_search_dense_sa.txt",
+            (True, False, False): "r1_k_search_sampled_sa.txt",
+            (False, False, False): "r1_k_search_v1_lf_only_sorted.txt"}.get((bool(verified), bool(dense), bool(seeded)))
+    if name is None:
+        return None
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total = 0.0
     try:
@@ -449,12 +453,17 @@ def run_ours(args, rank, world, local_rank):
     R = int(info.rank_record_bytes)
     # SURVEY 8d per query: m + [8 if D>0] + 2*R*steps + 16; a query finished by text verification adds its
     # walk (R per LF step), one SA-sample sector and one sector of packed text instead of further LF steps
-    alg_bytes = (nq * (m + 16 + (8 if args.lookup_depth > 0 else 0)) + 2 * R * steps_exec
+    seed_depth = int(info.seed_table_depth)
+    table_depth = max(args.lookup_depth, seed_depth if m >= seed_depth else 0)
+    # the library skips the per-batch suffix sort when a lookup level already replaces the steps the sort
+    # would let neighbouring threads share (api.cu plan_sort): ns^depth >= queries
+    sorted_batch = not (table_depth > 0 and int(info.num_searchable_dense_symbols) ** table_depth >= nq)
+    alg_bytes = (nq * (m + 16 + (8 if table_depth > 0 else 0)) + 2 * R * steps_exec
                  + R * int(st.walk_steps) + 64 * int(st.verified_queries))
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
     value = world * nq / (kernel_ms * 1e-3)
     dense_bytes = int(info.dense_suffix_array_bytes)
-    traffic = ncu_traffic_bytes(args, st.verified_queries > 0, dense_bytes > 0)
+    traffic = ncu_traffic_bytes(args, st.verified_queries > 0, dense_bytes > 0, int(info.seed_table_depth) > 0)
     random_access = None
     if traffic:
         # What bounds the kernel: DRAM serves a random access as a whole 128 B line on this part (ncu on
@@ -472,18 +481,22 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": workload_name(args), "queries_per_gpu": nq,
                    "l2": "inputs larger than L2: 1.55 GB rank records accessed at random, 375 MB of queries",
                    "index_image_bytes": int(info.image_bytes), "dense_suffix_array_bytes": dense_bytes,
+                   "seed_table_depth": seed_depth, "seed_table_bytes": int(info.seed_table_bytes),
                    "rank_record_bytes": R,
                    "lf_steps_per_step": steps_exec, "verified_queries_per_step": int(st.verified_queries),
                    "verify_walk_steps_per_step": int(st.walk_steps), "step_ms_min_median_max": [round(min(step_ms), 3),
                                                                             round(statistics.median(step_ms), 3),
                                                                             round(max(step_ms), 3)],
-                   "launches_per_step": "k_query_keys + cub radix sort (suffix order) + k_search", "setup_s": {"data": round(t_data, 2), "index_build": round(t_build, 2),
+                   "launches_per_step": ("k_query_keys + cub radix sort (suffix order) + k_search" if sorted_batch
+                                         else "k_search (a lookup level of depth %d replaces the shared steps: no sort)" % table_depth), "setup_s": {"data": round(t_data, 2), "index_build": round(t_build, 2),
                                                                  "replicate": round(t_bcast, 2)}},
         "clocks": clock_info,
         "e2e": {"value": world * nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": nq * m,
                 "d2h_bytes_per_step": nq * 8, "ms_per_step": e2e_ms, "kernel_ms_inside": st.kernel_ms_search, "ms_per_step_by_rank_and_numa_node": e2e_ms_ranks,
                 "gpu_launches_per_step": int(st.kernel_launches)},
-        "gpu_launches": 2 * args.steps,  # k_query_keys + k_search per step (+ 6 cub radix-sort kernels)
+        # this repo's kernels per step: k_search (+ k_query_keys when the batch is sorted; cub's 5 radix-sort
+        # launches are library code and not counted)
+        "gpu_launches": (2 if sorted_batch else 1) * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_kind": peak_kind, "random_access": random_access, "kernel": "k_search<K32, VERIFY>" if st.verified_queries else "k_search<K32>",
                      "algorithmic_bytes_per_launch": alg_bytes,

@@ -20,6 +20,7 @@ GDX_FLAG_VERIFY_SUFFIX_ARRAY = 1
 GDX_FLAG_NO_TEXT = 2
 GDX_FLAG_NO_INVERSE_SAMPLES = 4
 GDX_FLAG_NO_DENSE_SUFFIX_ARRAY = 8
+GDX_FLAG_NO_SEED_TABLE = 16
 
 
 class gdx_alphabet(C.Structure):
@@ -59,7 +60,8 @@ class gdx_index_info(C.Structure):
                 ("device", C.c_int32), ("image_bytes", C.c_uint64), ("rank_bytes", C.c_uint64),
                 ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64), ("num_samples", C.c_uint64),
                 ("num_text_borders", C.c_uint64), ("text_bytes", C.c_uint64),
-                ("inverse_sample_bytes", C.c_uint64), ("dense_suffix_array_bytes", C.c_uint64)]
+                ("inverse_sample_bytes", C.c_uint64), ("dense_suffix_array_bytes", C.c_uint64), ("seed_table_bytes", C.c_uint64),
+                ("seed_table_depth", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class gdx_stats(C.Structure):
@@ -89,6 +91,7 @@ PROTOTYPES = {
     "gdx_index_destroy": (None, [_vp]),
     "gdx_index_get_info": (C.c_int, [_vp, _P(gdx_index_info)]),
     "gdx_index_set_dense_suffix_array": (C.c_int, [_vp, C.c_int32]),
+    "gdx_index_set_seed_table_depth": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_save_to_file": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "gdx_index_load_from_file": (C.c_int, [C.c_char_p, _i32, _P(_vp), _vp, _u64, _P(_u64)]),
     "gdx_index_header_bytes": (_u64, []),

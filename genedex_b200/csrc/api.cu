@@ -347,6 +347,9 @@ struct gdx_index {
     void *dense_sa = nullptr;      // accelerator outside the image (gdx_index_set_dense_suffix_array)
     uint64_t dense_sa_bytes = 0;
     bool no_dense_sa = false;      // GDX_FLAG_NO_DENSE_SUFFIX_ARRAY
+    void *seed_lut = nullptr;      // accelerator outside the image (gdx_index_set_seed_table_depth)
+    uint64_t seed_lut_bytes = 0;
+    bool no_seed_table = false;    // GDX_FLAG_NO_SEED_TABLE
     mutable std::mutex mu;
     mutable std::vector<Workspace *> free_ws;
     mutable std::vector<PinnedHits> pinned;
@@ -559,6 +562,91 @@ void drop_dense_sa(gdx_index *idx) {
     cudaFree(idx->dense_sa);
     idx->dense_sa = nullptr;
     idx->dense_sa_bytes = 0;
+}
+
+// ---- seed table accelerator (include/genedex_b200.h: gdx_index_set_seed_table_depth) -------------------
+void drop_seed_table(gdx_index *idx) {
+    if (!idx->seed_lut) return;
+    idx->dev.seed_lookup = nullptr;
+    idx->dev.seed_depth = 0;
+    cudaFree(idx->seed_lut);
+    idx->seed_lut = nullptr;
+    idx->seed_lut_bytes = 0;
+}
+
+// entries of level d, 0 if ns^d overflows 2^40
+uint64_t seed_entries(uint32_t ns, uint32_t d) {
+    uint64_t e = 1;
+    for (uint32_t i = 0; i < d; ++i) {
+        e *= ns;
+        if (e > (1ull << 40)) return 0;
+    }
+    return e;
+}
+
+gdx_status build_seed_table(gdx_index *idx, uint32_t depth) {
+    drop_seed_table(idx);
+    const ImageHeader &h = idx->h;
+    if (depth == 0 || h.n == 0 || h.ns == 0) return GDX_OK;
+    const uint64_t esz = h.wide ? 16 : 8, last = seed_entries(h.ns, depth), prev = seed_entries(h.ns, depth - 1);
+    if (last == 0 || depth > 40) return fail(GDX_ERR_UNSUPPORTED, "seed table of depth %u is too large", depth);
+    // levels alternate between the final buffer and a temporary one of the size of level depth - 1
+    void *fin = nullptr, *tmp = nullptr;
+    if (cudaMalloc(&fin, last * esz) != cudaSuccess || cudaMalloc(&tmp, prev * esz) != cudaSuccess) {
+        cudaGetLastError();
+        if (fin) cudaFree(fin);
+        return fail(GDX_ERR_OOM, "seed table of depth %u: %llu bytes of device memory not available", depth,
+                    (unsigned long long)((last + prev) * esz));
+    }
+    void *cur = (depth % 2 == 0) ? fin : tmp;  // level 0 lives where level `depth` will not collide: parity of depth
+    cudaError_t e;
+    if (h.wide) {
+        const uint64_t e0[2] = {0, h.n};
+        e = cudaMemcpy(cur, e0, sizeof e0, cudaMemcpyHostToDevice);
+    } else {
+        const uint32_t e0[2] = {0, (uint32_t)h.n};
+        e = cudaMemcpy(cur, e0, sizeof e0, cudaMemcpyHostToDevice);
+    }
+    gdx_status st = GDX_OK;
+    for (uint32_t d = 1; d <= depth && e == cudaSuccess && st == GDX_OK; ++d) {
+        void *nxt = cur == fin ? tmp : fin;
+        const uint64_t entries = seed_entries(h.ns, d);
+        st = dispatch_layout(h.layout, [&](auto L) -> gdx_status {
+            k_lut_extend<decltype(L)><<<(unsigned)div_up(entries, 256), 256>>>(idx->dev, cur, nxt, entries);
+            return GDX_OK;
+        });
+        e = cudaGetLastError();
+        cur = nxt;
+    }
+    if (e == cudaSuccess && st == GDX_OK) e = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    if (st != GDX_OK || e != cudaSuccess || cur != fin) {
+        cudaFree(fin);
+        return st != GDX_OK ? st : fail(GDX_ERR_CUDA, "seed table: %s", cudaGetErrorString(e));
+    }
+    idx->seed_lut = fin;
+    idx->seed_lut_bytes = last * esz;
+    idx->dev.seed_lookup = fin;
+    idx->dev.seed_depth = depth;
+    return GDX_OK;
+}
+
+void auto_seed_table(gdx_index *idx) {
+    if (!idx || idx->no_seed_table || idx->h.n == 0 || idx->h.ns < 2) return;
+    const char *e = getenv("GDX_SEED_TABLE");
+    uint32_t depth = 0;
+    if (e) {
+        if (atoi(e) <= 0) return;
+        depth = (uint32_t)atoi(e);
+    } else {
+        while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= idx->h.n) ++depth;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
+        const uint64_t esz = idx->h.wide ? 16 : 8;
+        while (depth > 0 && (seed_entries(idx->h.ns, depth) + seed_entries(idx->h.ns, depth - 1)) * esz > free_b / 4) --depth;
+    }
+    if (depth <= idx->h.lookup_depth) return;  // the configured table is at least as deep
+    if (build_seed_table(idx, depth) != GDX_OK) t_error.clear();  // optional: not an error of the call
 }
 
 // best effort after every way of creating a replica; the caller holds a DeviceGuard and has freed its temporaries
@@ -835,7 +923,9 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         r.release();
         if (st == GDX_OK) {
             (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
+            (*out)->no_seed_table = (config->flags & GDX_FLAG_NO_SEED_TABLE) != 0;
             auto_dense_sa(*out);
+            auto_seed_table(*out);
         }
         return st;
     }
@@ -859,7 +949,9 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     cudaFree(d_bwt);
     if (st == GDX_OK) {
         (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
+        (*out)->no_seed_table = (config->flags & GDX_FLAG_NO_SEED_TABLE) != 0;
         auto_dense_sa(*out);
+        auto_seed_table(*out);
     }
     return st;
 }
@@ -919,7 +1011,10 @@ extern "C" gdx_status gdx_index_create_from_bwt(const uint8_t *bwt, const gdx_pa
     src.d_bwt = d_bwt;
     gdx_status st = build_image(src, device, out);
     cudaFree(d_bwt);
-    if (st == GDX_OK) auto_dense_sa(*out);
+    if (st == GDX_OK) {
+        auto_dense_sa(*out);
+        auto_seed_table(*out);
+    }
     return st;
 }
 
@@ -953,7 +1048,10 @@ extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_
     src.d_bwt = d_bwt;
     gdx_status st = build_image(src, device, out);
     cudaFree(d_bwt);
-    if (st == GDX_OK) auto_dense_sa(*out);
+    if (st == GDX_OK) {
+        auto_dense_sa(*out);
+        auto_seed_table(*out);
+    }
     return st;
 }
 
@@ -1069,6 +1167,7 @@ extern "C" void gdx_index_destroy(gdx_index *idx) {
     for (auto &p : idx->pinned)
         if (p.p) cudaFreeHost(p.p);
     if (idx->dense_sa) cudaFree(idx->dense_sa);
+    if (idx->seed_lut) cudaFree(idx->seed_lut);
     if (idx->own_image && idx->image) cudaFree(idx->image);
     delete idx;
 }
@@ -1096,6 +1195,9 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->text_bytes = h.text_bits ? h.off_isa - h.off_text : 0;
     out->inverse_sample_bytes = h.has_isa ? h.image_bytes - h.off_isa : 0;
     out->dense_suffix_array_bytes = idx->dense_sa_bytes;
+    out->seed_table_bytes = idx->seed_lut_bytes;
+    out->seed_table_depth = idx->dev.seed_depth;
+    out->reserved = 0;
     return GDX_OK;
 }
 
@@ -1220,9 +1322,20 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
             return st;
         }
         auto_dense_sa(idx);
+        auto_seed_table(idx);
     }
     *out = idx;
     return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    DeviceGuard guard(idx->device);
+    if (depth <= 0) {
+        drop_seed_table(idx);
+        return GDX_OK;
+    }
+    return build_seed_table(idx, (uint32_t)depth);
 }
 
 extern "C" gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on) {
@@ -1313,9 +1426,21 @@ bool bucket_mode() {
     return on;
 }
 
-SortPlan plan_sort(const gdx_index *idx, uint64_t nq) {
+// fixed_len: length of every query of the batch, 0 = variable
+SortPlan plan_sort(const gdx_index *idx, uint64_t nq, uint64_t fixed_len) {
     SortPlan p;
     if (!sort_enabled() || nq < kSortMinQueries || nq >= 0xffffffffull) return p;
+    // The sort makes neighbouring threads share the first ~log_ns(nq) search steps.  When a lookup level
+    // (configured, or the seed table accelerator) already replaces that many steps there is nothing left to
+    // share: reading the queries in their own order is then cheaper (coalesced, no sort): 1.39 vs 2.01 ms per
+    // 7.5 M queries at depth 13.
+    {
+        uint32_t d = idx->h.lookup_depth;
+        if (idx->dev.seed_lookup && idx->dev.seed_depth > d && (fixed_len == 0 || fixed_len >= idx->dev.seed_depth))
+            d = idx->dev.seed_depth;
+        const uint64_t entries = seed_entries(idx->h.ns, d);
+        if (d > 0 && (entries == 0 || entries >= nq)) return p;
+    }
     uint32_t bits = 1;
     while ((1u << bits) < idx->h.ns) ++bits;
     p.key_bits = bits;
@@ -1565,7 +1690,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         const uint64_t byte0 = query_bytes_end(qs, q0), byte1 = query_bytes_end(qs, q1);
         Slot &sl = ws->slot[k % kSlots];
         // growing a slot buffer frees the old one: only safe once the slot's stream has drained
-        const SortPlan sp = plan_sort(idx, cq);
+        const SortPlan sp = plan_sort(idx, cq, qs->offsets ? 0 : qs->fixed_len);
         if (sl.bytes.cap < byte1 - byte0 + 16 || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
             (!dev_a && (sl.out_a.cap < cq * 8 || ((mode == 0 || lp) && sl.out_b.cap < cq * 8))) ||
             (sp.use && sl.sort.cap < sp.total_bytes))
@@ -2035,7 +2160,7 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
     dq.nq = dq_in->nq;
     dq.base = 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const SortPlan sp = plan_sort(idx, dq.nq);
+    const SortPlan sp = plan_sort(idx, dq.nq, dq.offsets ? 0 : dq.fixed_len);
     const uint32_t *perm = nullptr;
     void *scratch = nullptr;
     if (sp.use) {  // stream-ordered scratch from the device's memory pool

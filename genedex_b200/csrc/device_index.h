@@ -62,6 +62,7 @@ struct DevIndex {
     const uint64_t *count;
     const uint8_t *text;
     const void *isa;  // sampled inverse suffix array (same element width as samples) or nullptr
+    const void *seed_lookup;  // level seed_depth of a lookup table deeper than the configured one, or nullptr
     uint64_t n, ntexts, n_border;
     uint32_t sigma, ns, sampling_rate, lookup_depth;
     uint32_t wide, noff, stride, derived_symbol;
@@ -71,6 +72,7 @@ struct DevIndex {
     // array, or the dense accelerator (rate 1) once gdx_index_set_dense_suffix_array has built it
     uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (default 8)
     uint32_t isa_rate;              // sampling rate of the inverse samples (= the configured rate)
+    uint32_t seed_depth, pad3;
     uint64_t lut_level_off[kMaxLookupDepth + 1];
     uint64_t lut_pow[kMaxLookupDepth + 1];
     uint8_t io_to_dense[256];
@@ -104,6 +106,9 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.sampling_shift = 0xffffffffu;
     d.verify_min_remaining = 8;
     d.isa_rate = h.sampling_rate;
+    d.seed_lookup = nullptr;
+    d.seed_depth = 0;
+    d.pad3 = 0;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {
         uint32_t s = 0;
         while ((1u << s) < h.sampling_rate) ++s;

@@ -18,6 +18,7 @@
 //   k_planes_to_bwt reference bit planes -> dense BWT        (condensed.rs:343-362)
 //   k_records_to_bwt device records -> dense BWT (export)
 //   k_densify       SA[row] for every row from the sampled suffix array (accelerator)
+//   k_lut_extend    one level of the seed table (accelerator: a deeper lookup level outside the image)
 //   k_gather        random-gather ceiling microbenchmark     
 //
 // All hot loads are random sector accesses into HBM: there is no reuse to stage through shared
@@ -519,18 +520,51 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         bool bad = false;
 
         // K1: lookup_table.rs:68-161 -- first suffix symbol is the least significant digit
-        const uint64_t depth = len < ix.lookup_depth ? len : ix.lookup_depth;
+        uint64_t depth = len < ix.lookup_depth ? len : ix.lookup_depth;
         uint64_t pos = len - depth;
         uint64_t li = 0;
-        for (uint64_t j = 0; j < depth; ++j) {
-            const uint32_t c = GDX_SYMBOL_AT(pos + j);
-            // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
-            // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
-            if (c == 0 || c > ix.ns) bad = true;
-            li += (uint64_t)(c - 1) * ix.lut_pow[j];
-        }
         uint64_t s = 0, e = 0;
-        if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
+        // Seed table accelerator (gdx_index_set_seed_table_depth): one level of a lookup table deeper than
+        // the configured one.  Its entries are exactly what the configured table + LF steps produce (an empty
+        // interval stays as it was when it became empty, k_lut_extend), so it may stand in whenever all of its
+        // symbols are searchable; anything else (invalid byte, `N`, short query) takes the configured path,
+        // which keeps the reference's lazy panic and the documented deviation where they were.
+        bool seeded = false;
+        if (ix.seed_lookup && len >= ix.seed_depth) {
+            const uint64_t p0 = len - ix.seed_depth;
+            uint64_t pw = 1;
+            bool ok = true;
+            for (uint32_t j = 0; j < ix.seed_depth; ++j) {
+                const uint32_t c = GDX_SYMBOL_AT(p0 + j);
+                if (c == 0 || c > ix.ns) ok = false;
+                li += (uint64_t)(c - 1) * pw;
+                pw *= ix.ns;
+            }
+            if (ok) {
+                if (ix.wide) {
+                    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ix.seed_lookup) + li);
+                    s = v.x;
+                    e = v.y;
+                } else {
+                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ix.seed_lookup) + li);
+                    s = v.x;
+                    e = v.y;
+                }
+                pos = p0;
+                seeded = true;
+            }
+            li = 0;
+        }
+        if (!seeded) {
+            for (uint64_t j = 0; j < depth; ++j) {
+                const uint32_t c = GDX_SYMBOL_AT(pos + j);
+                // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
+                // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
+                if (c == 0 || c > ix.ns) bad = true;
+                li += (uint64_t)(c - 1) * ix.lut_pow[j];
+            }
+            if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
+        }
 
         // K2: batch_computed_cursors.rs:62-70.  The verification runs inline, as soon as a lane's interval
         // has one row: its dependent DRAM fetches then overlap the LF steps of the other lanes of the warp
@@ -810,6 +844,30 @@ k_lut_fill(const __grid_constant__ DevIndex ix, void *__restrict__ lookup, uint3
         reinterpret_cast<ulonglong2 *>(lookup)[entry] = make_ulonglong2(s, e);
     else
         reinterpret_cast<uint2 *>(lookup)[entry] = make_uint2((uint32_t)s, (uint32_t)e);
+}
+
+// one level of the seed table from the previous one, each in its own buffer (same rule as k_lut_fill)
+template <class L>
+__global__ void __launch_bounds__(256)
+k_lut_extend(const __grid_constant__ DevIndex ix, const void *__restrict__ prev, void *__restrict__ out, uint64_t entries) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= entries) return;
+    uint64_t s, e;
+    if (ix.wide) {
+        const ulonglong2 v = reinterpret_cast<const ulonglong2 *>(prev)[i / ix.ns];
+        s = v.x;
+        e = v.y;
+    } else {
+        const uint2 v = reinterpret_cast<const uint2 *>(prev)[i / ix.ns];
+        s = v.x;
+        e = v.y;
+    }
+    const uint32_t c = (uint32_t)(i % ix.ns) + 1;
+    if (s != e) lf_pair<L>(ix, c, s, e);  // cursor.rs:40-51
+    if (ix.wide)
+        reinterpret_cast<ulonglong2 *>(out)[i] = make_ulonglong2(s, e);
+    else
+        reinterpret_cast<uint2 *>(out)[i] = make_uint2((uint32_t)s, (uint32_t)e);
 }
 
 // condensed.rs:343-362 symbol_at over the reference's own plane array: [block][plane] u64

@@ -126,6 +126,13 @@ class FmIndexConfig:
             0 if allow else _lib.GDX_FLAG_NO_DENSE_SUFFIX_ARRAY)
         return self
 
+    def seed_table(self, allow: bool = True) -> "FmIndexConfig":
+        """Allow (default) or forbid the seed table accelerator: one level of a lookup table deeper than the
+        configured one (largest depth with ns^depth <= text length), built when device memory is ample
+        (`FmIndex.set_seed_table_depth` forces a depth).  Results and error behaviour are identical."""
+        self._flags = (self._flags & ~_lib.GDX_FLAG_NO_SEED_TABLE) | (0 if allow else _lib.GDX_FLAG_NO_SEED_TABLE)
+        return self
+
     def device(self, ordinal: int) -> "FmIndexConfig":
         self._device = ordinal
         return self
@@ -185,6 +192,10 @@ class FmIndex:
     def set_dense_suffix_array(self, on: bool = True) -> None:
         """Build now (raises if it does not fit) or free the dense suffix array accelerator."""
         _check(self._lib.gdx_index_set_dense_suffix_array(self._h, 1 if on else 0))
+
+    def set_seed_table_depth(self, depth: int) -> None:
+        """(Re)build the seed table accelerator at this depth now (raises if it does not fit); 0 frees it."""
+        _check(self._lib.gdx_index_set_seed_table_depth(self._h, int(depth)))
 
     def num_texts(self) -> int:
         return int(self.info().num_texts)

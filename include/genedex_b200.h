@@ -83,6 +83,8 @@ typedef struct gdx_config {
 #define GDX_FLAG_NO_INVERSE_SAMPLES 4u
 /* never build the dense suffix array accelerator (see gdx_index_set_dense_suffix_array) for this index */
 #define GDX_FLAG_NO_DENSE_SUFFIX_ARRAY 8u
+/* never build the seed table accelerator (see gdx_index_set_seed_table_depth) for this index */
+#define GDX_FLAG_NO_SEED_TABLE 16u
 
 /* src/lib.rs:331-335 Hit { text_id, position } */
 typedef struct gdx_hit {
@@ -143,6 +145,9 @@ typedef struct gdx_index_info {
     uint64_t text_bytes;           /* packed text section, 0 if absent */
     uint64_t inverse_sample_bytes; /* sampled inverse suffix array, 0 if absent */
     uint64_t dense_suffix_array_bytes; /* device-only accelerator outside the image, 0 if absent */
+    uint64_t seed_table_bytes;         /* device-only accelerator outside the image, 0 if absent */
+    uint32_t seed_table_depth;         /* 0 if absent */
+    uint32_t reserved;
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */
@@ -211,6 +216,21 @@ gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);
  * per index).  on != 0 builds it now (GDX_ERR_OOM if it does not fit), on == 0 frees it.  Must not run
  * concurrently with queries on the same handle. */
 gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
+
+/* Seed table accelerator (memory for speed).  The index keeps the lookup tables of the configured depth
+ * (lookup_table.rs:19-23) -- that is what is saved, exported and replicated, and what decides every
+ * error behaviour.  On top of it a replica can hold ONE level of a deeper lookup table (depth d: ns^d
+ * entries of 8 B, 16 B beyond 2^32 - 1 symbols), filled on the device level by level with the same
+ * rule as the reference (lookup_table.rs:225-258).  A query whose last d symbols are all searchable starts
+ * from that entry instead of the configured table + LF steps; the entry is bit for bit the interval those
+ * steps produce (also when it is empty), every other query takes the configured path.  Results, error
+ * behaviour and reported lookup_table_depth are unchanged.
+ * Built automatically after construction / load / adopt / replicate with the largest d such that
+ * ns^d <= text length, if that needs at most a quarter of the free device memory (GDX_SEED_TABLE=0 never,
+ * =d that depth; GDX_FLAG_NO_SEED_TABLE per index).  depth > 0 (re)builds it at that depth now
+ * (GDX_ERR_OOM / GDX_ERR_UNSUPPORTED if it does not fit), depth <= 0 frees it.  Must not run concurrently
+ * with queries on the same handle. */
+gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth);
 
 /* ---- index files: FmIndex::save_to_file / load_from_file (src/lib.rs:296-327) -------------------------
  * The crate serialises its host structs with the `savefile` crate (schema version 0); that byte format

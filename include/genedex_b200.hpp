@@ -200,6 +200,8 @@ public:
     const gdx_index *handle() const { return h_->p; }
     // build (true) or free (false) the dense suffix array accelerator; not while queries are running
     void set_dense_suffix_array(bool on) { check(gdx_index_set_dense_suffix_array(h_->p, on ? 1 : 0)); }
+    // (re)build the seed table accelerator at this depth, 0 frees it; not while queries are running
+    void set_seed_table_depth(int depth) { check(gdx_index_set_seed_table_depth(h_->p, depth)); }
 
 private:
     std::shared_ptr<detail::Handle> h_;  // FmIndex: Clone (lib.rs:92) shares the device image
@@ -278,6 +280,8 @@ public:
     FmIndexConfig &keep_inverse_samples(bool keep = true) { return flag(GDX_FLAG_NO_INVERSE_SAMPLES, !keep); }
     // dense suffix array accelerator (gdx_index_set_dense_suffix_array): default = built when memory is ample
     FmIndexConfig &dense_suffix_array(bool allow = true) { return flag(GDX_FLAG_NO_DENSE_SUFFIX_ARRAY, !allow); }
+    // seed table accelerator (gdx_index_set_seed_table_depth): default = built when memory is ample
+    FmIndexConfig &seed_table(bool allow = true) { return flag(GDX_FLAG_NO_SEED_TABLE, !allow); }
     FmIndexConfig &device(int ordinal) {
         cfg_.device = ordinal;
         return *this;

@@ -717,3 +717,59 @@ def test_dense_suffix_array_accelerator_changes_no_result(gdx):
         assert never.info().dense_suffix_array_bytes == 0
         util.assert_same_results(oidx, never, queries)
         cfg.dense_suffix_array(True)
+
+
+def test_seed_table_accelerator_changes_no_result(gdx):
+    """gdx_index_set_seed_table_depth: a deeper lookup level outside the image stands in for the configured
+    table + LF steps; cursors (also empty ones), counts, hits and the lazy invalid-symbol behaviour stay
+    those of the configured depth."""
+    rng = random.Random(99)
+    texts = [bytes(rng.choice(b"ACGTN" if rng.random() < 0.02 else b"ACGT") for _ in range(rng.randrange(3000, 12000)))
+             for _ in range(4)]
+    oa = util.oracle_alphabet("ascii_dna_with_n")
+    for cfg_depth in (0, 3):
+        oidx = O.OracleIndex.build(texts, oa, "u32", sampling_rate=4, lookup_depth=cfg_depth)
+        cfg = gdx.FmIndexConfig("u32").lookup_table_depth(cfg_depth)
+        pidx = cfg.construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        n = pidx.total_text_len()
+        if "GDX_SEED_TABLE" not in os.environ:
+            auto = pidx.info().seed_table_depth
+            assert 4 ** auto <= n < 4 ** (auto + 1) and pidx.info().seed_table_bytes == 8 * 4 ** auto
+        valid, raising = [], []
+        for _ in range(1500):
+            t = rng.choice(texts)
+            m = rng.randrange(0, 40)
+            p = rng.randrange(0, len(t) - m)
+            q = bytearray(t[p:p + m])
+            kind = rng.randrange(6)
+            if kind == 1 and q:  # mismatch: often an empty interval inside the seed
+                q[rng.randrange(len(q))] = rng.choice(b"ACGT")
+            elif kind == 2 and q:  # invalid byte somewhere
+                q[rng.randrange(len(q))] = ord("X")
+            elif kind == 3 and q:  # N somewhere
+                q[rng.randrange(len(q))] = ord("N")
+            elif kind == 4:  # random: absent from the text after a few symbols
+                q = bytearray(rng.choice(b"ACGT") for _ in range(m))
+            q = bytes(q)
+            if cfg_depth > 0 and b"N" in q[-cfg_depth:].upper():
+                continue  # documented deviation of the configured table itself
+            try:
+                oidx.count_many([q])
+                valid.append(q)
+            except O.OraclePanic:
+                raising.append(q)
+        assert len(valid) > 800 and len(raising) > 20
+        for depth in (None, 0, 2, 5, 9):
+            if depth is not None:
+                pidx.set_seed_table_depth(depth)
+                assert pidx.info().seed_table_depth == depth
+                assert pidx.info().seed_table_bytes == (8 * 4 ** depth if depth else 0)
+            util.assert_same_results(oidx, pidx, valid)
+            for q in raising:  # panics in the reference <=> error here, per query
+                for fn in (pidx.count_many, pidx.locate_many, pidx.cursors_for_many_queries):
+                    with pytest.raises(gdx.InvalidSymbolError):
+                        fn([q])
+        assert pidx.info().lookup_table_depth == cfg_depth
+        never = cfg.seed_table(False).construct_index(texts, gdx.alphabet.ascii_dna_with_n())
+        assert never.info().seed_table_depth == 0 and never.info().seed_table_bytes == 0
+        util.assert_same_results(oidx, never, valid)

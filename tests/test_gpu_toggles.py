@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TOGGLES = [
     {"GDX_SORT_MODE": "bucket", "GDX_LOCATE_PIPELINE": "0", "GDX_L2_PERSIST": "0"},
-    {"GDX_VERIFY": "0", "GDX_SORT_QUERIES": "0", "GDX_DENSE_SA": "0", "GDX_CHUNK_FIRST_MB": "1", "GDX_CHUNK_MAX_MB": "2",
+    {"GDX_VERIFY": "0", "GDX_SORT_QUERIES": "0", "GDX_DENSE_SA": "0", "GDX_SEED_TABLE": "0", "GDX_CHUNK_FIRST_MB": "1", "GDX_CHUNK_MAX_MB": "2",
      "GDX_CHUNK_TAIL_MB": "1"},
     {"GDX_FORCE_WIDE": "1", "GDX_VERIFY_MIN": "2", "GDX_CHUNK_MAX_MB": "256", "GDX_L2_FETCH_GRANULARITY": "0"},
 ]
@@ -25,6 +25,6 @@ def test_parity_under_toggles(env):
     e.update(env)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
                           "-q", "-x", "-p", "no:cacheprovider", "-k",
-                          "chunking or verification_shortcut or cursor_shortcut or many_hits or dense_suffix"],
+                          "chunking or verification_shortcut or cursor_shortcut or many_hits or dense_suffix or seed_table"],
                          env=e, capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]

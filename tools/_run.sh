@@ -1,2 +1,6 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "extend or cursor" 2>&1 | tail -4
-python tools/run_configs.py c3 c4d0 --out gpurun_out/configs_r1_x.jsonl > gpurun_out/configs_x.log 2>&1; tail -2 gpurun_out/configs_x.log | cut -c1-1200
+for d in 12 13 14; do
+for srt in 1 0; do
+echo "D=$d sort=$srt"; GDX_SORT_QUERIES=$srt python bench.py --lookup-depth $d --steps 10 --warmup 3 --no-cpu-baseline --no-locate 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('value %.1fM q/s  %.3f ms | e2e %.1fM %.2f ms | build %s'%(d['value']/1e6,d['ms_per_step'],d['e2e']['value']/1e6,d['e2e']['ms_per_step'],d['config']['setup_s']))"
+done; done
