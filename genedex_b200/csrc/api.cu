@@ -587,7 +587,9 @@ uint64_t seed_entries(uint32_t ns, uint32_t d) {
 gdx_status build_seed_table(gdx_index *idx, uint32_t depth) {
     drop_seed_table(idx);
     const ImageHeader &h = idx->h;
-    if (depth == 0 || h.n == 0 || h.ns == 0) return GDX_OK;
+    // a level no deeper than the configured table would change nothing for the better and would move the
+    // eager translation of the configured suffix (lookup_table.rs:154-157): not built
+    if (depth <= h.lookup_depth || h.n == 0 || h.ns == 0) return GDX_OK;
     const uint64_t esz = h.wide ? 16 : 8, last = seed_entries(h.ns, depth), prev = seed_entries(h.ns, depth - 1);
     if (last == 0 || depth > 40) return fail(GDX_ERR_UNSUPPORTED, "seed table of depth %u is too large", depth);
     // levels alternate between the final buffer and a temporary one of the size of level depth - 1

@@ -227,8 +227,8 @@ gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
  * behaviour and reported lookup_table_depth are unchanged.
  * Built automatically after construction / load / adopt / replicate with the largest d such that
  * ns^d <= text length, if that needs at most a quarter of the free device memory (GDX_SEED_TABLE=0 never,
- * =d that depth; GDX_FLAG_NO_SEED_TABLE per index).  depth > 0 (re)builds it at that depth now
- * (GDX_ERR_OOM / GDX_ERR_UNSUPPORTED if it does not fit), depth <= 0 frees it.  Must not run concurrently
+ * =d that depth; GDX_FLAG_NO_SEED_TABLE per index).  depth > configured depth (re)builds it at that depth now
+ * (GDX_ERR_OOM / GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  Must not run concurrently
  * with queries on the same handle. */
 gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth);
 
