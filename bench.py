@@ -277,7 +277,7 @@ def run_reference(args, rank, world):
     ms = 1e3 * sum(times) / len(times)
     value = per_step / (ms * 1e-3)
     sample = f"{per_step} of the {nq} queries per step, {cores} threads, contiguous chunk per thread"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": "len-50 count queries/s on 3.1 Gbp DNA index", "value": value,
         "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
@@ -285,7 +285,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ---- this repo's arm ---------------------------------------------------------------------------------
@@ -509,10 +509,28 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "locate": locate,
     }
-    print(json.dumps(out))
+    emit_json(out)
+
+
+_JSON_FD = None
+
+
+def emit_json(obj):
+    """The ONE line of the contract goes to the real stdout; everything else written to fd 1 by libraries
+    (NCCL prints its version banner there) was redirected to stderr in main()."""
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
