@@ -70,7 +70,7 @@ struct DevIndex {
     uint32_t text_bits;
     // samples / sampling_rate / sampling_shift describe what resolve_row reads: the image's sampled suffix
     // array, or the dense accelerator (rate 1) once gdx_index_set_dense_suffix_array has built it
-    uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (default 8)
+    uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (8; 4 with the dense suffix array)
     uint32_t isa_rate;              // sampling rate of the inverse samples (= the configured rate)
     uint32_t seed_depth, pad3;
     uint64_t lut_level_off[kMaxLookupDepth + 1];

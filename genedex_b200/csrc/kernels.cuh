@@ -359,7 +359,7 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8
 constexpr uint64_t kDirectHit = ~0ull;
 // k_search switches from LF steps to "resolve the row + compare against the text" when the interval has
 // one row and at least DevIndex::verify_min_remaining symbols are left (a walk + sample + text read costs
-// about 5 random sectors; default 8, GDX_VERIFY_MIN overrides it for measurements)
+// about 5 random sectors; default 8, 4 once the dense suffix array is built; GDX_VERIFY_MIN overrides it for measurements)
 
 // ---- sort key of a query: its last symbols, last symbol most significant ---------------------------
 // Backward search consumes a query right to left, so queries that share a suffix walk the same
