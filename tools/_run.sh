@@ -1,8 +1,4 @@
-for v in 8 5 4 3 2; do echo "VERIFY_MIN=$v"; GDX_VERIFY_MIN=$v python tools/run_configs.py c4d0 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('count %.3f ms  cursors %.3f ms  locate e2e %.2f  lf_steps %d'%(d['count_kernel_ms'], d['cursors_kernel_ms'], d['locate_e2e_ms'], d['lf_steps']))"; done
-echo DNA; for v in 8 4 3; do GDX_VERIFY_MIN=$v python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-locate 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print('value %.1fM q/s  %.3f ms'%(d['value']/1e6,d['ms_per_step']))"; done
+python -m pytest tests -m gpu -q --timeout=1500 -p no:cacheprovider 2>&1 | tail -3
+python tools/fuzz_parity.py --seconds 40 --seed 51 2>&1 | tail -1
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r1_final3.json 2> gpurun_out/bench_r1_final3.err; tail -c 300 gpurun_out/bench_r1_final3.err
+python tools/run_configs.py --out gpurun_out/configs_r1_final3.jsonl > gpurun_out/configs_final3.log 2>&1; tail -1 gpurun_out/configs_final3.log | cut -c1-200
