@@ -578,12 +578,12 @@ void drop_seed_table(gdx_index *idx) {
     idx->seed_lut_bytes = 0;
 }
 
-// entries of level d, 0 if ns^d overflows 2^40
+// entries of level d, 0 if ns^d exceeds 2^36 (grid and memory limits)
 uint64_t seed_entries(uint32_t ns, uint32_t d) {
     uint64_t e = 1;
     for (uint32_t i = 0; i < d; ++i) {
         e *= ns;
-        if (e > (1ull << 40)) return 0;
+        if (e > (1ull << 36)) return 0;
     }
     return e;
 }
