@@ -28,14 +28,14 @@ int main(void) {
     /* texts = [b"aACGT", b"acGtn"], FmIndexConfig::<i32>::new().suffix_array_sampling_rate(2) */
     const uint8_t texts[] = "aACGTacGtn";
     const uint64_t text_offsets[3] = {0, 5, 10};
-    gdx_config config = {GDX_I32, 2, 0, 1, GDX_CONSTRUCT_AUTO, -1, 0};
+    gdx_config config = {GDX_I32, 2, 0, 1, GDX_CONSTRUCT_AUTO, -1, 0, 0};
     gdx_index *index = NULL;
     CHECK(gdx_index_build(texts, text_offsets, 2, &alphabet, &config, &index));
 
     /* index.count_many / locate_many(["AC", "CG", "GT", "GTN"]) */
     const uint8_t qbytes[] = "ACCGGTGTN";
     const uint64_t qoffsets[5] = {0, 2, 4, 6, 9};
-    gdx_queries queries = {qbytes, qoffsets, 0, 4};
+    gdx_queries queries = {qbytes, qoffsets, 0, 4, GDX_QUERIES_IO_BYTES, 0};
     uint64_t counts[4], hit_offsets[5], num_hits = 0;
     gdx_hit *hits = NULL;
     CHECK(gdx_count_many(index, &queries, counts));

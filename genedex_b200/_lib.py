@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GENEDEX_B200_LIB") or os.path.join(_HERE, "csrc", "libgenedex_b200.so")
 
 GDX_OK, GDX_ERR_INVALID_SYMBOL, GDX_ERR_BAD_ARG, GDX_ERR_CUDA, GDX_ERR_OOM, GDX_ERR_TEXT_TOO_LONG, \
-    GDX_ERR_UNSUPPORTED = range(7)
+    GDX_ERR_UNSUPPORTED, GDX_ERR_BUSY = range(8)
 GDX_I32, GDX_U32, GDX_I64 = 0, 1, 2
 GDX_CONSTRUCT_HOST, GDX_CONSTRUCT_DEVICE, GDX_CONSTRUCT_AUTO = 0, 1, 2
 GDX_FLAG_VERIFY_SUFFIX_ARRAY = 1
@@ -21,6 +21,9 @@ GDX_FLAG_NO_TEXT = 2
 GDX_FLAG_NO_INVERSE_SAMPLES = 4
 GDX_FLAG_NO_DENSE_SUFFIX_ARRAY = 8
 GDX_FLAG_NO_SEED_TABLE = 16
+GDX_QUERIES_IO_BYTES, GDX_QUERIES_PACKED_2BIT = 0, 1
+GDX_NCCL_UNIQUE_ID_BYTES = 128
+GDX_ABI_VERSION = 2
 
 
 class gdx_alphabet(C.Structure):
@@ -31,7 +34,8 @@ class gdx_alphabet(C.Structure):
 class gdx_config(C.Structure):
     _fields_ = [("storage", C.c_uint32), ("suffix_array_sampling_rate", C.c_uint32),
                 ("lookup_table_depth", C.c_uint32), ("performance_priority", C.c_uint32),
-                ("construction", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32)]
+                ("construction", C.c_uint32), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("accelerator_budget_bytes", C.c_uint64)]
 
 
 class gdx_hit(C.Structure):
@@ -39,7 +43,8 @@ class gdx_hit(C.Structure):
 
 
 class gdx_queries(C.Structure):
-    _fields_ = [("bytes", C.c_void_p), ("offsets", C.c_void_p), ("fixed_len", C.c_uint64), ("nq", C.c_uint64)]
+    _fields_ = [("bytes", C.c_void_p), ("offsets", C.c_void_p), ("fixed_len", C.c_uint64), ("nq", C.c_uint64),
+                ("encoding", C.c_uint32), ("first_symbol", C.c_uint32)]
 
 
 class gdx_parts(C.Structure):
@@ -49,7 +54,8 @@ class gdx_parts(C.Structure):
                 ("sampling_rate", C.c_uint32), ("text_border_rows", C.c_void_p),
                 ("text_border_positions", C.c_void_p), ("num_text_borders", C.c_uint64),
                 ("sentinel_indices", C.c_void_p), ("num_texts", C.c_uint64),
-                ("lookup_table_depth", C.c_uint32)]
+                ("lookup_table_depth", C.c_uint32), ("sampled_suffix_array_u32", C.c_void_p),
+                ("flags", C.c_uint32), ("accelerator_budget_bytes", C.c_uint64)]
 
 
 class gdx_index_info(C.Structure):
@@ -68,7 +74,9 @@ class gdx_stats(C.Structure):
     _fields_ = [("queries", C.c_uint64), ("lf_steps", C.c_uint64), ("hits", C.c_uint64),
                 ("walk_steps", C.c_uint64), ("kernel_ms_search", C.c_double),
                 ("kernel_ms_locate", C.c_double), ("kernel_launches", C.c_uint64),
-                ("verified_queries", C.c_uint64)]
+                ("verified_queries", C.c_uint64), ("locate_walk_steps", C.c_uint64),
+                ("packed_queries", C.c_uint64), ("exception_queries", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("shards", C.c_uint64)]
 
 
 # every symbol include/genedex_b200.h declares: name -> (restype, argtypes)
@@ -98,6 +106,18 @@ PROTOTYPES = {
     "gdx_index_export": (C.c_int, [_vp, _vp, _P(_vp), _P(_u64)]),
     "gdx_index_adopt_image": (C.c_int, [_vp, _vp, _i32, _i32, _P(_vp)]),
     "gdx_index_replicate": (C.c_int, [_vp, _P(_i32), _i32, _P(_vp)]),
+    "gdx_replicate_transport": (C.c_char_p, []),
+    "gdx_nccl_unique_id": (C.c_int, [_vp]),
+    "gdx_index_broadcast": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _P(_vp)]),
+    "gdx_shard_range": (None, [_u64, _u32, _u32, _P(_u64), _P(_u64)]),
+    "gdx_count_many_sharded": (C.c_int, [_P(_vp), _u32, _u32, _u32, _P(gdx_queries), _vp]),
+    "gdx_cursors_many_sharded": (C.c_int, [_P(_vp), _u32, _u32, _u32, _P(gdx_queries), _vp, _vp]),
+    "gdx_locate_many_sharded": (C.c_int, [_P(_vp), _u32, _u32, _u32, _P(gdx_queries), _vp, _P(_vp), _P(_u64)]),
+    "gdx_count_many_u32": (C.c_int, [_vp, _P(gdx_queries), _vp]),
+    "gdx_cursors_many_u32": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp]),
+    "gdx_packed_bytes": (_u64, [_u64]),
+    "gdx_pack_queries": (C.c_int, [_vp, _P(gdx_queries), _vp, _P(_u64)]),
+    "gdx_pack_symbols": (C.c_int, [_P(gdx_alphabet), _vp, _u64, _vp, _vp, _u64, _P(_u64)]),
     "gdx_cursors_many": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp]),
     "gdx_count_many": (C.c_int, [_vp, _P(gdx_queries), _vp]),
     "gdx_locate_many": (C.c_int, [_vp, _P(gdx_queries), _vp, _P(_vp), _P(_u64)]),
@@ -130,7 +150,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError = the library does not match the header
         fn.restype = res
         fn.argtypes = args
-    if lib.gdx_abi_version() != 1:
+    if lib.gdx_abi_version() != GDX_ABI_VERSION:
         raise ImportError("genedex_b200: ABI version mismatch between the Python package and the library")
     _lib = lib
     return lib

@@ -1,6 +1,7 @@
 // api.cu -- C ABI of genedex_b200 (include/genedex_b200.h): index handles, device image
 // construction from host parts, chunked H2D / kernel / D2H pipelines, locate CSR plumbing.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <type_traits>
 
 #include <algorithm>
@@ -14,6 +15,8 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -24,6 +27,7 @@
 #include "device_build.h"
 #include "device_index.h"
 #include "host_build.h"
+#include "host_pack.h"
 #include "kernels.cuh"
 
 using namespace gdx;
@@ -59,6 +63,20 @@ gdx_status fail(gdx_status st, const char *fmt, ...) {
         gdx_status _s = (expr);        \
         if (_s != GDX_OK) return _s;   \
     } while (0)
+
+// exceptions must not cross the C boundary (std::bad_alloc from a host vector, std::system_error from a thread)
+template <class F>
+gdx_status guarded(F &&f) noexcept {
+    try {
+        return f();
+    } catch (const std::bad_alloc &) {
+        return fail(GDX_ERR_OOM, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(GDX_ERR_BAD_ARG, "unexpected failure: %s", e.what());
+    } catch (...) {
+        return fail(GDX_ERR_BAD_ARG, "unexpected failure");
+    }
+}
 
 uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 uint64_t div_up(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
@@ -162,84 +180,12 @@ bool is_pinned(const void *p) {
     return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
 }
 
-// A few host threads that copy between pageable caller memory and the pinned staging buffers: one thread
-// moves ~10 GB/s, a PCIe Gen5 link 52 GB/s.  One job at a time; the calling thread works too.
-class HostPool {
-public:
-    static HostPool &get() {
-        static HostPool pool;
-        return pool;
-    }
-    void copy(void *dst, const void *src, uint64_t bytes) {
-        constexpr uint64_t kPiece = 2ull << 20;
-        if (bytes <= 2 * kPiece || workers_.empty()) {
-            memcpy(dst, src, bytes);
-            return;
-        }
-        std::lock_guard<std::mutex> one_job(job_mu_);
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            dst_ = (uint8_t *)dst;
-            src_ = (const uint8_t *)src;
-            bytes_ = bytes;
-            pieces_ = (bytes + kPiece - 1) / kPiece;
-            next_.store(0);
-            done_ = 0;
-            ++generation_;
-        }
-        cv_.notify_all();
-        work(kPiece);
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return done_ == pieces_; });
-    }
-
-private:
-    HostPool() {
-        unsigned n = std::thread::hardware_concurrency();
-        n = n > 2 ? std::min(7u, n / 2) : 0;  // plus the caller
-        for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
-    }
-    ~HostPool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto &t : workers_) t.join();
-    }
-    void work(uint64_t piece) {
-        for (;;) {
-            const uint64_t k = next_.fetch_add(1);
-            if (k >= pieces_) break;
-            const uint64_t off = k * piece, nb = std::min(piece, bytes_ - off);
-            memcpy(dst_ + off, src_ + off, nb);
-            std::lock_guard<std::mutex> lk(mu_);
-            if (++done_ == pieces_) done_cv_.notify_all();
-        }
-    }
-    void loop() {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
-                if (stop_) return;
-                seen = generation_;
-            }
-            work(2ull << 20);
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex mu_, job_mu_;
-    std::condition_variable cv_, done_cv_;
-    uint8_t *dst_ = nullptr;
-    const uint8_t *src_ = nullptr;
-    uint64_t bytes_ = 0, pieces_ = 0, done_ = 0, generation_ = 0;
-    std::atomic<uint64_t> next_{0};
-    bool stop_ = false;
-};
-
-constexpr uint64_t kStageMinBytes = 4ull << 20;  // smaller transfers go through the driver's own staging
+uint64_t env_bytes(const char *name, uint64_t dflt) {
+    const char *e = getenv(name);
+    return e && *e ? (uint64_t)strtoull(e, nullptr, 10) : dflt;
+}
+// smaller transfers go through the driver's own staging (GDX_STAGE_MIN_BYTES: tests force the staged paths)
+const uint64_t kStageMinBytes = env_bytes("GDX_STAGE_MIN_BYTES", 4ull << 20);
 
 constexpr int kSlots = 3;
 // Pipeline chunking (defaults 4 / 32 / 4 MB, profiles/r1_ab_pipeline_chunks.txt): the byte budget of
@@ -263,8 +209,13 @@ struct Slot {
     uint64_t *d_words = nullptr;  // device: [0] number of wide intervals, [1] worklist cursor
     uint64_t *h_words = nullptr;  // pinned: [0] hits of the chunk, [1] number of wide intervals
     cudaEvent_t ev_total = nullptr;
-    // staging for pageable caller buffers
+    // staging for pageable caller buffers / packed queries / narrow results
     HBuf h_in, h_off, h_out_a, h_out_b;
+    // queries of a packed chunk that hold a byte without a 2-bit code: offsets + slots + IO bytes, re-run raw
+    HBuf h_x;
+    DBuf xbuf;
+    std::vector<cudaEvent_t> ev_loc;  // pairs (begin, end) around the locate kernels of the current call
+    size_t ev_loc_used = 0;
     cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
     bool h2d_pending = false;
     std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
@@ -310,8 +261,10 @@ struct Workspace {
             if (s.ev_total) cudaEventDestroy(s.ev_total);
             if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
             if (s.ev_out) cudaEventDestroy(s.ev_out);
-            for (HBuf *b : {&s.h_in, &s.h_off, &s.h_out_a, &s.h_out_b}) b->release();
+            for (HBuf *b : {&s.h_in, &s.h_off, &s.h_out_a, &s.h_out_b, &s.h_x}) b->release();
+            s.xbuf.release();
             for (auto e : s.ev) cudaEventDestroy(e);
+            for (auto e : s.ev_loc) cudaEventDestroy(e);
         }
         if (small.h) cudaFreeHost(small.h);
         if (small.d) cudaFree(small.d);
@@ -327,6 +280,14 @@ struct Workspace {
             s.ev.push_back(e);
         }
         return s.ev[s.ev_used++];
+    }
+    cudaEvent_t next_locate_event(Slot &s) {
+        if (s.ev_loc_used == s.ev_loc.size()) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            s.ev_loc.push_back(e);
+        }
+        return s.ev_loc[s.ev_loc_used++];
     }
 };
 
@@ -346,10 +307,12 @@ struct gdx_index {
     DevIndex dev;
     void *dense_sa = nullptr;      // accelerator outside the image (gdx_index_set_dense_suffix_array)
     uint64_t dense_sa_bytes = 0;
-    bool no_dense_sa = false;      // GDX_FLAG_NO_DENSE_SUFFIX_ARRAY
     void *seed_lut = nullptr;      // accelerator outside the image (gdx_index_set_seed_table_depth)
     uint64_t seed_lut_bytes = 0;
-    bool no_seed_table = false;    // GDX_FLAG_NO_SEED_TABLE
+    PackTable pack;                // io byte -> 2-bit code (host packer, host_pack.h)
+    // host-buffer queries hold this shared for the whole call; (re)building or freeing an accelerator needs it
+    // exclusively and reports GDX_ERR_BUSY instead of pulling memory from under a running kernel
+    mutable std::shared_mutex cfg_mu;
     mutable std::mutex mu;
     mutable std::vector<Workspace *> free_ws;
     mutable std::vector<PinnedHits> pinned;
@@ -439,7 +402,16 @@ struct ImageSources {
     // optional sampled inverse suffix array (one of them, only together with d_text)
     const uint64_t *h_isa64 = nullptr;      // host
     const uint32_t *d_isa32 = nullptr;      // device
+    const uint32_t *h_samples32 = nullptr;  // host, the crate's own Vec<u32> for 32-bit storage
+    // accelerator policy of the index (travels with the image)
+    uint32_t accel_flags = 0;
+    uint64_t accel_budget = 0;
 };
+
+uint32_t accel_flags_from_config(uint32_t flags) {
+    return ((flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) ? kAccelNoDenseSA : 0u) |
+           ((flags & GDX_FLAG_NO_SEED_TABLE) ? kAccelNoSeedTable : 0u);
+}
 
 gdx_status validate_alphabet(const gdx_alphabet &a) {
     if (a.num_dense_symbols < 2 || a.num_dense_symbols > 256)
@@ -452,7 +424,8 @@ gdx_status validate_alphabet(const gdx_alphabet &a) {
     return GDX_OK;
 }
 
-gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
+// wide_override: -1 = decide from the text length (and GDX_FORCE_WIDE), 0 / 1 = as given (header validation)
+gdx_status plan_header(const ImageSources &src, ImageHeader &h, int wide_override = -1) {
     memset(&h, 0, sizeof h);
     h.magic = kImageMagic;
     h.version = GDX_ABI_VERSION;
@@ -464,10 +437,13 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     h.storage = src.storage;
     h.sampling_rate = src.sampling_rate;
     h.lookup_depth = src.lookup_depth;
+    h.accel_flags = src.accel_flags;
+    h.accel_budget = src.accel_budget;
     // 64-bit samples / lookup entries are only needed beyond 2^32 - 1 symbols; GDX_FORCE_WIDE=1 selects them
     // for any text so that this path can be tested without a 4.3 G symbol index
     const char *fw = getenv("GDX_FORCE_WIDE");
     h.wide = (src.n > 0xffffffffull || (fw && atoi(fw) != 0)) ? 1 : 0;
+    if (wide_override >= 0) h.wide = (src.n > 0xffffffffull || wide_override) ? 1 : 0;
     h.layout = choose_layout(h.sigma);
     memcpy(h.io_to_dense, src.alphabet->io_to_dense, 256);
     if (src.lookup_depth > kMaxLookupDepth)
@@ -520,8 +496,43 @@ gdx_status plan_header(const ImageSources &src, ImageHeader &h) {
     return GDX_OK;
 }
 
+// An image header that comes from a file or a peer is untrusted: every size, offset and the record layout are
+// re-derived from its scalar fields and must match, so that no kernel ever indexes with a value the planner
+// would not have produced.
+gdx_status validate_header(const ImageHeader &h) {
+    if (h.magic != kImageMagic || h.version != GDX_ABI_VERSION)
+        return fail(GDX_ERR_BAD_ARG, "not a genedex_b200 image header of this version (magic/version mismatch)");
+    gdx_alphabet a;
+    memcpy(a.io_to_dense, h.io_to_dense, 256);
+    a.num_dense_symbols = h.sigma;
+    a.num_searchable_dense_symbols = h.ns;
+    GDX_TRY(validate_alphabet(a));
+    if (h.sampling_rate == 0 || h.lookup_depth > kMaxLookupDepth || h.storage > GDX_I64 || h.ntexts == 0 ||
+        h.n_border > h.n || h.ntexts > h.n || (h.text_bits != 0 && h.text_bits != 4 && h.text_bits != 8) || h.has_isa > 1 ||
+        h.wide > 1 || h.n > (1ull << 48))
+        return fail(GDX_ERR_BAD_ARG, "image header: field out of range");
+    ImageSources src;
+    src.alphabet = &a;
+    src.storage = h.storage;
+    src.sampling_rate = h.sampling_rate;
+    src.lookup_depth = h.lookup_depth;
+    src.n = h.n;
+    src.ntexts = h.ntexts;
+    src.n_border = h.n_border;
+    src.d_text = h.text_bits ? reinterpret_cast<const uint8_t *>(&a) : nullptr;            // presence only
+    src.d_isa32 = h.has_isa ? reinterpret_cast<const uint32_t *>(&a) : nullptr;            // presence only
+    src.accel_flags = h.accel_flags;
+    src.accel_budget = h.accel_budget;
+    ImageHeader want;
+    GDX_TRY(plan_header(src, want, (int)h.wide));
+    if (memcmp(&want, &h, sizeof(ImageHeader)) != 0)
+        return fail(GDX_ERR_BAD_ARG, "image header is inconsistent (sizes / offsets do not match its own fields)");
+    return GDX_OK;
+}
+
 // run-time overrides of kernel parameters (measurements only)
 gdx_status init_policies(gdx_index *idx) {
+    build_pack_table(idx->h.io_to_dense, idx->h.ns, idx->pack);
     if (const char *vm = getenv("GDX_VERIFY_MIN"))
         if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
     return GDX_OK;
@@ -637,19 +648,36 @@ gdx_status build_seed_table(gdx_index *idx, uint32_t depth) {
     return GDX_OK;
 }
 
+// Accelerator policy (include/genedex_b200.h): flags and byte budget live in the image header, so every way of
+// making a replica follows the same rule.  Without a budget an accelerator may take a quarter of the memory
+// that is free right now.  GDX_DENSE_SA / GDX_SEED_TABLE override the policy for measurements.
+uint64_t accel_room(const gdx_index *idx) {
+    if (idx->h.accel_budget) {
+        const uint64_t used = idx->dense_sa_bytes + idx->seed_lut_bytes;
+        return idx->h.accel_budget > used ? idx->h.accel_budget - used : 0;
+    }
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    return free_b / 4;
+}
+
 void auto_seed_table(gdx_index *idx) {
-    if (!idx || idx->no_seed_table || idx->h.n == 0 || idx->h.ns < 2) return;
+    if (!idx || idx->h.n == 0 || idx->h.ns < 2) return;
     const char *e = getenv("GDX_SEED_TABLE");
     uint32_t depth = 0;
     if (e) {
         if (atoi(e) <= 0) return;
         depth = (uint32_t)atoi(e);
     } else {
+        if (idx->h.accel_flags & kAccelNoSeedTable) return;
         while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= idx->h.n) ++depth;
+        const uint64_t esz = idx->h.wide ? 16 : 8, room = accel_room(idx);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
-        const uint64_t esz = idx->h.wide ? 16 : 8;
-        while (depth > 0 && (seed_entries(idx->h.ns, depth) + seed_entries(idx->h.ns, depth - 1)) * esz > free_b / 4) --depth;
+        // the finished level must fit the budget; the temporary previous level only has to fit the device
+        while (depth > 0 && (seed_entries(idx->h.ns, depth) * esz > room ||
+                             (seed_entries(idx->h.ns, depth) + seed_entries(idx->h.ns, depth - 1)) * esz > free_b))
+            --depth;
     }
     if (depth <= idx->h.lookup_depth) return;  // the configured table is at least as deep
     if (build_seed_table(idx, depth) != GDX_OK) t_error.clear();  // optional: not an error of the call
@@ -657,13 +685,12 @@ void auto_seed_table(gdx_index *idx) {
 
 // best effort after every way of creating a replica; the caller holds a DeviceGuard and has freed its temporaries
 void auto_dense_sa(gdx_index *idx) {
-    if (!idx || idx->no_dense_sa || idx->h.n == 0) return;
+    if (!idx || idx->h.n == 0) return;
     const char *e = getenv("GDX_DENSE_SA");
     if (e && atoi(e) == 0) return;
     if (!(e && atoi(e) != 0)) {
-        size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
-        if (idx->h.n * (idx->h.wide ? 8ull : 4ull) > free_b / 4) return;
+        if (idx->h.accel_flags & kAccelNoDenseSA) return;
+        if (idx->h.n * (idx->h.wide ? 8ull : 4ull) > accel_room(idx)) return;
     }
     if (build_dense_sa(idx) != GDX_OK) t_error.clear();  // optional: not an error of the call
 }
@@ -728,6 +755,14 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
                 std::vector<uint32_t> narrow(h.n_samples);
                 for (uint64_t i = 0; i < h.n_samples; ++i) narrow[i] = (uint32_t)src.h_samples64[i];
                 IMG_TRY(cudaMemcpy(dst, narrow.data(), h.n_samples * 4, cudaMemcpyHostToDevice));
+            }
+        } else if (src.h_samples32) {
+            if (!h.wide) {
+                IMG_TRY(cudaMemcpy(dst, src.h_samples32, h.n_samples * 4, cudaMemcpyHostToDevice));
+            } else {
+                std::vector<uint64_t> wide(h.n_samples);
+                for (uint64_t i = 0; i < h.n_samples; ++i) wide[i] = src.h_samples32[i];
+                IMG_TRY(cudaMemcpy(dst, wide.data(), h.n_samples * 8, cudaMemcpyHostToDevice));
             }
         } else if (src.d_samples) {
             const unsigned g = (unsigned)div_up(h.n_samples, 256);
@@ -883,6 +918,8 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     src.count = ct.count.data();
     src.sentinels = ct.sentinels.data();
     src.ntexts = num_texts;
+    src.accel_flags = accel_flags_from_config(config->flags);
+    src.accel_budget = config->accelerator_budget_bytes;
 
     // the dense text goes to the device once: input of the device suffix sort and source of the
     // optional text section of the image
@@ -928,8 +965,6 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         st = build_image(src, device, out);
         r.release();
         if (st == GDX_OK) {
-            (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
-            (*out)->no_seed_table = (config->flags & GDX_FLAG_NO_SEED_TABLE) != 0;
             auto_dense_sa(*out);
             auto_seed_table(*out);
         }
@@ -954,8 +989,6 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
     st = build_image(src, device, out);
     cudaFree(d_bwt);
     if (st == GDX_OK) {
-        (*out)->no_dense_sa = (config->flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) != 0;
-        (*out)->no_seed_table = (config->flags & GDX_FLAG_NO_SEED_TABLE) != 0;
         auto_dense_sa(*out);
         auto_seed_table(*out);
     }
@@ -992,7 +1025,12 @@ static gdx_status sources_from_parts(const gdx_parts *parts, ImageSources &src,
     src.border_rows = rows.data();
     src.border_pos = pos.data();
     src.n_border = rows.size();
+    if ((parts->sampled_suffix_array != nullptr) == (parts->sampled_suffix_array_u32 != nullptr) && parts->text_len)
+        return fail(GDX_ERR_BAD_ARG, "exactly one of sampled_suffix_array / sampled_suffix_array_u32 must be set");
     src.h_samples64 = parts->sampled_suffix_array;
+    src.h_samples32 = parts->sampled_suffix_array_u32;
+    src.accel_flags = accel_flags_from_config(parts->flags);
+    src.accel_budget = parts->accelerator_budget_bytes;
     return GDX_OK;
 }
 
@@ -1264,11 +1302,19 @@ extern "C" gdx_status gdx_index_load_from_file(const char *path, int32_t device_
         fread(&h, sizeof h, 1, fc.f) != 1 || h.magic != kImageMagic || h.version != GDX_ABI_VERSION ||
         h.image_bytes != p.image_bytes)
         return fail(GDX_ERR_BAD_ARG, "%s is not a genedex_b200 index file of this version", path);
+    GDX_TRY(validate_header(h));
+    // the sizes in the prefix must add up to the size of the file before anything is allocated from them
+    const off_t here = ftello(fc.f);
+    if (here < 0 || fseeko(fc.f, 0, SEEK_END) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
+    const off_t file_size = ftello(fc.f);
+    if (fseeko(fc.f, here, SEEK_SET) != 0 || file_size < here || p.user_bytes > (uint64_t)(file_size - here) ||
+        p.image_bytes != (uint64_t)(file_size - here) - p.user_bytes)
+        return fail(GDX_ERR_BAD_ARG, "%s is truncated or corrupt (section sizes do not add up to the file size)", path);
     if (user_bytes_out) *user_bytes_out = p.user_bytes;
     if (p.user_bytes) {
-        std::vector<uint8_t> blob(p.user_bytes);
-        if (fread(blob.data(), p.user_bytes, 1, fc.f) != 1) return fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
-        if (user_data_out) memcpy(user_data_out, blob.data(), std::min<uint64_t>(p.user_bytes, user_capacity));
+        const uint64_t keep = user_data_out ? std::min<uint64_t>(p.user_bytes, user_capacity) : 0;
+        if (keep && fread(user_data_out, keep, 1, fc.f) != 1) return fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
+        if (fseeko(fc.f, here + (off_t)p.user_bytes, SEEK_SET) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
     }
     int device;
     GDX_TRY(resolve_device(device_req, &device));
@@ -1310,11 +1356,11 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
     *out = nullptr;
     ImageHeader h;
     memcpy(&h, header, sizeof h);
-    if (h.magic != kImageMagic || h.version != GDX_ABI_VERSION)
-        return fail(GDX_ERR_BAD_ARG, "not a genedex_b200 image header (magic/version mismatch)");
+    GDX_TRY(validate_header(h));
     int device;
     GDX_TRY(resolve_device(device_req, &device));
-    gdx_index *idx = new gdx_index();
+    gdx_index *idx = new (std::nothrow) gdx_index();
+    if (!idx) return fail(GDX_ERR_OOM, "out of host memory");
     idx->h = h;
     idx->image = device_image;
     idx->own_image = own_image != 0;
@@ -1336,6 +1382,8 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
 
 extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth) {
     if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the seed table cannot change now");
     DeviceGuard guard(idx->device);
     if (depth <= 0) {
         drop_seed_table(idx);
@@ -1346,34 +1394,253 @@ extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t dep
 
 extern "C" gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on) {
     if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the dense suffix array cannot change now");
     DeviceGuard guard(idx->device);
     if (on) return build_dense_sa(idx);
     drop_dense_sa(idx);
     return GDX_OK;
 }
 
+// ---- NCCL, loaded at run time ---------------------------------------------------------------------------
+// The library does not link libnccl: a process that already carries one (PyTorch bundles its own libnccl.so.2)
+// must not get a second copy, and single-GPU users need none.  The handful of entry points used here has been
+// ABI-stable since NCCL 2.
+namespace {
+struct Nccl {
+    typedef struct ncclComm *comm_t;
+    struct unique_id {
+        char internal[GDX_NCCL_UNIQUE_ID_BYTES];
+    };
+    int (*GetUniqueId)(unique_id *) = nullptr;
+    int (*CommInitRank)(comm_t *, int, unique_id, int) = nullptr;
+    int (*CommInitAll)(comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    int (*Broadcast)(const void *, void *, size_t, int /*ncclDataType_t*/, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+    static constexpr int kUint8 = 1;  // ncclUint8
+};
+
+const Nccl &nccl() {
+    static const Nccl n = [] {
+        Nccl r;
+        const char *names[] = {getenv("GDX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        void *h = nullptr;
+        for (const char *nm : names)
+            if (nm && *nm && (h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!h) {
+            r.why = "libnccl.so.2 could not be loaded";
+            return r;
+        }
+        auto sym = [&](const char *name) { return dlsym(h, name); };
+        r.GetUniqueId = (decltype(r.GetUniqueId))sym("ncclGetUniqueId");
+        r.CommInitRank = (decltype(r.CommInitRank))sym("ncclCommInitRank");
+        r.CommInitAll = (decltype(r.CommInitAll))sym("ncclCommInitAll");
+        r.CommDestroy = (decltype(r.CommDestroy))sym("ncclCommDestroy");
+        r.Broadcast = (decltype(r.Broadcast))sym("ncclBroadcast");
+        r.GroupStart = (decltype(r.GroupStart))sym("ncclGroupStart");
+        r.GroupEnd = (decltype(r.GroupEnd))sym("ncclGroupEnd");
+        r.GetErrorString = (decltype(r.GetErrorString))sym("ncclGetErrorString");
+        r.ok = r.GetUniqueId && r.CommInitRank && r.CommInitAll && r.CommDestroy && r.Broadcast && r.GroupStart &&
+               r.GroupEnd && r.GetErrorString;
+        if (!r.ok) r.why = "libnccl.so.2 lacks an expected entry point";
+        return r;
+    }();
+    return n;
+}
+
+#define NCCL_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        int _r = (expr);                                                                                   \
+        if (_r != 0) return fail(GDX_ERR_CUDA, "%s failed: %s", #expr, nccl().GetErrorString(_r));         \
+    } while (0)
+
+thread_local const char *t_transport = "";
+constexpr uint64_t kBroadcastPiece = 1ull << 30;
+}  // namespace
+
+extern "C" const char *gdx_replicate_transport(void) { return t_transport; }
+
 extern "C" gdx_status gdx_index_replicate(const gdx_index *idx, const int32_t *devices, int32_t n_devices,
                                           gdx_index **out_replicas) {
-    if (!idx || !devices || !out_replicas || n_devices < 0) return fail(GDX_ERR_BAD_ARG, "bad argument");
-    for (int i = 0; i < n_devices; ++i) out_replicas[i] = nullptr;
-    for (int i = 0; i < n_devices; ++i) {
-        int device;
-        GDX_TRY(resolve_device(devices[i], &device));
-        DeviceGuard guard(device);
-        void *img = nullptr;
-        CUDA_TRY(cudaMalloc(&img, idx->h.image_bytes));
-        cudaError_t e = cudaMemcpyPeer(img, device, idx->image, idx->device, idx->h.image_bytes);
-        if (e != cudaSuccess) {
-            cudaFree(img);
-            return fail(GDX_ERR_CUDA, "peer copy to device %d failed: %s", device, cudaGetErrorString(e));
+    return guarded([&]() -> gdx_status {
+        if (!idx || !devices || !out_replicas || n_devices < 0) return fail(GDX_ERR_BAD_ARG, "bad argument");
+        t_transport = "";
+        for (int i = 0; i < n_devices; ++i) out_replicas[i] = nullptr;
+        std::vector<int> dev(n_devices);
+        for (int i = 0; i < n_devices; ++i) GDX_TRY(resolve_device(devices[i], &dev[i]));
+        std::vector<void *> img(n_devices, nullptr);
+        auto free_images = [&] {
+            for (int i = 0; i < n_devices; ++i)
+                if (img[i]) {
+                    DeviceGuard g(dev[i]);
+                    cudaFree(img[i]);
+                    img[i] = nullptr;
+                }
+        };
+        const uint64_t bytes = idx->h.image_bytes;
+        for (int i = 0; i < n_devices; ++i) {
+            DeviceGuard g(dev[i]);
+            cudaError_t e = cudaMalloc(&img[i], bytes ? bytes : 1);
+            if (e != cudaSuccess) {
+                free_images();
+                return fail(GDX_ERR_OOM, "replica on device %d: %s", dev[i], cudaGetErrorString(e));
+            }
         }
-        gdx_status st = gdx_index_adopt_image(&idx->h, img, device, 1, &out_replicas[i]);
+        // communicator over the source device + every distinct other target; targets on the source device (and
+        // repeated targets) are filled by device-to-device copies afterwards
+        std::vector<int> comm_dev{idx->device};
+        std::vector<int> member(n_devices, -1);  // rank of target i in the communicator, -1 = copy
+        for (int i = 0; i < n_devices; ++i) {
+            if (std::find(comm_dev.begin(), comm_dev.end(), dev[i]) != comm_dev.end()) continue;
+            member[i] = (int)comm_dev.size();
+            comm_dev.push_back(dev[i]);
+        }
+        const bool want_nccl = comm_dev.size() > 1 && !(getenv("GDX_REPLICATE") && strcmp(getenv("GDX_REPLICATE"), "peer") == 0);
+        bool done = comm_dev.size() <= 1;
+        if (want_nccl && nccl().ok) {
+            const Nccl &N = nccl();
+            const int world = (int)comm_dev.size();
+            std::vector<Nccl::comm_t> comms(world, nullptr);
+            std::vector<cudaStream_t> streams(world, nullptr);
+            gdx_status st = [&]() -> gdx_status {
+                NCCL_TRY(N.CommInitAll(comms.data(), world, comm_dev.data()));
+                for (int r = 0; r < world; ++r) {
+                    DeviceGuard g(comm_dev[r]);
+                    CUDA_TRY(cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking));
+                }
+                for (uint64_t off = 0; off < bytes; off += kBroadcastPiece) {
+                    const uint64_t nb = std::min(kBroadcastPiece, bytes - off);
+                    NCCL_TRY(N.GroupStart());
+                    for (int r = 0; r < world; ++r) {
+                        void *recv = (uint8_t *)idx->image + off;  // root: in place
+                        for (int i = 0; i < n_devices && r > 0; ++i)
+                            if (member[i] == r) recv = (uint8_t *)img[i] + off;
+                        DeviceGuard g(comm_dev[r]);
+                        NCCL_TRY(N.Broadcast((const uint8_t *)idx->image + off, recv, nb, Nccl::kUint8, 0, comms[r], streams[r]));
+                    }
+                    NCCL_TRY(N.GroupEnd());
+                }
+                for (int r = 0; r < world; ++r) {
+                    DeviceGuard g(comm_dev[r]);
+                    CUDA_TRY(cudaStreamSynchronize(streams[r]));
+                }
+                return GDX_OK;
+            }();
+            for (int r = 0; r < world; ++r) {
+                DeviceGuard g(comm_dev[r]);
+                if (streams[r]) cudaStreamDestroy(streams[r]);
+                if (comms[r]) N.CommDestroy(comms[r]);
+            }
+            if (st != GDX_OK) {
+                free_images();
+                return st;
+            }
+            t_transport = "nccl";
+            done = true;
+        }
+        for (int i = 0; i < n_devices; ++i) {
+            if (done && member[i] >= 0) continue;
+            // same device as the source or as an earlier target (or no NCCL): a plain copy
+            DeviceGuard g(dev[i]);
+            const void *from = idx->image;
+            int from_dev = idx->device;
+            if (done && member[i] < 0 && dev[i] != idx->device)
+                for (int j = 0; j < i; ++j)
+                    if (dev[j] == dev[i] && member[j] >= 0) {
+                        from = img[j];
+                        from_dev = dev[j];
+                    }
+            cudaError_t e = cudaMemcpyPeer(img[i], dev[i], from, from_dev, bytes);
+            if (e != cudaSuccess) {
+                free_images();
+                return fail(GDX_ERR_CUDA, "copy to device %d failed: %s", dev[i], cudaGetErrorString(e));
+            }
+            if (!done && *t_transport == 0) t_transport = "peer";
+        }
+        if (*t_transport == 0) t_transport = "peer";
+        for (int i = 0; i < n_devices; ++i) {
+            gdx_status st = gdx_index_adopt_image(&idx->h, img[i], dev[i], 1, &out_replicas[i]);
+            if (st != GDX_OK) {
+                for (int j = 0; j < i; ++j) {
+                    gdx_index_destroy(out_replicas[j]);
+                    out_replicas[j] = nullptr;
+                    img[j] = nullptr;
+                }
+                free_images();
+                return st;
+            }
+            img[i] = nullptr;  // owned by the replica now
+        }
+        return GDX_OK;
+    });
+}
+
+extern "C" gdx_status gdx_nccl_unique_id(void *id_out) {
+    if (!id_out) return fail(GDX_ERR_BAD_ARG, "id_out is NULL");
+    if (!nccl().ok) return fail(GDX_ERR_UNSUPPORTED, "NCCL is not available: %s", nccl().why.c_str());
+    Nccl::unique_id id;
+    NCCL_TRY(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return GDX_OK;
+}
+
+extern "C" gdx_status gdx_index_broadcast(const gdx_index *src, const void *unique_id, int32_t rank, int32_t world,
+                                          int32_t root, int32_t device_req, gdx_index **out) {
+    return guarded([&]() -> gdx_status {
+        if (!out || !unique_id || world < 1 || rank < 0 || rank >= world || root < 0 || root >= world)
+            return fail(GDX_ERR_BAD_ARG, "bad argument");
+        *out = nullptr;
+        if ((rank == root) != (src != nullptr)) return fail(GDX_ERR_BAD_ARG, "src must be given on the root rank and only there");
+        if (!nccl().ok) return fail(GDX_ERR_UNSUPPORTED, "NCCL is not available: %s", nccl().why.c_str());
+        const Nccl &N = nccl();
+        int device;
+        GDX_TRY(resolve_device(rank == root ? src->device : device_req, &device));
+        DeviceGuard guard(device);
+        Nccl::unique_id id;
+        memcpy(&id, unique_id, sizeof id);
+        Nccl::comm_t comm = nullptr;
+        NCCL_TRY(N.CommInitRank(&comm, world, id, rank));
+        cudaStream_t stream = nullptr;
+        void *d_hdr = nullptr, *image = nullptr;
+        ImageHeader h;
+        gdx_status st = [&]() -> gdx_status {
+            CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaMalloc(&d_hdr, sizeof(ImageHeader)));
+            if (rank == root) CUDA_TRY(cudaMemcpyAsync(d_hdr, &src->h, sizeof(ImageHeader), cudaMemcpyHostToDevice, stream));
+            NCCL_TRY(N.Broadcast(d_hdr, d_hdr, sizeof(ImageHeader), Nccl::kUint8, root, comm, stream));
+            CUDA_TRY(cudaMemcpyAsync(&h, d_hdr, sizeof(ImageHeader), cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            GDX_TRY(validate_header(h));
+            if (rank == root) image = src->image;
+            else CUDA_TRY(cudaMalloc(&image, h.image_bytes ? h.image_bytes : 1));
+            for (uint64_t off = 0; off < h.image_bytes; off += kBroadcastPiece) {
+                const uint64_t nb = std::min(kBroadcastPiece, h.image_bytes - off);
+                NCCL_TRY(N.Broadcast((uint8_t *)image + off, (uint8_t *)image + off, nb, Nccl::kUint8, root, comm, stream));
+            }
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            return GDX_OK;
+        }();
+        if (d_hdr) cudaFree(d_hdr);
+        if (stream) cudaStreamDestroy(stream);
+        N.CommDestroy(comm);
         if (st != GDX_OK) {
-            cudaFree(img);
+            if (rank != root && image) cudaFree(image);
             return st;
         }
-    }
-    return GDX_OK;
+        t_transport = "nccl";
+        if (rank == root) {
+            *out = const_cast<gdx_index *>(src);
+            return GDX_OK;
+        }
+        st = gdx_index_adopt_image(&h, image, device, 1, out);
+        if (st != GDX_OK) cudaFree(image);
+        return st;
+    });
 }
 
 // ================================================================================================
@@ -1389,20 +1656,27 @@ bool verify_enabled() {
     return on;
 }
 
-// mode 0: cursors (starts, ends); 1: counts; 2: locate intervals (interval or resolved hit)
+// mode 0: cursors (starts, ends); 1: counts; 2: locate intervals (interval or resolved hit);
+// narrow: results are written as uint32 (modes 0 and 1, texts shorter than 2^32)
 template <class L>
-void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint64_t *b, int mode,
+void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint64_t *b, int mode, bool narrow,
                    uint64_t qbase, uint64_t *err, unsigned long long *steps, const uint32_t *perm,
-                   cudaStream_t stream) {
+                   const uint32_t *slot_map, cudaStream_t stream) {
     if (dq.nq == 0) return;
     const unsigned grid = (unsigned)div_up(dq.nq, 256);
     const bool verify = idx->dev.text && verify_enabled();
-    if (verify && mode != 0)
-        k_search<L, true, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
-    else if (verify && idx->dev.isa)
-        k_search<L, true, true><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
-    else
-        k_search<L, false, false><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mode, qbase, err, steps, perm);
+    const int mf = mode | (narrow ? kModeNarrow : 0);
+#define GDX_LAUNCH(V, C, P) k_search<L, V, C, P><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mf, qbase, err, steps, perm, slot_map)
+    if (dq.packed) {
+        if (verify && mode != 0) GDX_LAUNCH(true, false, true);
+        else if (verify && idx->dev.isa) GDX_LAUNCH(true, true, true);
+        else GDX_LAUNCH(false, false, true);
+    } else {
+        if (verify && mode != 0) GDX_LAUNCH(true, false, false);
+        else if (verify && idx->dev.isa) GDX_LAUNCH(true, true, false);
+        else GDX_LAUNCH(false, false, false);
+    }
+#undef GDX_LAUNCH
 }
 
 // ---- suffix sort of a query batch (locality of the first search steps, see k_query_keys) -------------
@@ -1495,17 +1769,38 @@ gdx_status sort_queries(const gdx_index *idx, const DevQueries &dq, const SortPl
     return GDX_OK;
 }
 
-gdx_status check_queries(const gdx_queries *q) {
+gdx_status check_queries(const gdx_index *idx, const gdx_queries *q) {
     if (!q) return fail(GDX_ERR_BAD_ARG, "queries is NULL");
     if (q->offsets && q->nq && q->offsets[q->nq] < q->offsets[0])
         return fail(GDX_ERR_BAD_ARG, "queries->offsets must be non-decreasing");
     if (q->nq && !q->offsets && q->fixed_len && !q->bytes) return fail(GDX_ERR_BAD_ARG, "queries->bytes is NULL");
+    if (q->encoding > GDX_QUERIES_PACKED_2BIT) return fail(GDX_ERR_BAD_ARG, "unknown queries->encoding %u", q->encoding);
+    if (q->encoding == GDX_QUERIES_PACKED_2BIT && idx && idx->h.ns > 4)
+        return fail(GDX_ERR_UNSUPPORTED, "2-bit packed queries need an alphabet with at most 4 searchable symbols (this one has %u)",
+                    idx->h.ns);
     return GDX_OK;
 }
 
+// index of the first symbol of query i in the batch's symbol stream (IO bytes or 2-bit codes)
 uint64_t query_bytes_end(const gdx_queries *q, uint64_t i) {
-    return q->offsets ? q->offsets[i] : i * q->fixed_len;
+    return q->offsets ? q->offsets[i] : i * q->fixed_len + q->first_symbol;
 }
+
+bool env_flag(const char *name, bool dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) != 0 : dflt;
+}
+// host-side 2-bit packing of large IO-byte batches (GDX_PACK_QUERIES=0 switches it off for A/B runs)
+bool pack_enabled() {
+    static const bool on = env_flag("GDX_PACK_QUERIES", true);
+    return on;
+}
+// results of large batches cross PCIe as uint32 when the text is shorter than 2^32 (GDX_NARROW_RESULTS=0: off)
+bool narrow_enabled() {
+    static const bool on = env_flag("GDX_NARROW_RESULTS", true);
+    return on;
+}
+const uint64_t kPackMinBytes = env_bytes("GDX_PACK_MIN_BYTES", 1ull << 20);
 
 gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out, uint64_t *cap_out);
 void release_pinned_hits(const gdx_index *idx, void *p);
@@ -1596,6 +1891,8 @@ struct LocatePipe {
             CUDA_TRY(sl.rows.reserve(n_hits * 8));
             CUDA_TRY(sl.hits.reserve(n_hits * 16));
             CUDA_TRY(sl.big.reserve((nbig + 1) * 8));
+            cudaEvent_t ev_begin = ws->next_locate_event(sl), ev_end = ws->next_locate_event(sl);
+            CUDA_TRY(cudaEventRecord(ev_begin, sl.stream));
             k_expand_rows<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(
                 sl.out_a.as<uint64_t>(), sl.out_b.as<uint64_t>(), sl.local_off.as<uint64_t>(), cq,
                 sl.rows.as<uint64_t>(), sl.big.as<uint64_t>(), reinterpret_cast<unsigned long long *>(sl.d_words + 1));
@@ -1605,15 +1902,17 @@ struct LocatePipe {
                                                                sl.local_off.as<uint64_t>(), sl.big.as<uint64_t>(),
                                                                sl.rows.as<uint64_t>());
             }
-            unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 5);
+            unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 10);
             GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
                 k_locate_walk<decltype(L)><<<(unsigned)div_up(n_hits, 256), 256, 0, sl.stream>>>(
                     idx->dev, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk);
                 return GDX_OK;
             }));
             CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(ev_end, sl.stream));
             CUDA_TRY(cudaMemcpyAsync((gdx_hit *)pinned + base, sl.hits.p, n_hits * sizeof(gdx_hit),
                                      cudaMemcpyDeviceToHost, sl.stream));
+            t_stats.d2h_bytes += n_hits * sizeof(gdx_hit);
             t_stats.kernel_launches += 2 + (nbig ? 1 : 0);
         }
         k_add_base<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.local_off.as<uint64_t>(), cq, base);
@@ -1627,37 +1926,56 @@ struct LocatePipe {
         } else {
             CUDA_TRY(cudaMemcpyAsync(hit_offsets + q0, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
+        t_stats.d2h_bytes += cq * 8;
         t_stats.kernel_launches += 1;
         total += n_hits;
         return GDX_OK;
     }
 };
 
-// Chunked pipeline over kSlots streams: H2D(query bytes) -> k_search -> D2H(results) per chunk.
+// Chunked pipeline over kSlots streams: stage / pack -> H2D(queries) -> k_search -> D2H(results) per chunk.
 // If dev_a/dev_b are given the results stay on the device (locate path) and nothing is copied back.
-gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *qs, uint64_t *out_a,
-                       uint64_t *out_b, int mode, uint64_t *dev_a, uint64_t *dev_b, LocatePipe *lp = nullptr) {
+// out_elem: bytes per element of the caller's result arrays (8, or 4 for the *_u32 entry points).
+gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *qs, void *out_a_v, void *out_b_v,
+                       uint32_t out_elem, int mode, uint64_t *dev_a, uint64_t *dev_b, LocatePipe *lp = nullptr) {
     const uint64_t nq = qs->nq;
-    for (int s = 0; s < kSlots; ++s) ws->slot[s].ev_used = 0;
-    CUDA_TRY(cudaMemset(ws->small.d, 0xff, 4 * sizeof(uint64_t)));
-    CUDA_TRY(cudaMemset(ws->small.d + 4, 0, 12 * sizeof(uint64_t)));
+    uint8_t *out_a = (uint8_t *)out_a_v, *out_b = (uint8_t *)out_b_v;
+    for (int s = 0; s < kSlots; ++s) ws->slot[s].ev_used = ws->slot[s].ev_loc_used = 0;
+    // error words / counters are reset on slot 0's stream; the other slot streams (non-blocking: no implicit
+    // ordering with anything) wait for that before their first kernel
+    CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 4 * sizeof(uint64_t), ws->slot[0].stream));
+    CUDA_TRY(cudaMemsetAsync(ws->small.d + 4, 0, 12 * sizeof(uint64_t), ws->slot[0].stream));
+    CUDA_TRY(cudaEventRecord(ws->ev_a, ws->slot[0].stream));
+    for (int s = 1; s < kSlots; ++s) CUDA_TRY(cudaStreamWaitEvent(ws->slot[s].stream, ws->ev_a, 0));
     unsigned long long *d_steps = reinterpret_cast<unsigned long long *>(ws->small.d + 4);
     static const bool trace = getenv("GDX_TRACE") && atoi(getenv("GDX_TRACE")) != 0;
     struct TraceRow {
         int k;
         uint64_t nq, bytes;
         cudaEvent_t h2d_begin, k_begin, k_end, d2h_end;
+        double host_stage_ms;
     };
     std::vector<TraceRow> trace_rows;
     const auto t_host0 = std::chrono::steady_clock::now();
-    const uint64_t byte_end = query_bytes_end(qs, nq);
+    const uint64_t sym_end = query_bytes_end(qs, nq);
+    const uint64_t total_syms = sym_end - query_bytes_end(qs, 0);
+    const bool prepacked = qs->encoding == GDX_QUERIES_PACKED_2BIT;
+    const uint64_t total_in = prepacked ? (total_syms + 3) / 4 : total_syms;
     // Ordinary (pageable) caller memory would make every cudaMemcpyAsync a blocking, driver-staged copy at
-    // 8-14 GB/s.  Large batches are staged through the slots' own pinned buffers instead, copied by a few
-    // host threads (HostPool); pinned caller buffers take the direct path.
-    const uint64_t total_in = byte_end - query_bytes_end(qs, 0);
+    // 8-14 GB/s.  Large batches are staged through the slots' own pinned buffers instead, filled by the host
+    // thread pool; while they are staged, IO bytes of a <= 4-symbol alphabet are packed to 2 bits (a quarter
+    // of the PCIe bytes) -- that pays for pinned caller buffers too.
+    bool pack_on = nq && !prepacked && idx->pack.usable && pack_enabled() && total_in >= kPackMinBytes;
     const bool stage_in = nq && total_in >= kStageMinBytes && !is_pinned(qs->bytes);
     const bool stage_off = nq && qs->offsets && nq * 8 >= kStageMinBytes && !is_pinned(qs->offsets);
-    const bool stage_out = nq && !dev_a && !lp && nq * 8 >= kStageMinBytes && !is_pinned(out_a);
+    const bool to_host = nq && !dev_a && !lp;
+    const bool large_out = nq * 8 >= kStageMinBytes;
+    // results as uint32 on the device: always for the u32 entry points, for large batches of the u64 ones
+    // (widened by the pool while they are handed to the caller)
+    const bool narrow = to_host && !idx->h.wide && (out_elem == 4 || (large_out && narrow_enabled()));
+    const bool widen = narrow && out_elem == 8;
+    const bool stage_out = to_host && (widen || (large_out && !is_pinned(out_a)));
+    const uint32_t dev_elem = narrow ? 4 : 8;
     struct PendingOut {
         int slot = 0;
         uint64_t q0 = 0, cq = 0;
@@ -1668,24 +1986,34 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         p.valid = false;
         Slot &ps = ws->slot[p.slot];
         CUDA_TRY(cudaEventSynchronize(ps.ev_out));
-        HostPool::get().copy(out_a + p.q0, ps.h_out_a.p, p.cq * 8);
-        if (mode == 0) HostPool::get().copy(out_b + p.q0, ps.h_out_b.p, p.cq * 8);
+        if (widen) {
+            HostPool::get().widen_u32((uint64_t *)out_a + p.q0, (const uint32_t *)ps.h_out_a.p, p.cq);
+            if (mode == 0) HostPool::get().widen_u32((uint64_t *)out_b + p.q0, (const uint32_t *)ps.h_out_b.p, p.cq);
+        } else {
+            HostPool::get().copy(out_a + p.q0 * out_elem, ps.h_out_a.p, p.cq * out_elem);
+            if (mode == 0) HostPool::get().copy(out_b + p.q0 * out_elem, ps.h_out_b.p, p.cq * out_elem);
+        }
         return GDX_OK;
     };
     for (int s2 = 0; s2 < kSlots; ++s2) ws->slot[s2].h2d_pending = false;
+    std::vector<uint64_t> exc;       // symbol positions (chunk relative) the packer could not encode
+    std::vector<uint32_t> exc_q;     // the queries (chunk relative) that hold them
+    uint64_t packed_queries = 0, exception_queries = 0, h2d_bytes = 0, d2h_bytes = 0;
     uint64_t budget = kChunkFirst;
     uint64_t q0 = 0;
     int k = 0;
     while (q0 < nq) {
-        // chunk [q0, q1): about `budget` query bytes, at least one query
-        const uint64_t remaining = byte_end - query_bytes_end(qs, q0);
-        uint64_t want = budget;
-        if (remaining <= budget) want = remaining > 2 * kChunkTail ? remaining - kChunkTail : remaining;
+        // chunk [q0, q1): about `budget` input bytes (packed bytes count four-fold: the budget is PCIe time),
+        // at least one query
+        const uint64_t unit = (pack_on || prepacked) ? 4 : 1;
+        const uint64_t remaining = sym_end - query_bytes_end(qs, q0);
+        uint64_t want = budget * unit;
+        if (remaining <= want) want = remaining > 2 * kChunkTail * unit ? remaining - kChunkTail * unit : remaining;
         uint64_t q1;
         if (qs->offsets) {
-            const uint64_t *b = qs->offsets + q0 + 1, *e = qs->offsets + nq + 1;
-            const uint64_t *it = std::upper_bound(b, e, qs->offsets[q0] + want);
-            q1 = q0 + (uint64_t)(it - b);
+            const uint64_t *ob = qs->offsets + q0 + 1, *oe = qs->offsets + nq + 1;
+            const uint64_t *it = std::upper_bound(ob, oe, qs->offsets[q0] + want);
+            q1 = q0 + (uint64_t)(it - ob);
             if (q1 == q0) q1 = q0 + 1;
         } else {
             q1 = q0 + (qs->fixed_len ? std::max<uint64_t>(1, want / qs->fixed_len) : kChunkMaxQueries);
@@ -1693,51 +2021,160 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         q1 = std::min<uint64_t>(q1, std::min<uint64_t>(nq, q0 + kChunkMaxQueries));
         budget = std::min<uint64_t>(budget * 2, kChunkMax);
         const uint64_t cq = q1 - q0;
-        const uint64_t byte0 = query_bytes_end(qs, q0), byte1 = query_bytes_end(qs, q1);
+        const uint64_t sym0 = query_bytes_end(qs, q0), sym1 = query_bytes_end(qs, q1), nsym = sym1 - sym0;
         Slot &sl = ws->slot[k % kSlots];
-        // growing a slot buffer frees the old one: only safe once the slot's stream has drained
         const SortPlan sp = plan_sort(idx, cq, qs->offsets ? 0 : qs->fixed_len);
-        if (sl.bytes.cap < byte1 - byte0 + 16 || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
+        // growing a slot buffer frees the old one: only safe once the slot's stream has drained
+        const uint64_t in_cap = nsym + 64;  // enough for either representation of the chunk
+        if (sl.bytes.cap < in_cap || (qs->offsets && sl.offsets.cap < (cq + 1) * 8) ||
             (!dev_a && (sl.out_a.cap < cq * 8 || ((mode == 0 || lp) && sl.out_b.cap < cq * 8))) ||
             (sp.use && sl.sort.cap < sp.total_bytes))
             CUDA_TRY(cudaStreamSynchronize(sl.stream));
-        CUDA_TRY(sl.bytes.reserve(byte1 - byte0 + 16));
+        CUDA_TRY(sl.bytes.reserve(in_cap));
         cudaEvent_t ev_h2d = nullptr;
         if (trace) {
             cudaEventCreate(&ev_h2d);
             cudaEventRecord(ev_h2d, sl.stream);
         }
-        if ((stage_in || stage_off) && sl.h2d_pending) {  // the slot's staging buffers are free again
+        if (sl.h2d_pending) {  // the slot's staging buffers are free again once their last upload is done
             CUDA_TRY(cudaEventSynchronize(sl.ev_h2d));
             sl.h2d_pending = false;
         }
-        if (byte1 > byte0) {
-            const uint8_t *src = qs->bytes + byte0;
-            if (stage_in) {
-                CUDA_TRY(sl.h_in.reserve(byte1 - byte0));
-                HostPool::get().copy(sl.h_in.p, src, byte1 - byte0);
-                src = (const uint8_t *)sl.h_in.p;
-            }
-            CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, src, byte1 - byte0, cudaMemcpyHostToDevice, sl.stream));
-        }
+        const auto t_stage0 = std::chrono::steady_clock::now();
         DevQueries dq;
         dq.bytes = sl.bytes.as<uint8_t>();
+        dq.packed = nullptr;
         dq.offsets = nullptr;
+        dq.offsets32 = nullptr;
         dq.fixed_len = qs->fixed_len;
         dq.nq = cq;
         dq.base = 0;
-        if (qs->offsets) {
+        dq.shift = 0;
+        // large variable-length batches: offsets cross PCIe chunk relative as uint32
+        const bool narrow_off = qs->offsets && nq * 8 >= kStageMinBytes && nsym + 4 < 0xffffffffull && narrow_enabled();
+        bool used_staging = false;
+        uint64_t nx = 0;  // queries of this chunk that go through the IO-byte kernel after the packed one
+        bool chunk_packed = false;
+        if (nsym && pack_on) {
+            CUDA_TRY(sl.h_in.reserve((nsym + 3) / 4 + 8));
+            pack2_parallel(idx->pack, qs->bytes + sym0, nsym, (uint8_t *)sl.h_in.p, exc);
+            exc_q.clear();
+            for (uint64_t pos : exc) {
+                uint64_t q;
+                if (qs->offsets) {
+                    const uint64_t *ob = qs->offsets + q0, *oe = qs->offsets + q1 + 1;
+                    q = (uint64_t)(std::upper_bound(ob, oe, sym0 + pos) - ob) - 1;
+                } else {
+                    q = pos / qs->fixed_len;
+                }
+                if (exc_q.empty() || exc_q.back() != (uint32_t)q) exc_q.push_back((uint32_t)q);
+            }
+            if (exc_q.size() * 8 > cq) {
+                // this is not a batch of plain searchable symbols: IO bytes from here on
+                pack_on = false;
+            } else {
+                chunk_packed = true;
+                nx = exc_q.size();
+                CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, sl.h_in.p, (nsym + 3) / 4, cudaMemcpyHostToDevice, sl.stream));
+                h2d_bytes += (nsym + 3) / 4;
+                dq.bytes = nullptr;
+                dq.packed = sl.bytes.as<uint32_t>();
+                used_staging = true;
+            }
+        }
+        if (nsym && !chunk_packed) {
+            if (prepacked) {  // the caller's stream, from the byte that holds the chunk's first symbol
+                const uint64_t b0 = sym0 / 4, b1 = (sym1 + 3) / 4;
+                const uint8_t *src = qs->bytes + b0;
+                if (stage_in) {
+                    CUDA_TRY(sl.h_in.reserve(b1 - b0));
+                    HostPool::get().copy(sl.h_in.p, src, b1 - b0);
+                    src = (const uint8_t *)sl.h_in.p;
+                    used_staging = true;
+                }
+                CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, src, b1 - b0, cudaMemcpyHostToDevice, sl.stream));
+                h2d_bytes += b1 - b0;
+                dq.bytes = nullptr;
+                dq.packed = sl.bytes.as<uint32_t>();
+                dq.shift = sym0 & 3;
+            } else {
+                const uint8_t *src = qs->bytes + sym0;
+                if (stage_in) {
+                    CUDA_TRY(sl.h_in.reserve(nsym));
+                    HostPool::get().copy(sl.h_in.p, src, nsym);
+                    src = (const uint8_t *)sl.h_in.p;
+                    used_staging = true;
+                }
+                CUDA_TRY(cudaMemcpyAsync(sl.bytes.p, src, nsym, cudaMemcpyHostToDevice, sl.stream));
+                h2d_bytes += nsym;
+            }
+        } else if (!nsym && prepacked) {
+            dq.bytes = nullptr;
+            dq.packed = sl.bytes.as<uint32_t>();
+        }
+        if (qs->offsets && narrow_off) {
+            // chunk-relative 32-bit offsets, narrowed by the pool into pinned staging: half the PCIe bytes
+            CUDA_TRY(sl.offsets.reserve((cq + 1) * 8));
+            CUDA_TRY(sl.h_off.reserve((cq + 1) * 4));
+            const uint64_t *osrc = qs->offsets + q0;
+            uint32_t *o32 = (uint32_t *)sl.h_off.p;
+            const uint64_t rel = sym0 - dq.shift, cnt = cq + 1;
+            constexpr uint64_t kPiece = 1ull << 18;
+            HostPool::get().parallel_for(div_up(cnt, kPiece), [&](uint64_t piece) {
+                const uint64_t lo = piece * kPiece, hi = std::min(cnt, lo + kPiece);
+                for (uint64_t i = lo; i < hi; ++i) o32[i] = (uint32_t)(osrc[i] - rel);
+            });
+            used_staging = true;
+            CUDA_TRY(cudaMemcpyAsync(sl.offsets.p, o32, cnt * 4, cudaMemcpyHostToDevice, sl.stream));
+            h2d_bytes += cnt * 4;
+            dq.offsets32 = sl.offsets.as<uint32_t>();
+            dq.shift = 0;
+        } else if (qs->offsets) {
             CUDA_TRY(sl.offsets.reserve((cq + 1) * 8));
             const uint64_t *osrc = qs->offsets + q0;
             if (stage_off) {
                 CUDA_TRY(sl.h_off.reserve((cq + 1) * 8));
                 HostPool::get().copy(sl.h_off.p, osrc, (cq + 1) * 8);
                 osrc = (const uint64_t *)sl.h_off.p;
+                used_staging = true;
             }
             CUDA_TRY(cudaMemcpyAsync(sl.offsets.p, osrc, (cq + 1) * 8, cudaMemcpyHostToDevice, sl.stream));
+            h2d_bytes += (cq + 1) * 8;
             dq.offsets = sl.offsets.as<uint64_t>();
-            dq.base = byte0;
+            dq.base = sym0 - dq.shift;
+            dq.shift = 0;
         }
+        // queries with an exception byte: their offsets, result slots and IO bytes in one upload
+        DevQueries xq = {};
+        const uint32_t *x_slots = nullptr;
+        if (nx) {
+            uint64_t xbytes = 0;
+            for (uint32_t q : exc_q) xbytes += query_bytes_end(qs, q0 + q + 1) - query_bytes_end(qs, q0 + q);
+            const uint64_t off_slots = (nx + 1) * 8, off_bytes = align_up(off_slots + nx * 4, 8), tot = off_bytes + xbytes + 8;
+            if (sl.xbuf.cap < tot) CUDA_TRY(cudaStreamSynchronize(sl.stream));
+            CUDA_TRY(sl.xbuf.reserve(tot));
+            CUDA_TRY(sl.h_x.reserve(tot));
+            uint64_t *xo = (uint64_t *)sl.h_x.p;
+            uint32_t *xs = (uint32_t *)((uint8_t *)sl.h_x.p + off_slots);
+            uint8_t *xb = (uint8_t *)sl.h_x.p + off_bytes;
+            uint64_t acc = 0;
+            for (uint64_t i = 0; i < nx; ++i) {
+                const uint64_t b0 = query_bytes_end(qs, q0 + exc_q[i]), b1 = query_bytes_end(qs, q0 + exc_q[i] + 1);
+                xo[i] = acc;
+                xs[i] = exc_q[i];
+                memcpy(xb + acc, qs->bytes + b0, b1 - b0);
+                acc += b1 - b0;
+            }
+            xo[nx] = acc;
+            CUDA_TRY(cudaMemcpyAsync(sl.xbuf.p, sl.h_x.p, off_bytes + xbytes, cudaMemcpyHostToDevice, sl.stream));
+            h2d_bytes += off_bytes + xbytes;
+            xq.bytes = sl.xbuf.as<uint8_t>() + off_bytes;
+            xq.offsets = sl.xbuf.as<uint64_t>();
+            xq.nq = nx;
+            x_slots = reinterpret_cast<const uint32_t *>(sl.xbuf.as<uint8_t>() + off_slots);
+            used_staging = true;
+        }
+        const double stage_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_stage0).count();
         uint64_t *a, *b;
         if (dev_a) {
             a = dev_a + q0;
@@ -1751,13 +2188,13 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
                 b = sl.out_b.as<uint64_t>();
             }
         }
-        if (stage_in || stage_off) {
+        if (used_staging) {
             CUDA_TRY(cudaEventRecord(sl.ev_h2d, sl.stream));
             sl.h2d_pending = true;
         }
         cudaEvent_t e0 = ws->next_event(sl), e1 = ws->next_event(sl);
         CUDA_TRY(cudaEventRecord(e0, sl.stream));
-        if (trace) trace_rows.push_back(TraceRow{k, cq, byte1 - byte0, ev_h2d, e0, e1, nullptr});
+        if (trace) trace_rows.push_back(TraceRow{k, cq, chunk_packed || prepacked ? (nsym + 3) / 4 : nsym, ev_h2d, e0, e1, nullptr, stage_ms});
         const uint32_t *perm = nullptr;
         if (sp.use) {
             CUDA_TRY(sl.sort.reserve(sp.total_bytes));
@@ -1765,36 +2202,44 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             t_stats.kernel_launches += 2;
         }
         gdx_status st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-            launch_search<decltype(L)>(idx, dq, a, b, mode, q0, ws->small.d + (k % kSlots), d_steps, perm, sl.stream);
+            launch_search<decltype(L)>(idx, dq, a, b, mode, narrow, q0, ws->small.d + (k % kSlots), d_steps, perm, nullptr,
+                                       sl.stream);
+            if (nx)  // overwrites the slots of the queries the packed kernel could not see correctly
+                launch_search<decltype(L)>(idx, xq, a, b, mode, narrow, q0, ws->small.d + (k % kSlots), d_steps, nullptr,
+                                           x_slots, sl.stream);
             return GDX_OK;
         });
         GDX_TRY(st);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(e1, sl.stream));
+        if (chunk_packed || prepacked) packed_queries += cq;
+        exception_queries += nx;
         if (lp) {  // locate continues per chunk; the previous chunk is finished while this one runs
             const LocatePipe::Pending prev = lp->take_pending();
             GDX_TRY(lp->stage_counts(sl, k % kSlots, q0, cq));
             GDX_TRY(lp->finish(prev));
         } else if (stage_out) {  // results go to pinned staging; the previous chunk's are handed over meanwhile
             PendingOut prev = pend_out;
-            CUDA_TRY(sl.h_out_a.reserve(cq * 8));
-            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            CUDA_TRY(sl.h_out_a.reserve(cq * dev_elem));
+            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, a, cq * dev_elem, cudaMemcpyDeviceToHost, sl.stream));
             if (mode == 0) {
-                CUDA_TRY(sl.h_out_b.reserve(cq * 8));
-                CUDA_TRY(cudaMemcpyAsync(sl.h_out_b.p, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+                CUDA_TRY(sl.h_out_b.reserve(cq * dev_elem));
+                CUDA_TRY(cudaMemcpyAsync(sl.h_out_b.p, b, cq * dev_elem, cudaMemcpyDeviceToHost, sl.stream));
             }
             CUDA_TRY(cudaEventRecord(sl.ev_out, sl.stream));
             pend_out = PendingOut{k % kSlots, q0, cq, true};
+            d2h_bytes += cq * dev_elem * (mode == 0 ? 2 : 1);
             GDX_TRY(finish_out(prev));
         } else if (!dev_a) {
-            CUDA_TRY(cudaMemcpyAsync(out_a + q0, a, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
-            if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0, b, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            d2h_bytes += cq * out_elem * (mode == 0 ? 2 : 1);
+            CUDA_TRY(cudaMemcpyAsync(out_a + q0 * out_elem, a, cq * out_elem, cudaMemcpyDeviceToHost, sl.stream));
+            if (mode == 0) CUDA_TRY(cudaMemcpyAsync(out_b + q0 * out_elem, b, cq * out_elem, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (trace) {
             cudaEventCreate(&trace_rows.back().d2h_end);
             cudaEventRecord(trace_rows.back().d2h_end, sl.stream);
         }
-        t_stats.kernel_launches += 1;
+        t_stats.kernel_launches += 1 + (nx ? 1 : 0);
         q0 = q1;
         ++k;
     }
@@ -1805,7 +2250,8 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     for (int s = 0; s < kSlots; ++s) CUDA_TRY(cudaStreamSynchronize(ws->slot[s].stream));
     if (trace && !trace_rows.empty()) {
         const double t_sync = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
-        fprintf(stderr, "[gdx trace] host: all chunks issued at %.3f ms, streams drained at %.3f ms\n", t_issue, t_sync);
+        fprintf(stderr, "[gdx trace] host: all chunks issued at %.3f ms, streams drained at %.3f ms (%u pool threads)\n", t_issue,
+                t_sync, HostPool::get().threads());
         cudaEvent_t base = trace_rows[0].h2d_begin;
         for (auto &r : trace_rows) {
             float a = 0, b = 0, c = 0, d = 0;
@@ -1814,8 +2260,8 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             cudaEventElapsedTime(&b, base, r.k_begin);
             cudaEventElapsedTime(&c, base, r.k_end);
             cudaEventElapsedTime(&d, base, r.d2h_end);
-            fprintf(stderr, "[gdx trace] chunk %2d slot %d nq %8llu bytes %10llu | h2d %.3f..%.3f | kernels %.3f..%.3f | d2h ..%.3f\n",
-                    r.k, r.k % kSlots, (unsigned long long)r.nq, (unsigned long long)r.bytes, a, b, b, c, d);
+            fprintf(stderr, "[gdx trace] chunk %2d slot %d nq %8llu h2d bytes %10llu host stage %.3f ms | h2d %.3f..%.3f | kernels %.3f..%.3f | d2h ..%.3f\n",
+                    r.k, r.k % kSlots, (unsigned long long)r.nq, (unsigned long long)r.bytes, r.host_stage_ms, a, b, b, c, d);
         }
         for (auto &r : trace_rows) {
             cudaEventDestroy(r.h2d_begin);
@@ -1823,18 +2269,30 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         }
     }
     CUDA_TRY(cudaMemcpy(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    double ms = 0;
-    for (int s = 0; s < kSlots; ++s)
+    double ms = 0, ms_loc = 0;
+    for (int s = 0; s < kSlots; ++s) {
         for (size_t i = 0; i + 1 < ws->slot[s].ev_used; i += 2) {
             float t = 0;
             cudaEventElapsedTime(&t, ws->slot[s].ev[i], ws->slot[s].ev[i + 1]);
             ms += t;
         }
+        for (size_t i = 0; i + 1 < ws->slot[s].ev_loc_used; i += 2) {
+            float t = 0;
+            cudaEventElapsedTime(&t, ws->slot[s].ev_loc[i], ws->slot[s].ev_loc[i + 1]);
+            ms_loc += t;
+        }
+    }
     t_stats.queries = nq;
     t_stats.lf_steps = ws->small.h[4];
-    t_stats.walk_steps = ws->small.h[5];
+    t_stats.walk_steps = ws->small.h[5] + ws->small.h[10];
+    t_stats.locate_walk_steps = ws->small.h[10];
     t_stats.verified_queries = ws->small.h[9];
     t_stats.kernel_ms_search = ms;
+    t_stats.kernel_ms_locate = ms_loc;
+    t_stats.packed_queries = packed_queries;
+    t_stats.exception_queries = exception_queries;
+    t_stats.h2d_bytes = h2d_bytes;
+    t_stats.d2h_bytes += d2h_bytes;
     uint64_t bad = kNoError;
     for (int s = 0; s < kSlots; ++s) bad = std::min(bad, ws->small.h[s]);
     if (bad != kNoError) {
@@ -1895,7 +2353,7 @@ gdx_status locate_device_intervals(const gdx_index *idx, Workspace *ws, const ui
                                                     ws->big_list.as<uint64_t>(), ws->rows.as<uint64_t>());
             t_stats.kernel_launches += 1;
         }
-        unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 5);
+        unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 10);
         gdx_status s2 = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
             k_locate_walk<decltype(L)><<<(unsigned)div_up(total, 256), 256, 0, st>>>(
                 idx->dev, ws->rows.as<uint64_t>(), total, ws->hits.as<ulonglong2>(), d_walk);
@@ -1947,19 +2405,20 @@ gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out,
 }
 
 gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64_t total, uint64_t *hit_offsets,
-                         gdx_hit **hits, uint64_t *num_hits) {
+                         gdx_hit **hits, uint64_t *num_hits, bool write_last = true) {
     cudaStream_t st = ws->slot[0].stream;
     void *h = nullptr;
     GDX_TRY(acquire_pinned_hits(idx, total * sizeof(gdx_hit), &h));
     if (total) CUDA_TRY(cudaMemcpyAsync(h, ws->hits.p, total * sizeof(gdx_hit), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(hit_offsets, ws->hit_offsets.p, (n + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hit_offsets, ws->hit_offsets.p, (n + (write_last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, ws->ev_a, ws->ev_b);
     t_stats.kernel_ms_locate = ms;
     t_stats.hits = total;
-    t_stats.walk_steps += ws->small.h[5];
+    t_stats.walk_steps += ws->small.h[10];
+    t_stats.locate_walk_steps = ws->small.h[10];
     *hits = (gdx_hit *)h;
     *num_hits = total;
     return GDX_OK;
@@ -1967,34 +2426,31 @@ gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64
 
 }  // namespace
 
-extern "C" gdx_status gdx_cursors_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *starts,
-                                       uint64_t *ends) {
-    GDX_TRY(begin_call(idx, "gdx_cursors_many"));
-    GDX_TRY(check_queries(queries));
-    if (queries->nq && (!starts || !ends)) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+namespace {
+
+// mode 0: cursors, 1: counts; elem: bytes per element of the caller's arrays
+gdx_status search_many_impl(const gdx_index *idx, const gdx_queries *queries, void *a, void *b, uint32_t elem, int mode,
+                            const char *what) {
+    GDX_TRY(begin_call(idx, what));
+    GDX_TRY(check_queries(idx, queries));
+    if (queries->nq && (!a || (mode == 0 && !b))) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+    if (elem == 4 && idx->h.wide) return fail(GDX_ERR_UNSUPPORTED, "32-bit results need a text shorter than 2^32 symbols");
+    std::shared_lock<std::shared_mutex> cfg(idx->cfg_mu);
     DeviceGuard guard(idx->device);
     WsLease lease(idx);
     if (!lease.w) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
-    return search_host(idx, lease.w, queries, starts, ends, 0, nullptr, nullptr);
+    return search_host(idx, lease.w, queries, a, b, elem, mode, nullptr, nullptr);
 }
 
-extern "C" gdx_status gdx_count_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *counts) {
-    GDX_TRY(begin_call(idx, "gdx_count_many"));
-    GDX_TRY(check_queries(queries));
-    if (queries->nq && !counts) return fail(GDX_ERR_BAD_ARG, "output is NULL");
-    DeviceGuard guard(idx->device);
-    WsLease lease(idx);
-    if (!lease.w) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
-    return search_host(idx, lease.w, queries, counts, nullptr, 1, nullptr, nullptr);
-}
-
-extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
-                                      gdx_hit **hits, uint64_t *num_hits) {
+// write_last = false: hit_offsets[nq] is left alone (it is the first entry of the next shard's range)
+gdx_status locate_many_impl(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets, gdx_hit **hits,
+                            uint64_t *num_hits, bool write_last = true) {
     GDX_TRY(begin_call(idx, "gdx_locate_many"));
-    GDX_TRY(check_queries(queries));
+    GDX_TRY(check_queries(idx, queries));
     if (!hit_offsets || !hits || !num_hits) return fail(GDX_ERR_BAD_ARG, "output is NULL");
     *hits = nullptr;
     *num_hits = 0;
+    std::shared_lock<std::shared_mutex> cfg(idx->cfg_mu);
     DeviceGuard guard(idx->device);
     WsLease lease(idx);
     Workspace *ws = lease.w;
@@ -2006,13 +2462,13 @@ extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *q
         LocatePipe lp{idx, ws, hit_offsets};
         lp.stage_offsets = n * 8 >= kStageMinBytes && !is_pinned(hit_offsets);
         GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * sizeof(gdx_hit), &lp.pinned, &lp.pinned_cap));
-        gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 2, nullptr, nullptr, &lp);
+        gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 8, 2, nullptr, nullptr, &lp);
         if (st != GDX_OK) {
             for (int s2 = 0; s2 < kSlots; ++s2) cudaStreamSynchronize(ws->slot[s2].stream);
             release_pinned_hits(idx, lp.pinned);
             return st;
         }
-        hit_offsets[n] = lp.total;
+        if (write_last) hit_offsets[n] = lp.total;
         t_stats.hits = lp.total;
         *hits = (gdx_hit *)lp.pinned;
         *num_hits = lp.total;
@@ -2021,10 +2477,249 @@ extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *q
     // a buffer may only be replaced once nothing in flight uses it: every call ends synchronized
     CUDA_TRY(ws->starts.reserve((n + 1) * 8));
     CUDA_TRY(ws->ends.reserve((n + 1) * 8));
-    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 2, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
+    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 8, 2, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
     uint64_t total = 0;
     GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
-    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits, write_last);
+}
+
+}  // namespace
+
+extern "C" gdx_status gdx_cursors_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *starts,
+                                       uint64_t *ends) {
+    return guarded([&] { return search_many_impl(idx, queries, starts, ends, 8, 0, "gdx_cursors_many"); });
+}
+extern "C" gdx_status gdx_cursors_many_u32(const gdx_index *idx, const gdx_queries *queries, uint32_t *starts,
+                                           uint32_t *ends) {
+    return guarded([&] { return search_many_impl(idx, queries, starts, ends, 4, 0, "gdx_cursors_many_u32"); });
+}
+extern "C" gdx_status gdx_count_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *counts) {
+    return guarded([&] { return search_many_impl(idx, queries, counts, nullptr, 8, 1, "gdx_count_many"); });
+}
+extern "C" gdx_status gdx_count_many_u32(const gdx_index *idx, const gdx_queries *queries, uint32_t *counts) {
+    return guarded([&] { return search_many_impl(idx, queries, counts, nullptr, 4, 1, "gdx_count_many_u32"); });
+}
+extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
+                                      gdx_hit **hits, uint64_t *num_hits) {
+    return guarded([&] { return locate_many_impl(idx, queries, hit_offsets, hits, num_hits); });
+}
+
+extern "C" uint64_t gdx_packed_bytes(uint64_t total_symbols) { return align_up((total_symbols + 3) / 4, 4); }
+
+extern "C" gdx_status gdx_pack_queries(const gdx_index *idx, const gdx_queries *q, uint8_t *packed_out,
+                                       uint64_t *first_unencodable) {
+    return guarded([&]() -> gdx_status {
+        if (!idx || !packed_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        GDX_TRY(check_queries(idx, q));
+        if (q->encoding != GDX_QUERIES_IO_BYTES) return fail(GDX_ERR_BAD_ARG, "the batch is already packed");
+        if (!idx->pack.usable)
+            return fail(GDX_ERR_UNSUPPORTED, "2-bit packing needs an alphabet with at most 4 searchable symbols (this one has %u)",
+                        idx->h.ns);
+        const uint64_t s0 = query_bytes_end(q, 0), s1 = query_bytes_end(q, q->nq);
+        // symbols in front of the first query keep their place in the stream so that offsets stay valid
+        const uint64_t nbytes = gdx_packed_bytes(s1);
+        std::vector<uint64_t> exc;
+        if (s0) memset(packed_out, 0, (s0 + 3) / 4);
+        // the packer writes whole bytes: start on the byte that holds symbol s0 (codes before it belong to no query)
+        const uint64_t a0 = s0 & ~3ull;
+        pack2_parallel(idx->pack, q->bytes + a0, s1 - a0, packed_out + a0 / 4, exc);
+        for (uint64_t i = (s1 + 3) / 4; i < nbytes; ++i) packed_out[i] = 0;
+        uint64_t first = ~0ull;
+        for (uint64_t pos : exc) {
+            const uint64_t sym = a0 + pos;
+            if (sym < s0) continue;
+            first = q->offsets ? (uint64_t)(std::upper_bound(q->offsets, q->offsets + q->nq + 1, sym) - q->offsets) - 1
+                               : (sym - q->first_symbol) / q->fixed_len;
+            break;
+        }
+        if (first_unencodable) *first_unencodable = first;
+        return GDX_OK;
+    });
+}
+
+extern "C" gdx_status gdx_pack_symbols(const gdx_alphabet *alphabet, const uint8_t *io_bytes, uint64_t n,
+                                       uint8_t *packed_out, uint64_t *exception_positions, uint64_t capacity,
+                                       uint64_t *num_exceptions) {
+    return guarded([&]() -> gdx_status {
+        if (!alphabet || (n && (!io_bytes || !packed_out))) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        GDX_TRY(validate_alphabet(*alphabet));
+        PackTable t;
+        build_pack_table(alphabet->io_to_dense, alphabet->num_searchable_dense_symbols, t);
+        if (!t.usable) return fail(GDX_ERR_UNSUPPORTED, "2-bit packing needs an alphabet with at most 4 searchable symbols");
+        std::vector<uint64_t> exc;
+        pack2_parallel(t, io_bytes, n, packed_out, exc);
+        if (num_exceptions) *num_exceptions = exc.size();
+        for (uint64_t i = 0; i < exc.size() && i < capacity && exception_positions; ++i) exception_positions[i] = exc[i];
+        return GDX_OK;
+    });
+}
+
+// ================================================================================================
+// one batch over several replicas
+// ================================================================================================
+extern "C" void gdx_shard_range(uint64_t n_items, uint32_t shard, uint32_t n_shards, uint64_t *begin, uint64_t *end) {
+    // contiguous, balanced, order-preserving: the first n_items % n_shards shards get one item more
+    if (n_shards == 0) n_shards = 1;
+    if (shard > n_shards) shard = n_shards;
+    const uint64_t base = n_items / n_shards, rem = n_items % n_shards;
+    const uint64_t b = (uint64_t)shard * base + std::min<uint64_t>(shard, rem);
+    if (begin) *begin = b;
+    if (end) *end = shard >= n_shards ? b : b + base + (shard < rem ? 1 : 0);
+}
+
+namespace {
+
+// the queries [b, e) of a batch as a batch of their own
+gdx_queries sub_batch(const gdx_queries &q, uint64_t b, uint64_t e) {
+    gdx_queries s = q;
+    s.nq = e - b;
+    if (q.offsets) {
+        s.offsets = q.offsets + b;  // absolute stream positions: the symbol pointer stays
+    } else {
+        const uint64_t sym = (uint64_t)q.first_symbol + b * q.fixed_len;
+        if (q.encoding == GDX_QUERIES_PACKED_2BIT) {
+            s.bytes = q.bytes + sym / 4;
+            s.first_symbol = (uint32_t)(sym & 3);
+        } else {
+            s.bytes = q.bytes + sym;
+            s.first_symbol = 0;
+        }
+    }
+    return s;
+}
+
+struct ShardResult {
+    gdx_status st = GDX_OK;
+    std::string error;
+    uint64_t error_query = 0;
+    gdx_stats stats = {};
+};
+
+// runs work(k, begin, end) for every local shard on its own host thread (shard 0 on the caller's) and merges
+// status, error text and statistics into the caller's thread-local state
+template <class F>
+gdx_status run_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard, uint32_t n_shards,
+                       const gdx_queries *queries, F &&work) {
+    if (!replicas || n_local == 0 || n_shards == 0 || first_shard + n_local > n_shards)
+        return fail(GDX_ERR_BAD_ARG, "bad shard arguments (n_local %u, first_shard %u, n_shards %u)", n_local, first_shard, n_shards);
+    for (uint32_t k = 0; k < n_local; ++k) {
+        if (!replicas[k]) return fail(GDX_ERR_BAD_ARG, "replica %u is NULL", k);
+        const ImageHeader &h0 = replicas[0]->h, &hk = replicas[k]->h;
+        if (hk.n != h0.n || hk.sigma != h0.sigma || hk.ns != h0.ns || hk.sampling_rate != h0.sampling_rate ||
+            hk.lookup_depth != h0.lookup_depth || hk.ntexts != h0.ntexts)
+            return fail(GDX_ERR_BAD_ARG, "replica %u is not a replica of replica 0", k);
+    }
+    GDX_TRY(check_queries(replicas[0], queries));
+    std::vector<ShardResult> res(n_local);
+    auto run = [&](uint32_t k) {
+        uint64_t b = 0, e = 0;
+        gdx_shard_range(queries->nq, first_shard + k, n_shards, &b, &e);
+        ShardResult &r = res[k];
+        r.st = guarded([&] { return work(k, b, e); });
+        if (r.st != GDX_OK) {
+            r.error = t_error;
+            r.error_query = b + t_error_query;
+        }
+        r.stats = t_stats;
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t k = 1; k < n_local; ++k) threads.emplace_back(run, k);
+    run(0);
+    for (auto &t : threads) t.join();
+    gdx_stats sum = {};
+    gdx_status st = GDX_OK;
+    for (uint32_t k = 0; k < n_local; ++k) {
+        const gdx_stats &x = res[k].stats;
+        sum.queries += x.queries;
+        sum.lf_steps += x.lf_steps;
+        sum.hits += x.hits;
+        sum.walk_steps += x.walk_steps;
+        sum.locate_walk_steps += x.locate_walk_steps;
+        sum.kernel_launches += x.kernel_launches;
+        sum.verified_queries += x.verified_queries;
+        sum.packed_queries += x.packed_queries;
+        sum.exception_queries += x.exception_queries;
+        sum.h2d_bytes += x.h2d_bytes;
+        sum.d2h_bytes += x.d2h_bytes;
+        sum.kernel_ms_search = std::max(sum.kernel_ms_search, x.kernel_ms_search);  // the shards run side by side
+        sum.kernel_ms_locate = std::max(sum.kernel_ms_locate, x.kernel_ms_locate);
+        if (st == GDX_OK && res[k].st != GDX_OK) {  // the error of the lowest failing shard = the first offending query
+            st = res[k].st;
+            t_error = res[k].error;
+            t_error_query = res[k].error_query;
+        }
+    }
+    sum.shards = n_local;
+    t_stats = sum;
+    return st;
+}
+
+}  // namespace
+
+extern "C" gdx_status gdx_count_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                             uint32_t n_shards, const gdx_queries *queries, uint64_t *counts) {
+    return guarded([&] {
+        return run_sharded(replicas, n_local, first_shard, n_shards, queries, [&](uint32_t k, uint64_t b, uint64_t e) {
+            const gdx_queries sub = sub_batch(*queries, b, e);
+            return search_many_impl(replicas[k], &sub, counts ? counts + b : nullptr, nullptr, 8, 1, "gdx_count_many_sharded");
+        });
+    });
+}
+
+extern "C" gdx_status gdx_cursors_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                               uint32_t n_shards, const gdx_queries *queries, uint64_t *starts,
+                                               uint64_t *ends) {
+    return guarded([&] {
+        return run_sharded(replicas, n_local, first_shard, n_shards, queries, [&](uint32_t k, uint64_t b, uint64_t e) {
+            const gdx_queries sub = sub_batch(*queries, b, e);
+            return search_many_impl(replicas[k], &sub, starts ? starts + b : nullptr, ends ? ends + b : nullptr, 8, 0,
+                                    "gdx_cursors_many_sharded");
+        });
+    });
+}
+
+extern "C" gdx_status gdx_locate_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                              uint32_t n_shards, const gdx_queries *queries, uint64_t *hit_offsets,
+                                              gdx_hit **shard_hits, uint64_t *shard_first_hit) {
+    return guarded([&]() -> gdx_status {
+        if (!hit_offsets || !shard_hits || !shard_first_hit) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+        for (uint32_t k = 0; k < n_local; ++k) shard_hits[k] = nullptr;
+        std::vector<uint64_t> n_hits(n_local, 0), begins(n_local, 0), ends(n_local, 0);
+        // every shard writes its own CSR offsets (starting at 0) into its range of hit_offsets -- not the entry one
+        // past the range, which is the next shard's first; the ranges are rebased below
+        gdx_status st = run_sharded(replicas, n_local, first_shard, n_shards, queries, [&](uint32_t k, uint64_t b, uint64_t e) {
+            const gdx_queries sub = sub_batch(*queries, b, e);
+            begins[k] = b;
+            ends[k] = e;
+            return locate_many_impl(replicas[k], &sub, hit_offsets + b, &shard_hits[k], &n_hits[k], false);
+        });
+        if (st != GDX_OK) {
+            for (uint32_t k = 0; k < n_local; ++k)
+                if (shard_hits[k]) {
+                    gdx_free_hits(replicas[k], shard_hits[k]);
+                    shard_hits[k] = nullptr;
+                }
+            return st;
+        }
+        uint64_t acc = 0;
+        for (uint32_t k = 0; k < n_local; ++k) {
+            shard_first_hit[k] = acc;
+            if (acc) {
+                uint64_t *o = hit_offsets + begins[k];
+                const uint64_t cnt = ends[k] - begins[k], base = acc;
+                constexpr uint64_t kPiece = 1ull << 18;
+                HostPool::get().parallel_for(div_up(cnt, kPiece), [&](uint64_t piece) {
+                    const uint64_t lo = piece * kPiece, hi = std::min(cnt, lo + kPiece);
+                    for (uint64_t i = lo; i < hi; ++i) o[i] += base;
+                });
+            }
+            acc += n_hits[k];
+        }
+        shard_first_hit[n_local] = acc;
+        hit_offsets[ends[n_local - 1]] = acc;
+        t_stats.hits = acc;
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, const uint64_t *ends,
@@ -2159,12 +2854,22 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
                                 uint64_t *d_error, void *stream) {
     if (!idx || !dq_in) return fail(GDX_ERR_BAD_ARG, "NULL argument");
     DeviceGuard guard(idx->device);
+    // (offsets is a device pointer here: nothing of the batch may be dereferenced on the host)
+    if (dq_in->encoding > GDX_QUERIES_PACKED_2BIT) return fail(GDX_ERR_BAD_ARG, "unknown queries->encoding %u", dq_in->encoding);
+    if (dq_in->encoding == GDX_QUERIES_PACKED_2BIT && idx->h.ns > 4)
+        return fail(GDX_ERR_UNSUPPORTED, "2-bit packed queries need an alphabet with at most 4 searchable symbols");
     DevQueries dq;
-    dq.bytes = dq_in->bytes;
+    const bool packed = dq_in->encoding == GDX_QUERIES_PACKED_2BIT;
+    if (packed && (reinterpret_cast<uintptr_t>(dq_in->bytes) & 3u))
+        return fail(GDX_ERR_BAD_ARG, "a packed device batch must be 4-byte aligned (and a multiple of 4 bytes long)");
+    dq.bytes = packed ? nullptr : dq_in->bytes;
+    dq.packed = packed ? reinterpret_cast<const uint32_t *>(dq_in->bytes) : nullptr;
     dq.offsets = dq_in->offsets;
+    dq.offsets32 = nullptr;
     dq.fixed_len = dq_in->fixed_len;
     dq.nq = dq_in->nq;
     dq.base = 0;
+    dq.shift = dq_in->first_symbol;
     cudaStream_t st = (cudaStream_t)stream;
     const SortPlan sp = plan_sort(idx, dq.nq, dq.offsets ? 0 : dq.fixed_len);
     const uint32_t *perm = nullptr;
@@ -2174,7 +2879,7 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
         GDX_TRY(sort_queries(idx, dq, sp, scratch, st, &perm));
     }
     GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-        launch_search<decltype(L)>(idx, dq, a, b, mode, 0, d_error, nullptr, perm, st);
+        launch_search<decltype(L)>(idx, dq, a, b, mode, false, 0, d_error, nullptr, perm, nullptr, st);
         return GDX_OK;
     }));
     CUDA_TRY(cudaGetLastError());

@@ -26,6 +26,7 @@ namespace gdx {
 
 constexpr uint64_t kImageMagic = 0x3130305842584447ull;  // "GDXBX001"
 constexpr uint32_t kMaxLookupDepth = 24;
+constexpr uint32_t kAccelNoDenseSA = 1, kAccelNoSeedTable = 2;
 
 struct ImageHeader {
     uint64_t magic;
@@ -37,13 +38,15 @@ struct ImageHeader {
     uint64_t n_samples;
     uint64_t n_records;
     uint64_t n_superblocks;
-    uint32_t sigma, ns, storage, sampling_rate, lookup_depth, pad0;
+    uint32_t sigma, ns, storage, sampling_rate, lookup_depth;
+    uint32_t accel_flags;  // kAccelNoDenseSA | kAccelNoSeedTable: accelerator policy, travels with the image
     RankLayout layout;
     uint64_t off_records, off_sbc, off_samples, off_lookup, off_border_rows, off_border_pos,
         off_sentinels, off_count, off_text;
     uint32_t text_bits;  // 0 = no text section, 4 or 8
     uint32_t has_isa;    // sampled inverse suffix array present
     uint64_t off_isa;
+    uint64_t accel_budget;  // bytes the accelerators of a replica may take together, 0 = automatic
     uint64_t image_bytes;
     uint64_t lut_level_off[kMaxLookupDepth + 1];  // entry offset of level d
     uint64_t lut_pow[kMaxLookupDepth + 1];        // ns^d

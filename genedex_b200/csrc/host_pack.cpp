@@ -1,0 +1,269 @@
+// host_pack.cpp -- see host_pack.h
+#include "host_pack.h"
+
+#include <immintrin.h>
+#include <sched.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+namespace gdx {
+
+// ---- thread pool --------------------------------------------------------------------------------------
+namespace {
+struct Job {
+    const std::function<void(uint64_t)> *fn;
+    uint64_t pieces;
+    std::atomic<uint64_t> next{0};
+    std::atomic<uint64_t> done{0};
+};
+}  // namespace
+
+struct HostPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, done_cv;
+    std::deque<std::shared_ptr<Job>> queue;  // jobs that may still have unclaimed pieces
+    bool stop = false;
+
+    // claims and runs pieces of `job` until none is left
+    void work(const std::shared_ptr<Job> &job) {
+        for (;;) {
+            const uint64_t k = job->next.fetch_add(1, std::memory_order_relaxed);
+            if (k >= job->pieces) break;
+            (*job->fn)(k);
+            if (job->done.fetch_add(1, std::memory_order_acq_rel) + 1 == job->pieces) {
+                std::lock_guard<std::mutex> lk(mu);
+                done_cv.notify_all();
+            }
+        }
+    }
+    void loop() {
+        for (;;) {
+            std::shared_ptr<Job> job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    while (!queue.empty() && queue.front()->next.load(std::memory_order_relaxed) >= queue.front()->pieces)
+                        queue.pop_front();  // fully claimed: nothing left to hand out
+                    return stop || !queue.empty();
+                });
+                if (stop) return;
+                job = queue.front();
+            }
+            work(job);
+        }
+    }
+};
+
+static unsigned usable_cpus() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof set, &set) == 0) {
+        const int c = CPU_COUNT(&set);
+        if (c > 0) return (unsigned)c;
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? h : 1;
+}
+
+HostPool::HostPool() : impl_(new Impl()) {
+    // GDX_HOST_THREADS = total threads working on one staging job (default: the CPUs this process may run
+    // on, at most 32); bench.py gives every rank of a multi-process run its own share of the cores first
+    unsigned total = std::min(32u, usable_cpus());
+    if (const char *e = getenv("GDX_HOST_THREADS"))
+        if (atoi(e) > 0) total = (unsigned)atoi(e);
+    for (unsigned i = 1; i < total; ++i) impl_->workers.emplace_back([this] { impl_->loop(); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv.notify_all();
+    for (auto &t : impl_->workers) t.join();
+    delete impl_;
+}
+
+HostPool &HostPool::get() {
+    static HostPool pool;
+    return pool;
+}
+
+unsigned HostPool::threads() const { return (unsigned)impl_->workers.size() + 1; }
+
+void HostPool::parallel_for(uint64_t pieces, const std::function<void(uint64_t)> &fn) {
+    if (pieces == 0) return;
+    if (pieces == 1 || impl_->workers.empty()) {
+        for (uint64_t k = 0; k < pieces; ++k) fn(k);
+        return;
+    }
+    auto job = std::make_shared<Job>();
+    job->fn = &fn;
+    job->pieces = pieces;
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->queue.push_back(job);
+    }
+    impl_->cv.notify_all();
+    impl_->work(job);
+    std::unique_lock<std::mutex> lk(impl_->mu);
+    impl_->done_cv.wait(lk, [&] { return job->done.load(std::memory_order_acquire) == job->pieces; });
+}
+
+void HostPool::copy(void *dst, const void *src, uint64_t bytes) {
+    constexpr uint64_t kPiece = 1ull << 20;
+    if (bytes <= 2 * kPiece) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const uint64_t pieces = (bytes + kPiece - 1) / kPiece;
+    parallel_for(pieces, [&](uint64_t k) {
+        const uint64_t off = k * kPiece, nb = std::min(kPiece, bytes - off);
+        memcpy((uint8_t *)dst + off, (const uint8_t *)src + off, nb);
+    });
+}
+
+void HostPool::widen_u32(uint64_t *dst, const uint32_t *src, uint64_t n) {
+    constexpr uint64_t kPiece = 1ull << 18;  // elements
+    const uint64_t pieces = (n + kPiece - 1) / kPiece;
+    parallel_for(pieces, [&](uint64_t k) {
+        const uint64_t b = k * kPiece, e = std::min(n, b + kPiece);
+        for (uint64_t i = b; i < e; ++i) dst[i] = src[i];
+    });
+}
+
+// ---- 2-bit packer ---------------------------------------------------------------------------------------
+void build_pack_table(const uint8_t io_to_dense[256], uint32_t num_searchable, PackTable &t) {
+    memset(&t, 0, sizeof t);
+    t.usable = num_searchable >= 1 && num_searchable <= 4;
+    for (int x = 0; x < 256; ++x) {
+        const uint32_t d = io_to_dense[x];
+        t.code[x] = (t.usable && d >= 1 && d <= num_searchable) ? (uint8_t)(d - 1) : 0xff;
+    }
+    if (!t.usable) return;
+    // nibble-split classification: try "class = code" first, then "class = byte value" (<= 8 valid bytes)
+    for (int attempt = 0; attempt < 2 && !t.simd_ok; ++attempt) {
+        int cls[256];
+        int nclasses = 0;
+        bool fits = true;
+        for (int x = 0; x < 256; ++x) {
+            cls[x] = -1;
+            if (t.code[x] == 0xff) continue;
+            cls[x] = attempt == 0 ? t.code[x] : nclasses;
+            ++nclasses;
+            if (attempt == 1 && nclasses > 8) fits = false;
+        }
+        if (!fits) break;
+        memset(t.lo_class, 0, 16);
+        memset(t.hi_class, 0, 16);
+        memset(t.code_lo, 0, 16);
+        for (int x = 0; x < 256; ++x)
+            if (cls[x] >= 0) {
+                t.lo_class[x & 15] |= (uint8_t)(1u << cls[x]);
+                t.hi_class[x >> 4] |= (uint8_t)(1u << cls[x]);
+                t.code_lo[x & 15] = t.code[x];
+            }
+        bool ok = true;
+        for (int x = 0; x < 256 && ok; ++x) {
+            const bool valid = (t.lo_class[x & 15] & t.hi_class[x >> 4]) != 0;
+            if (valid != (t.code[x] != 0xff)) ok = false;
+            else if (valid && t.code_lo[x & 15] != t.code[x]) ok = false;
+        }
+        t.simd_ok = ok;
+    }
+}
+
+static void pack2_scalar(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t pos0,
+                         std::vector<uint64_t> &exc) {
+    uint64_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint8_t a = t.code[src[i]], b = t.code[src[i + 1]], c = t.code[src[i + 2]], d = t.code[src[i + 3]];
+        if ((a | b | c | d) & 0x80) {
+            uint8_t v = 0;
+            for (int k = 0; k < 4; ++k) {
+                const uint8_t ck = t.code[src[i + k]];
+                if (ck == 0xff) exc.push_back(pos0 + i + k);
+                else v |= (uint8_t)(ck << (2 * k));
+            }
+            dst[i >> 2] = v;
+        } else {
+            dst[i >> 2] = (uint8_t)(a | (b << 2) | (c << 4) | (d << 6));
+        }
+    }
+    if (i < n) {
+        uint8_t v = 0;
+        for (int k = 0; i + k < n; ++k) {
+            const uint8_t ck = t.code[src[i + k]];
+            if (ck == 0xff) exc.push_back(pos0 + i + k);
+            else v |= (uint8_t)(ck << (2 * k));
+        }
+        dst[i >> 2] = v;
+    }
+}
+
+__attribute__((target("avx2"))) static void pack2_avx2(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst,
+                                                       uint64_t pos0, std::vector<uint64_t> &exc) {
+    const __m256i lo_tab = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i *)t.lo_class));
+    const __m256i hi_tab = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i *)t.hi_class));
+    const __m256i code_tab = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i *)t.code_lo));
+    const __m256i nib = _mm256_set1_epi8(0x0f), zero = _mm256_setzero_si256();
+    const __m256i mul_1_4 = _mm256_set1_epi16(0x0401);       // bytes (1, 4): c0 + 4 c1 per 16-bit lane
+    const __m256i mul_1_16 = _mm256_set1_epi32(0x00100001);  // words (1, 16): + 16 (c2 + 4 c3) per 32-bit lane
+    const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1,
+                                            0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+    uint64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i x = _mm256_loadu_si256((const __m256i *)(src + i));
+        const __m256i lo = _mm256_and_si256(x, nib);
+        const __m256i hi = _mm256_and_si256(_mm256_srli_epi16(x, 4), nib);
+        const __m256i cls = _mm256_and_si256(_mm256_shuffle_epi8(lo_tab, lo), _mm256_shuffle_epi8(hi_tab, hi));
+        const __m256i inval = _mm256_cmpeq_epi8(cls, zero);
+        __m256i code = _mm256_shuffle_epi8(code_tab, lo);
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(inval);
+        if (m) {
+            code = _mm256_andnot_si256(inval, code);
+            for (uint32_t mm = m; mm; mm &= mm - 1) exc.push_back(pos0 + i + (uint64_t)__builtin_ctz(mm));
+        }
+        const __m256i p16 = _mm256_maddubs_epi16(code, mul_1_4);
+        const __m256i p32 = _mm256_madd_epi16(p16, mul_1_16);
+        const __m256i g = _mm256_shuffle_epi8(p32, gather);
+        const uint32_t o0 = (uint32_t)_mm256_extract_epi32(g, 0), o1 = (uint32_t)_mm256_extract_epi32(g, 4);
+        const uint64_t o = (uint64_t)o0 | ((uint64_t)o1 << 32);
+        memcpy(dst + (i >> 2), &o, 8);
+    }
+    if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
+}
+
+void pack2_serial(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t pos0,
+                  std::vector<uint64_t> &exceptions) {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !(getenv("GDX_PACK_SCALAR") && atoi(getenv("GDX_PACK_SCALAR")));
+    if (t.simd_ok && have_avx2) pack2_avx2(t, src, n, dst, pos0, exceptions);
+    else pack2_scalar(t, src, n, dst, pos0, exceptions);
+}
+
+void pack2_parallel(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst, std::vector<uint64_t> &exceptions) {
+    constexpr uint64_t kPiece = 256ull << 10;  // source bytes per piece, a multiple of 4: pieces own whole output bytes
+    exceptions.clear();
+    if (n <= kPiece) {
+        pack2_serial(t, src, n, dst, 0, exceptions);
+        return;
+    }
+    const uint64_t pieces = (n + kPiece - 1) / kPiece;
+    std::vector<std::vector<uint64_t>> per_piece(pieces);
+    HostPool::get().parallel_for(pieces, [&](uint64_t k) {
+        const uint64_t off = k * kPiece, nb = std::min(kPiece, n - off);
+        pack2_serial(t, src + off, nb, dst + (off >> 2), off, per_piece[k]);
+    });
+    for (auto &v : per_piece) exceptions.insert(exceptions.end(), v.begin(), v.end());
+}
+
+}  // namespace gdx

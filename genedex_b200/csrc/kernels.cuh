@@ -47,12 +47,89 @@
 namespace gdx {
 
 struct DevQueries {
-    const uint8_t *bytes;
+    const uint8_t *bytes;     // IO bytes, or nullptr when `packed` is set
     const uint64_t *offsets;  // nq + 1 entries or nullptr
+    const uint32_t *offsets32;  // the same, chunk relative and narrow (host pipeline: half the PCIe bytes), or nullptr
     uint64_t fixed_len;
     uint64_t nq;
     uint64_t base;            // subtracted from offsets[] (chunked uploads)
+    uint64_t shift;           // added to the start of every query (a packed chunk need not start on a byte boundary)
+    // 2-bit packed form (alphabets with <= 4 searchable symbols): symbol i of the batch (the same index
+    // that addresses `bytes`) sits at bits [2i, 2i+2) of this little-endian word stream, code = dense - 1.
+    // Every symbol of a packed batch is searchable by construction (the host packer routes queries with
+    // any other byte to the IO-byte kernel), so the packed kernel has no invalid-symbol path.
+    const uint32_t *packed;
 };
+
+// symbols [begin, begin + len) of the batch's stream belong to query q
+__device__ __forceinline__ void query_extent(const DevQueries &qs, uint64_t q, uint64_t &begin, uint64_t &len) {
+    if (qs.offsets32) {
+        const uint32_t b = __ldg(qs.offsets32 + q);
+        begin = b;
+        len = __ldg(qs.offsets32 + q + 1) - b;
+    } else if (qs.offsets) {
+        begin = __ldg(qs.offsets + q) - qs.base;
+        len = __ldg(qs.offsets + q + 1) - qs.base - begin;
+    } else {
+        begin = q * qs.fixed_len;
+        len = qs.fixed_len;
+    }
+    begin += qs.shift;
+}
+
+// ---- 2-bit packed queries ----------------------------------------------------------------------------
+// The last 64 symbols of a query live in two registers: symbol j (counted from the first staged symbol)
+// at bits [2j, 2j+2) of the 128-bit value hi:lo.
+struct PackedTail {
+    uint64_t lo, hi;
+};
+__device__ __forceinline__ uint32_t packed_code_global(const uint32_t *pk, uint64_t g) {
+    return (__ldg(pk + (g >> 4)) >> ((uint32_t)(g & 15) * 2)) & 3u;
+}
+// symbols [g0, g0 + nsym) of the stream, nsym <= 64; words past the last needed one are not touched
+__device__ __forceinline__ PackedTail load_packed_tail(const uint32_t *pk, uint64_t g0, uint32_t nsym) {
+    const uint32_t *w = pk + (g0 >> 4);
+    const uint32_t sh = (uint32_t)(g0 & 15) * 2;
+    const uint32_t nw = ((uint32_t)(g0 & 15) + nsym + 15u) >> 4;  // <= 5
+    uint32_t v[5];
+#pragma unroll
+    for (uint32_t k = 0; k < 5; ++k) v[k] = k < nw ? __ldg(w + k) : 0u;
+    uint32_t t[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) t[k] = __funnelshift_r(v[k], v[k + 1], sh);
+    PackedTail r;
+    r.lo = (uint64_t)t[0] | ((uint64_t)t[1] << 32);
+    r.hi = (uint64_t)t[2] | ((uint64_t)t[3] << 32);
+    return r;
+}
+// 2 * nsym bits starting at staged symbol `sym` (nsym <= 32; bits past symbol 63 read as 0)
+__device__ __forceinline__ uint64_t tail_bits(const PackedTail &t, uint32_t sym, uint32_t nsym) {
+    const uint32_t bit = sym * 2;
+    uint64_t v;
+    if (bit == 0) v = t.lo;
+    else if (bit < 64) v = (t.lo >> bit) | (t.hi << (64 - bit));
+    else v = bit < 128 ? t.hi >> (bit - 64) : 0ull;
+    return nsym >= 32 ? v : v & ((1ull << (2 * nsym)) - 1ull);
+}
+__device__ __forceinline__ uint32_t tail_code(const PackedTail &t, uint32_t sym) {
+    return (uint32_t)((sym < 32 ? t.lo : t.hi) >> ((sym & 31u) * 2)) & 3u;
+}
+// 16 2-bit codes -> 16 nibbles holding dense symbols (code + 1); 8 codes -> 8 bytes
+__device__ __forceinline__ uint64_t expand_codes_4(uint64_t x) {
+    x &= 0xffffffffull;
+    x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+    x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+    x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    return x + 0x1111111111111111ull;
+}
+__device__ __forceinline__ uint64_t expand_codes_8(uint64_t x) {
+    x &= 0xffffull;
+    x = (x | (x << 24)) & 0x000000ff000000ffull;
+    x = (x | (x << 12)) & 0x000f000f000f000full;
+    x = (x | (x << 6)) & 0x0303030303030303ull;
+    return x + 0x0101010101010101ull;
+}
 
 constexpr uint64_t kNoError = ~0ull;
 
@@ -221,6 +298,18 @@ __device__ __forceinline__ void lut_load(const DevIndex &ix, uint64_t entry, uin
     }
 }
 
+__device__ __forceinline__ void seed_load(const DevIndex &ix, uint64_t entry, uint64_t &s, uint64_t &e) {
+    if (ix.wide) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ix.seed_lookup) + entry);
+        s = v.x;
+        e = v.y;
+    } else {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ix.seed_lookup) + entry);
+        s = v.x;
+        e = v.y;
+    }
+}
+
 __device__ __forceinline__ void report_error(uint64_t *err, uint64_t q) {
     if (err) atomicMin(reinterpret_cast<unsigned long long *>(err), (unsigned long long)q);
 }
@@ -300,9 +389,10 @@ __device__ __forceinline__ uint32_t text_symbol(const DevIndex &ix, uint64_t p) 
 //   2 = an invalid symbol (dense 0, alphabet.rs:195-198) is reached before any mismatch.
 // Positions before the start of the first text read as 0 = sentinel, which no valid symbol matches.
 // The text section is padded so that the word after the last one may be read.
-template <int BITS>
-__device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8_t *tab, const uint8_t *sbytes,
-                                                 uint64_t tail_begin, const uint8_t *p, uint64_t pos, uint64_t at,
+// query_word(j0, cnt): dense symbols of query positions [j0, j0 + cnt), BITS bits each, symbol j0 lowest.
+// CHECK_ZERO = false: the query cannot hold an invalid symbol (2-bit packed batches).
+template <int BITS, bool CHECK_ZERO, class QW>
+__device__ __forceinline__ int compare_with_text(const DevIndex &ix, QW &&query_word, uint64_t pos, uint64_t at,
                                                  uint64_t &jm, uint32_t &cm) {
     constexpr uint32_t SPW = 64 / BITS;  // symbols per word
     constexpr uint64_t kLow = BITS == 4 ? 0x7777777777777777ull : 0x7f7f7f7f7f7f7f7full;
@@ -322,6 +412,29 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8
             const uint64_t missing = back0 - at;
             tw = missing >= SPW ? 0 : __ldg(text64) << (missing * BITS);
         }
+        const uint64_t qw = query_word(j0, cnt);
+        const uint64_t vm = cnt == SPW ? ~0ull : (1ull << (cnt * BITS)) - 1;
+        const uint64_t diff = (qw ^ tw) & vm;
+        const uint64_t zero = CHECK_ZERO ? ~(((qw & kLow) + kLow) | qw | kLow) & vm : 0ull;  // top bit of every symbol that is 0
+        if (diff | zero) {
+            const uint32_t km = diff ? (63u - (uint32_t)__clzll((long long)diff)) / BITS : 0;
+            if (CHECK_ZERO && zero && (!diff || (63u - (uint32_t)__clzll((long long)zero)) / BITS >= km)) return 2;
+            jm = j0 + km;
+            cm = (uint32_t)(qw >> (km * BITS)) & ((1u << BITS) - 1);
+            return 1;
+        }
+        j_hi = j0;
+    }
+    return 0;
+}
+
+// query words of an IO-byte query whose last bytes are staged in shared memory (tab = io -> dense)
+template <int BITS>
+struct ByteQueryWords {
+    const uint8_t *tab, *sbytes, *p;
+    uint64_t tail_begin;
+    __device__ __forceinline__ uint64_t operator()(uint64_t j0, uint32_t cnt) const {
+        constexpr uint32_t SPW = 64 / BITS;
         uint64_t qw = 0;
         if (j0 >= tail_begin) {  // the whole chunk is staged: two 32-bit halves, no per-symbol branch
             const uint8_t *sp = sbytes + (j0 - tail_begin);
@@ -340,20 +453,35 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, const uint8
                 qw |= (uint64_t)c << (k * BITS);
             }
         }
-        const uint64_t vm = cnt == SPW ? ~0ull : (1ull << (cnt * BITS)) - 1;
-        const uint64_t diff = (qw ^ tw) & vm;
-        const uint64_t zero = ~(((qw & kLow) + kLow) | qw | kLow) & vm;  // top bit of every symbol that is 0
-        if (diff | zero) {
-            const uint32_t km = diff ? (63u - (uint32_t)__clzll((long long)diff)) / BITS : 0;
-            if (zero && (!diff || (63u - (uint32_t)__clzll((long long)zero)) / BITS >= km)) return 2;
-            jm = j0 + km;
-            cm = (uint32_t)(qw >> (km * BITS)) & ((1u << BITS) - 1);
-            return 1;
-        }
-        j_hi = j0;
+        return qw;
     }
-    return 0;
-}
+};
+
+// query words of a 2-bit packed query whose last 64 symbols are in registers
+template <int BITS>
+struct PackedQueryWords {
+    PackedTail tail;
+    const uint32_t *pk;
+    uint64_t begin, tail_begin;  // stream index of query symbol 0; query position of the first staged symbol
+    __device__ __forceinline__ uint64_t operator()(uint64_t j0, uint32_t cnt) const {
+        constexpr uint32_t SPW = 64 / BITS;
+        uint64_t codes;
+        if (j0 >= tail_begin) {
+            codes = tail_bits(tail, (uint32_t)(j0 - tail_begin), SPW);
+        } else {
+            codes = 0;
+#pragma unroll 1
+            for (uint32_t k = 0; k < cnt; ++k) {
+                const uint64_t i = j0 + k;
+                const uint32_t c = i >= tail_begin ? tail_code(tail, (uint32_t)(i - tail_begin))
+                                                   : packed_code_global(pk, begin + i);
+                codes |= (uint64_t)c << (2 * k);
+            }
+        }
+        const uint64_t qw = BITS == 4 ? expand_codes_4(codes) : expand_codes_8(codes);
+        return cnt == SPW ? qw : qw & ((1ull << (cnt * BITS)) - 1);
+    }
+};
 
 // interval flag of the locate plumbing: start = resolved text position, end = kDirectHit
 constexpr uint64_t kDirectHit = ~0ull;
@@ -367,30 +495,34 @@ constexpr uint64_t kDirectHit = ~0ull;
 // them at the same time: the top of the search trie is then served by L2 instead of DRAM (the
 // north-star "query batches are sorted by lookup-table prefix so they share L2").  The sort only
 // permutes the order in which threads pick queries; every result still goes to the query's own slot.
+// sort key of query q: its last key_syms symbols, the last symbol most significant (unsearchable / invalid
+// symbols and positions in front of a short query count as code 0)
+__device__ __forceinline__ uint32_t query_sort_key(const DevIndex &ix, const DevQueries &qs, uint64_t q,
+                                                   uint32_t key_bits, uint32_t key_syms) {
+    uint64_t begin, len;
+    query_extent(qs, q, begin, len);
+    uint32_t key = 0;
+    for (uint32_t j = 0; j < key_syms; ++j) {
+        uint32_t code = 0;
+        if (j < len) {
+            if (qs.packed) {
+                code = packed_code_global(qs.packed, begin + len - 1 - j);
+            } else {
+                const uint32_t c = ix.io_to_dense[__ldg(qs.bytes + begin + len - 1 - j)];
+                code = (c >= 1 && c <= ix.ns) ? c - 1 : 0;
+            }
+        }
+        key = (key << key_bits) | code;
+    }
+    return key;
+}
+
 __global__ void __launch_bounds__(256)
 k_query_keys(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_t key_bits, uint32_t key_syms,
              uint32_t *__restrict__ keys, uint32_t *__restrict__ idx) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= qs.nq) return;
-    uint64_t begin, len;
-    if (qs.offsets) {
-        begin = __ldg(qs.offsets + q) - qs.base;
-        len = __ldg(qs.offsets + q + 1) - qs.base - begin;
-    } else {
-        begin = q * qs.fixed_len;
-        len = qs.fixed_len;
-    }
-    const uint8_t *p = qs.bytes + begin;
-    uint32_t key = 0;
-    for (uint32_t j = 0; j < key_syms; ++j) {
-        uint32_t code = 0;
-        if (j < len) {
-            const uint32_t c = ix.io_to_dense[__ldg(p + len - 1 - j)];
-            code = (c >= 1 && c <= ix.ns) ? c - 1 : 0;
-        }
-        key = (key << key_bits) | code;
-    }
-    keys[q] = key;
+    keys[q] = query_sort_key(ix, qs, q, key_bits, key_syms);
     idx[q] = (uint32_t)q;
 }
 
@@ -406,24 +538,7 @@ k_bucket_count(const __grid_constant__ DevIndex ix, const DevQueries qs, uint32_
                uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= qs.nq) return;
-    uint64_t begin, len;
-    if (qs.offsets) {
-        begin = __ldg(qs.offsets + q) - qs.base;
-        len = __ldg(qs.offsets + q + 1) - qs.base - begin;
-    } else {
-        begin = q * qs.fixed_len;
-        len = qs.fixed_len;
-    }
-    const uint8_t *p = qs.bytes + begin;
-    uint32_t key = 0;
-    for (uint32_t j = 0; j < key_syms; ++j) {
-        uint32_t code = 0;
-        if (j < len) {
-            const uint32_t c = ix.io_to_dense[__ldg(p + len - 1 - j)];
-            code = (c >= 1 && c <= ix.ns) ? c - 1 : 0;
-        }
-        key = (key << key_bits) | code;
-    }
+    const uint32_t key = query_sort_key(ix, qs, q, key_bits, key_syms);
     keys[q] = key;
     atomicAdd(hist + key, 1u);
 }
@@ -475,54 +590,92 @@ constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, co
 // produced -- so mode 0 (cursors) never uses it.  mode 2 = locate: out_a/out_b carry either the
 // interval or (text position, kDirectHit).
 // CURSORS (mode 0 with VERIFY): compile the inverse-sample path only into the variant that needs it
-template <class L, bool VERIFY, bool CURSORS>
+// PACKED: the batch is a 2-bit packed stream (DevQueries::packed); the last 64 symbols of a query are held
+// in two registers (no shared-memory staging, no translate table), lookup indices are bit-field extracts
+// when ns == 4, and there is no invalid-symbol path.
+// slot_map (optional): the result of query q goes to slot slot_map[q] (queries re-run through the IO-byte
+// kernel because they hold a byte the packer cannot encode); errors are reported for that slot.
+// out_bits: 64 or 32 (narrow results for texts shorter than 2^32: half the D2H bytes).
+constexpr int kModeNarrow = 8;  // mode flag: results are written as uint32
+
+template <class L, bool VERIFY, bool CURSORS, bool PACKED>
 __global__ void __launch_bounds__(256, VERIFY ? L::kVerifyMinBlocks : L::kSearchMinBlocks)
 k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__restrict__ out_a,
-         uint64_t *__restrict__ out_b, int mode, uint64_t q_index_base, uint64_t *err,
-         unsigned long long *stat_steps, const uint32_t *__restrict__ perm) {
-    __shared__ uint8_t tab[256];
-    __shared__ uint32_t stage[256 * kQuerySlotWords];
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = ix.io_to_dense[i];
-    __syncthreads();
+         uint64_t *__restrict__ out_b, int mode_flags, uint64_t q_index_base, uint64_t *err,
+         unsigned long long *stat_steps, const uint32_t *__restrict__ perm,
+         const uint32_t *__restrict__ slot_map) {
+    constexpr uint32_t kTabBytes = PACKED ? 4 : 256;
+    constexpr uint32_t kStageWords = PACKED ? 1 : 256 * kQuerySlotWords;
+    __shared__ uint8_t tab[kTabBytes];
+    __shared__ uint32_t stage[kStageWords];
+    if constexpr (!PACKED) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = ix.io_to_dense[i];
+        __syncthreads();
+    }
+    const int mode = mode_flags & 7;
+    const bool narrow = (mode_flags & kModeNarrow) != 0;
 
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0, vsteps = 0, vrows = 0;
     if (t < qs.nq) {
         const uint64_t q = perm ? (uint64_t)__ldg(perm + t) : t;
         uint64_t begin, len;
-        if (qs.offsets) {
-            begin = __ldg(qs.offsets + q) - qs.base;
-            len = __ldg(qs.offsets + q + 1) - qs.base - begin;
-        } else {
-            begin = q * qs.fixed_len;
-            len = qs.fixed_len;
-        }
-        const uint8_t *p = qs.bytes + begin;
+        query_extent(qs, q, begin, len);
+        const uint8_t *p = PACKED ? nullptr : qs.bytes + begin;
 
-        // stage bytes [len - tail, len) of the query: aligned words covering them
+        // the last kQueryStage symbols of the query
         const uint32_t tail = len < kQueryStage ? (uint32_t)len : kQueryStage;
-        const uint64_t tail_begin = len - tail;  // query position of the first staged byte
-        uint32_t *slot = stage + threadIdx.x * kQuerySlotWords;
-        const uint8_t *first = p + tail_begin;
-        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 3u);
-        if (tail) {  // global -> shared without a register round trip: all words of the query are in flight at once
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(first - mis);
-            const uint32_t nw = (mis + tail + 3u) >> 2;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot);
+        const uint64_t tail_begin = len - tail;  // query position of the first staged symbol
+        PackedTail ptail = {0, 0};
+        const uint8_t *sbytes = nullptr;
+        if constexpr (PACKED) {
+            if (tail) ptail = load_packed_tail(qs.packed, begin + tail_begin, tail);
+        } else {
+            // aligned words covering bytes [len - tail, len), global -> shared without a register round
+            // trip: all words of the query are in flight at once
+            uint32_t *slot = stage + threadIdx.x * kQuerySlotWords;
+            const uint8_t *first = p + tail_begin;
+            const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(first) & 3u);
+            if (tail) {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(first - mis);
+                const uint32_t nw = (mis + tail + 3u) >> 2;
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot);
 #pragma unroll 1
-            for (uint32_t k = 0; k < nw; ++k)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * k), "l"(w + k) : "memory");
-            asm volatile("cp.async.wait_all;" ::: "memory");
+                for (uint32_t k = 0; k < nw; ++k)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4 * k), "l"(w + k) : "memory");
+                asm volatile("cp.async.wait_all;" ::: "memory");
+            }
+            sbytes = reinterpret_cast<const uint8_t *>(slot) + mis;
         }
-        const uint8_t *sbytes = reinterpret_cast<const uint8_t *>(slot) + mis;
         // dense symbol of query position i
-#define GDX_SYMBOL_AT(i) tab[(i) >= tail_begin ? sbytes[(i) - tail_begin] : __ldg(p + (i))]
+        auto symbol_at = [&](uint64_t i) -> uint32_t {
+            if constexpr (PACKED)
+                return 1u + (i >= tail_begin ? tail_code(ptail, (uint32_t)(i - tail_begin))
+                                             : packed_code_global(qs.packed, begin + i));
+            else
+                return tab[i >= tail_begin ? sbytes[i - tail_begin] : __ldg(p + i)];
+        };
+        // lookup index of the d symbols starting at query position p0 (lookup_table.rs:68-161: the first
+        // symbol is the least significant digit); ok = false if one of them is invalid or not searchable
+        auto lookup_index = [&](uint64_t p0, uint32_t d, bool &ok) -> uint64_t {
+            if constexpr (PACKED) {
+                if (ix.ns == 4 && d <= 32 && p0 >= tail_begin)  // the digits are the packed bits themselves
+                    return d ? tail_bits(ptail, (uint32_t)(p0 - tail_begin), d) : 0ull;
+            }
+            uint64_t li = 0, f = 1;
+            for (uint32_t j = 0; j < d; ++j) {
+                const uint32_t c = symbol_at(p0 + j);
+                if (c == 0 || c > ix.ns) ok = false;
+                li += (uint64_t)(c - 1) * f;
+                f *= ix.ns;
+            }
+            return li;
+        };
         bool bad = false;
 
-        // K1: lookup_table.rs:68-161 -- first suffix symbol is the least significant digit
-        uint64_t depth = len < ix.lookup_depth ? len : ix.lookup_depth;
+        // K1: lookup_table.rs:68-161
+        const uint32_t depth = len < ix.lookup_depth ? (uint32_t)len : ix.lookup_depth;
         uint64_t pos = len - depth;
-        uint64_t li = 0;
         uint64_t s = 0, e = 0;
         // Seed table accelerator (gdx_index_set_seed_table_depth): one level of a lookup table deeper than
         // the configured one.  Its entries are exactly what the configured table + LF steps produce (an empty
@@ -532,37 +685,20 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         bool seeded = false;
         if (ix.seed_lookup && len >= ix.seed_depth) {
             const uint64_t p0 = len - ix.seed_depth;
-            uint64_t pw = 1;
             bool ok = true;
-            for (uint32_t j = 0; j < ix.seed_depth; ++j) {
-                const uint32_t c = GDX_SYMBOL_AT(p0 + j);
-                if (c == 0 || c > ix.ns) ok = false;
-                li += (uint64_t)(c - 1) * pw;
-                pw *= ix.ns;
-            }
+            const uint64_t li = lookup_index(p0, ix.seed_depth, ok);
             if (ok) {
-                if (ix.wide) {
-                    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(ix.seed_lookup) + li);
-                    s = v.x;
-                    e = v.y;
-                } else {
-                    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(ix.seed_lookup) + li);
-                    s = v.x;
-                    e = v.y;
-                }
+                seed_load(ix, li, s, e);
                 pos = p0;
                 seeded = true;
             }
-            li = 0;
         }
         if (!seeded) {
-            for (uint64_t j = 0; j < depth; ++j) {
-                const uint32_t c = GDX_SYMBOL_AT(pos + j);
-                // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
-                // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
-                if (c == 0 || c > ix.ns) bad = true;
-                li += (uint64_t)(c - 1) * ix.lut_pow[j];
-            }
+            // c == 0: invalid symbol (alphabet.rs:195-198).  c > ns: valid but not searchable; the
+            // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
+            bool ok = true;
+            const uint64_t li = lookup_index(pos, depth, ok);
+            bad = !ok;
             if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
         }
 
@@ -580,9 +716,16 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                 vrows = 1;
                 uint64_t jm = 0;     // query position of the first mismatch (from the right)
                 uint32_t cm = 0;     // its dense symbol
-                const int cmp = ix.text_bits == 4
-                                  ? compare_with_text<4>(ix, tab, sbytes, tail_begin, p, pos, at, jm, cm)
-                                  : compare_with_text<8>(ix, tab, sbytes, tail_begin, p, pos, at, jm, cm);
+                int cmp;
+                if constexpr (PACKED) {
+                    cmp = ix.text_bits == 4
+                              ? compare_with_text<4, false>(ix, PackedQueryWords<4>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm)
+                              : compare_with_text<8, false>(ix, PackedQueryWords<8>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm);
+                } else {
+                    cmp = ix.text_bits == 4
+                              ? compare_with_text<4, true>(ix, ByteQueryWords<4>{tab, sbytes, p, tail_begin}, pos, at, jm, cm)
+                              : compare_with_text<8, true>(ix, ByteQueryWords<8>{tab, sbytes, p, tail_begin}, pos, at, jm, cm);
+                }
                 const bool match = cmp == 0;
                 bad = cmp == 2;  // the reference reaches this symbol with a non-empty interval
                 if (bad) {
@@ -607,8 +750,8 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                 }
                 break;
             }
-            const uint32_t c = GDX_SYMBOL_AT(pos - 1);
-            if (c == 0) {
+            const uint32_t c = symbol_at(pos - 1);
+            if (!PACKED && c == 0) {
                 bad = true;
                 break;
             }
@@ -616,21 +759,29 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             --pos;
             ++steps;
         }
+        const uint64_t slot_q = slot_map ? (uint64_t)__ldg(slot_map + q) : q;
         if (bad) {
-            report_error(err, q_index_base + q);
+            report_error(err, q_index_base + slot_q);
             s = e = 0;
             direct = false;
         }
-        if (mode == 0) {
-            out_a[q] = s;
-            out_b[q] = e;
+        if (narrow) {
+            uint32_t *a32 = reinterpret_cast<uint32_t *>(out_a), *b32 = reinterpret_cast<uint32_t *>(out_b);
+            if (mode == 0) {
+                a32[slot_q] = (uint32_t)s;
+                b32[slot_q] = (uint32_t)e;
+            } else {
+                a32[slot_q] = (uint32_t)(e - s);
+            }
+        } else if (mode == 0) {
+            out_a[slot_q] = s;
+            out_b[slot_q] = e;
         } else if (mode == 1) {
-            out_a[q] = e - s;
+            out_a[slot_q] = e - s;
         } else {
-            out_a[q] = s;
-            out_b[q] = direct ? kDirectHit : e;
+            out_a[slot_q] = s;
+            out_b[slot_q] = direct ? kDirectHit : e;
         }
-#undef GDX_SYMBOL_AT
     }
     if (stat_steps) {  // [0] LF steps of the search, [1] walk steps of verified rows, [5] verified rows
         uint32_t tot = __reduce_add_sync(0xffffffffu, steps);

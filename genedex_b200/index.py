@@ -68,8 +68,10 @@ def pack_queries(queries: Iterable[bytes]):
     return np.ascontiguousarray(data), offsets
 
 
-def _queries_struct(data: np.ndarray, offsets: np.ndarray | None, fixed_len: int, nq: int) -> _lib.gdx_queries:
-    return _lib.gdx_queries(data.ctypes.data, None if offsets is None else offsets.ctypes.data, fixed_len, nq)
+def _queries_struct(data: np.ndarray, offsets: np.ndarray | None, fixed_len: int, nq: int,
+                    encoding: int = _lib.GDX_QUERIES_IO_BYTES) -> _lib.gdx_queries:
+    return _lib.gdx_queries(data.ctypes.data, None if offsets is None else offsets.ctypes.data, fixed_len, nq,
+                            encoding, 0)
 
 
 class FmIndexConfig:
@@ -84,6 +86,7 @@ class FmIndexConfig:
         self._construction = _lib.GDX_CONSTRUCT_AUTO  # all construction routes give the same index
         self._device = -1
         self._flags = 0
+        self._accel_budget = 0
 
     def suffix_array_sampling_rate(self, rate: int) -> "FmIndexConfig":
         assert rate > 0  # config.rs:28
@@ -133,6 +136,12 @@ class FmIndexConfig:
         self._flags = (self._flags & ~_lib.GDX_FLAG_NO_SEED_TABLE) | (0 if allow else _lib.GDX_FLAG_NO_SEED_TABLE)
         return self
 
+    def accelerator_budget(self, nbytes: int) -> "FmIndexConfig":
+        """Device memory the accelerators of a replica (dense suffix array, seed table) may take together;
+        0 = automatic (each at most a quarter of the free memory).  Travels with the index image."""
+        self._accel_budget = int(nbytes)
+        return self
+
     def device(self, ordinal: int) -> "FmIndexConfig":
         self._device = ordinal
         return self
@@ -147,7 +156,8 @@ class FmIndexConfig:
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         a = _alphabet_struct(alphabet)
         cfg = _lib.gdx_config(_STORAGE[self.storage], self._sampling_rate, self._lookup_depth,
-                              int(self._priority), self._construction, self._device, self._flags)
+                              int(self._priority), self._construction, self._device, self._flags,
+                              self._accel_budget)
         h = C.c_void_p()
         _check(lib.gdx_index_build(data.ctypes.data, offsets.ctypes.data, offsets.size - 1, C.byref(a),
                                    C.byref(cfg), C.byref(h)))
@@ -225,30 +235,50 @@ class FmIndex:
 
     # -- packed (numpy) forms: the zero-copy entry points the list forms are built on
     def cursors_many_packed(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
-                            nq: int | None = None, out: tuple[np.ndarray, np.ndarray] | None = None):
-        """-> (starts, ends); `out` = two uint64 arrays of >= nq entries to fill (e.g. pinned memory)."""
+                            nq: int | None = None, out: tuple[np.ndarray, np.ndarray] | None = None,
+                            encoding: int = _lib.GDX_QUERIES_IO_BYTES):
+        """-> (starts, ends); `out` = two uint64 (or two uint32) arrays of >= nq entries to fill (e.g. pinned memory)."""
         nq = (offsets.size - 1) if offsets is not None else nq
         starts, ends = out if out is not None else (np.empty(max(nq, 1), dtype=np.uint64),
                                                     np.empty(max(nq, 1), dtype=np.uint64))
-        q = _queries_struct(data, offsets, fixed_len, nq)
-        _check(self._lib.gdx_cursors_many(self._h, C.byref(q), starts.ctypes.data, ends.ctypes.data))
+        q = _queries_struct(data, offsets, fixed_len, nq, encoding)
+        fn = self._lib.gdx_cursors_many_u32 if starts.dtype == np.uint32 else self._lib.gdx_cursors_many
+        _check(fn(self._h, C.byref(q), starts.ctypes.data, ends.ctypes.data))
         return starts[:nq], ends[:nq]
 
     def count_many_packed(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
-                          nq: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+                          nq: int | None = None, out: np.ndarray | None = None,
+                          encoding: int = _lib.GDX_QUERIES_IO_BYTES) -> np.ndarray:
+        """`out` may be a uint64 or a uint32 array (the latter: gdx_count_many_u32, texts < 2^32 symbols);
+        encoding = GDX_QUERIES_PACKED_2BIT: `data` is a 2-bit stream made by pack_queries_2bit."""
         nq = (offsets.size - 1) if offsets is not None else nq
         counts = out if out is not None else np.empty(max(nq, 1), dtype=np.uint64)
-        q = _queries_struct(data, offsets, fixed_len, nq)
-        _check(self._lib.gdx_count_many(self._h, C.byref(q), counts.ctypes.data))
+        q = _queries_struct(data, offsets, fixed_len, nq, encoding)
+        fn = self._lib.gdx_count_many_u32 if counts.dtype == np.uint32 else self._lib.gdx_count_many
+        assert counts.dtype in (np.uint32, np.uint64)
+        _check(fn(self._h, C.byref(q), counts.ctypes.data))
         return counts[:nq]
 
+    def pack_queries_2bit(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
+                          nq: int | None = None, out: np.ndarray | None = None):
+        """IO bytes -> 2-bit stream (gdx_pack_queries); -> (packed uint8 array, index of the first query that
+        cannot be packed or None)."""
+        nq = (offsets.size - 1) if offsets is not None else nq
+        total = int(offsets[-1]) if offsets is not None else nq * fixed_len
+        nbytes = int(self._lib.gdx_packed_bytes(total))
+        packed = out if out is not None else np.empty(max(nbytes, 4), dtype=np.uint8)
+        first = C.c_uint64()
+        q = _queries_struct(data, offsets, fixed_len, nq)
+        _check(self._lib.gdx_pack_queries(self._h, C.byref(q), packed.ctypes.data, C.byref(first)))
+        return packed, (None if first.value == 2 ** 64 - 1 else int(first.value))
+
     def locate_many_packed(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
-                           nq: int | None = None):
+                           nq: int | None = None, encoding: int = _lib.GDX_QUERIES_IO_BYTES):
         """-> (hit_offsets[nq+1], hits[n,2] = (text_id, position)); hits of a query in SA-row order."""
         nq = (offsets.size - 1) if offsets is not None else nq
         hit_offsets = np.empty(nq + 1, dtype=np.uint64)
         hp, nh = C.c_void_p(), C.c_uint64()
-        q = _queries_struct(data, offsets, fixed_len, nq)
+        q = _queries_struct(data, offsets, fixed_len, nq, encoding)
         _check(self._lib.gdx_locate_many(self._h, C.byref(q), hit_offsets.ctypes.data, C.byref(hp), C.byref(nh)))
         return hit_offsets, self._take_hits(hp, nh.value)
 

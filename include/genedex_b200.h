@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GDX_ABI_VERSION 1
+#define GDX_ABI_VERSION 2
 
 typedef enum gdx_status {
     GDX_OK = 0,
@@ -39,7 +39,8 @@ typedef enum gdx_status {
     GDX_ERR_CUDA = 3,
     GDX_ERR_OOM = 4,
     GDX_ERR_TEXT_TOO_LONG = 5, /* src/construction/mod.rs:34 assert */
-    GDX_ERR_UNSUPPORTED = 6
+    GDX_ERR_UNSUPPORTED = 6,
+    GDX_ERR_BUSY = 7           /* an accelerator cannot be rebuilt / freed while queries run on the handle */
 } gdx_status;
 
 /* IndexStorage `I` of the reference (src/construction/mod.rs:59-73,146-252). It bounds the total
@@ -70,6 +71,11 @@ typedef struct gdx_config {
     uint32_t construction;           /* gdx_construction */
     int32_t device;                  /* CUDA device ordinal, -1 = current device */
     uint32_t flags;                  /* GDX_FLAG_* */
+    /* Device memory the optional accelerators of a replica (dense suffix array, seed table; see
+     * gdx_index_set_*) may take together, in bytes.  0 = automatic: each accelerator is built when it needs
+     * at most a quarter of the device memory that is free at that moment.  The budget is stored in the
+     * index image, so replicas, adopted and loaded indexes follow the same policy. */
+    uint64_t accelerator_budget_bytes;
 } gdx_config;
 
 /* re-check the device-built suffix array in O(n) (permutation + order) before it is used */
@@ -92,14 +98,30 @@ typedef struct gdx_hit {
     uint64_t position;
 } gdx_hit;
 
-/* A batch of queries in IO representation: query i = bytes[offsets[i] .. offsets[i+1]).
- * offsets == NULL means every query has length fixed_len and query i starts at i * fixed_len.
+/* How the symbols of a query batch are stored. */
+typedef enum gdx_query_encoding {
+    /* one IO byte per symbol, translated through the alphabet on the device (the reference's input) */
+    GDX_QUERIES_IO_BYTES = 0,
+    /* 2 bits per symbol, code = dense symbol - 1, symbol k of the batch at bits [2(k%4), 2(k%4)+2) of byte k/4.
+     * Only for alphabets with at most 4 searchable symbols (every DNA alphabet, alphabet.rs:251-300) and only
+     * for batches made of searchable symbols (gdx_pack_queries checks that).  A quarter of the PCIe bytes:
+     * for callers that keep their reads packed.  IO-byte batches are packed by the library itself while it
+     * stages them (see gdx_count_many). */
+    GDX_QUERIES_PACKED_2BIT = 1
+} gdx_query_encoding;
+
+/* A batch of queries: query i = symbols [offsets[i], offsets[i+1]) of the batch's symbol stream.
+ * offsets == NULL means every query has length fixed_len and query i starts at symbol i * fixed_len
+ * (+ first_symbol).  With GDX_QUERIES_IO_BYTES symbol k is bytes[k].
  * Replaces `impl IntoIterator<Item = Q: AsRef<[u8]>>` of src/lib.rs:155-158,179-182,241-244. */
 typedef struct gdx_queries {
     const uint8_t *bytes;
     const uint64_t *offsets; /* nq + 1 entries, or NULL */
     uint64_t fixed_len;
     uint64_t nq;
+    uint32_t encoding;       /* gdx_query_encoding */
+    uint32_t first_symbol;   /* fixed-length batches: stream index of the first symbol of query 0 (sub-batches of a
+                              * packed stream need not start on a byte boundary); 0 otherwise */
 } gdx_queries;
 
 /* The host-side structures of a constructed reference index, in the reference's own layout
@@ -114,7 +136,7 @@ typedef struct gdx_parts {
     const uint64_t *interleaved_blocks;   /* ceil((n+1)/64) * ceil(log2 sigma) words               */
     const uint16_t *interleaved_block_offsets; /* ceil((n+1)/64) * sigma (may be NULL: recomputed) */
     /* SampledSuffixArray, src/sampled_suffix_array.rs:18-23                                       */
-    const uint64_t *sampled_suffix_array; /* ceil(n / rate) entries                                */
+    const uint64_t *sampled_suffix_array; /* ceil(n / rate) entries, widened; or NULL and ...      */
     uint32_t sampling_rate;
     const uint64_t *text_border_rows;     /* keys of text_border_lookup                            */
     const uint64_t *text_border_positions;/* values of text_border_lookup                          */
@@ -123,6 +145,11 @@ typedef struct gdx_parts {
     const uint64_t *sentinel_indices;
     uint64_t num_texts;
     uint32_t lookup_table_depth;          /* tables are re-derived on the device                   */
+    /* ... the crate's own `suffix_array_data: Vec<u32>` (sampled_suffix_array.rs:18-23) as it is for the
+     * 32-bit storage types: no widened copy needed.  Exactly one of the two sample pointers is set. */
+    const uint32_t *sampled_suffix_array_u32;
+    uint32_t flags;                       /* GDX_FLAG_NO_DENSE_SUFFIX_ARRAY | GDX_FLAG_NO_SEED_TABLE */
+    uint64_t accelerator_budget_bytes;    /* as gdx_config.accelerator_budget_bytes                */
 } gdx_parts;
 
 typedef struct gdx_index gdx_index;
@@ -160,6 +187,12 @@ typedef struct gdx_stats {
     double kernel_ms_locate; /* CUDA-event time of the locate kernels                */
     uint64_t kernel_launches;
     uint64_t verified_queries; /* queries finished by one text comparison instead of LF steps */
+    uint64_t locate_walk_steps;/* the part of walk_steps spent in the locate kernel            */
+    uint64_t packed_queries;   /* queries that crossed PCIe 2-bit packed (host packer or pre-packed input) */
+    uint64_t exception_queries;/* queries of packed chunks re-run from their IO bytes (hold an unencodable byte) */
+    uint64_t h2d_bytes;        /* bytes copied host -> device by the call                      */
+    uint64_t d2h_bytes;        /* bytes copied device -> host by the call                      */
+    uint64_t shards;           /* replicas that worked on the call (1 unless *_sharded)        */
 } gdx_stats;
 
 uint32_t gdx_abi_version(void);
@@ -211,10 +244,12 @@ gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *out);
  * beyond 2^32 - 1 symbols), derived on the device from the samples in a fraction of a second:
  * resolving a row (locate, and the text verification of count/locate) is then one load instead of an
  * LF-walk of up to rate - 1 steps plus a load.  Results are identical with and without it.
- * It is built automatically after construction / load / adopt / replicate when it needs at most a
- * quarter of the free device memory (GDX_DENSE_SA=0 never, =1 always; GDX_FLAG_NO_DENSE_SUFFIX_ARRAY
- * per index).  on != 0 builds it now (GDX_ERR_OOM if it does not fit), on == 0 frees it.  Must not run
- * concurrently with queries on the same handle. */
+ * It is built automatically after construction / load / adopt / replicate when the policy of the index
+ * allows it: GDX_FLAG_NO_DENSE_SUFFIX_ARRAY never; gdx_config.accelerator_budget_bytes when set, else at most a
+ * quarter of the free device memory.  The policy travels with the image (replicas, files).  The environment
+ * variable GDX_DENSE_SA (0 never, 1 always) overrides it for measurements.
+ * on != 0 builds it now (GDX_ERR_OOM if it does not fit), on == 0 frees it.  Returns GDX_ERR_BUSY while host-buffer
+ * queries run on the handle; the caller must also have drained its own *_device launches. */
 gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
 
 /* Seed table accelerator (memory for speed).  The index keeps the lookup tables of the configured depth
@@ -226,10 +261,10 @@ gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
  * steps produce (also when it is empty), every other query takes the configured path.  Results, error
  * behaviour and reported lookup_table_depth are unchanged.
  * Built automatically after construction / load / adopt / replicate with the largest d such that
- * ns^d <= text length, if that needs at most a quarter of the free device memory (GDX_SEED_TABLE=0 never,
- * =d that depth; GDX_FLAG_NO_SEED_TABLE per index).  depth > configured depth (re)builds it at that depth now
- * (GDX_ERR_OOM / GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  Must not run concurrently
- * with queries on the same handle. */
+ * ns^d <= text length, under the same policy as the dense suffix array (GDX_FLAG_NO_SEED_TABLE,
+ * gdx_config.accelerator_budget_bytes, else a quarter of the free memory; GDX_SEED_TABLE=0 / =d overrides it
+ * for measurements).  depth > configured depth (re)builds it at that depth now (GDX_ERR_OOM /
+ * GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  GDX_ERR_BUSY as above. */
 gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth);
 
 /* ---- index files: FmIndex::save_to_file / load_from_file (src/lib.rs:296-327) -------------------------
@@ -252,16 +287,55 @@ gdx_status gdx_index_export(const gdx_index *idx, void *header_out, const void *
                             uint64_t *image_bytes);
 gdx_status gdx_index_adopt_image(const void *header, void *device_image, int32_t device,
                                  int32_t own_image, gdx_index **out);
-/* single-process convenience: replicas on other devices via peer copies from the source device */
+/* Single process, several GPUs: full replicas of `idx` on `devices` with ONE grouped ncclBroadcast of the
+ * device image from the source GPU over NVLink (ncclCommInitAll over the source device + the targets; NCCL is
+ * loaded at run time from libnccl.so.2).  A target equal to the source device gets a device-to-device copy.
+ * If NCCL cannot be loaded the copies go through cudaMemcpyPeer; gdx_replicate_transport() names what the
+ * last call on this thread used ("nccl", "peer").  Every replica then derives its own accelerators
+ * (no collective on the query path). */
 gdx_status gdx_index_replicate(const gdx_index *idx, const int32_t *devices, int32_t n_devices,
                                gdx_index **out_replicas);
+const char *gdx_replicate_transport(void);
+
+/* One process per GPU: rank 0 creates an NCCL unique id (128 bytes), hands it to the other ranks out of band
+ * (MPI, torch.distributed, a file, ...), then EVERY rank calls gdx_index_broadcast: the library joins the
+ * communicator (ncclCommInitRank), broadcasts image header + device image from rank `root` and adopts them.
+ * `src` is the root's index (NULL elsewhere).  *out: a new replica on `device`; on the root it is `src` itself
+ * (no copy, do not destroy it twice). */
+#define GDX_NCCL_UNIQUE_ID_BYTES 128
+gdx_status gdx_nccl_unique_id(void *id_out);
+gdx_status gdx_index_broadcast(const gdx_index *src, const void *unique_id, int32_t rank, int32_t world,
+                               int32_t root, int32_t device, gdx_index **out);
 
 /* ---- batched search with host buffers ----------------------------------------------------------*/
 /* FmIndex::cursors_for_many_queries (src/lib.rs:241-246): intervals [start,end) in input order. */
 gdx_status gdx_cursors_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *starts,
                             uint64_t *ends);
-/* FmIndex::count_many (src/lib.rs:155-161) */
+/* FmIndex::count_many (src/lib.rs:155-161).
+ * Large IO-byte batches over an alphabet with <= 4 searchable symbols are packed to 2 bits per symbol by a
+ * pool of host threads while they are staged into pinned memory (GDX_HOST_THREADS, default: the CPUs of the
+ * process), so a quarter of the bytes cross PCIe; queries holding any other byte (invalid, or valid but not
+ * searchable such as `N`) are re-run from their IO bytes, which keeps the reference's lazy invalid-symbol
+ * behaviour exact.  Results of large batches cross PCIe as uint32 when the text is shorter than 2^32. */
 gdx_status gdx_count_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *counts);
+/* the same with uint32 results written straight into the caller's arrays (GDX_ERR_UNSUPPORTED for texts of
+ * 2^32 symbols or more) */
+gdx_status gdx_count_many_u32(const gdx_index *idx, const gdx_queries *queries, uint32_t *counts);
+gdx_status gdx_cursors_many_u32(const gdx_index *idx, const gdx_queries *queries, uint32_t *starts,
+                                uint32_t *ends);
+/* Packs an IO-byte batch to GDX_QUERIES_PACKED_2BIT with the library's host packer (for callers that reuse
+ * a batch or keep reads packed).  packed_out: gdx_packed_bytes(total symbols) bytes, symbol k of the batch at
+ * stream index k (offsets / fixed_len stay valid for the packed batch).  *first_unencodable = index of the
+ * first query holding a byte without a 2-bit code, or UINT64_MAX; such a batch must be searched as IO bytes. */
+uint64_t gdx_packed_bytes(uint64_t total_symbols);
+gdx_status gdx_pack_queries(const gdx_index *idx, const gdx_queries *io_queries, uint8_t *packed_out,
+                            uint64_t *first_unencodable);
+/* The packer itself, without an index (host only, no GPU needed): n IO bytes -> (n + 3) / 4 packed bytes; the
+ * positions of bytes without a 2-bit code (packed as 0) go to exception_positions (up to `capacity`, sorted),
+ * their number to *num_exceptions. */
+gdx_status gdx_pack_symbols(const gdx_alphabet *alphabet, const uint8_t *io_bytes, uint64_t n,
+                            uint8_t *packed_out, uint64_t *exception_positions, uint64_t capacity,
+                            uint64_t *num_exceptions);
 /* FmIndex::locate_many (src/lib.rs:179-185): CSR result; hit_offsets has nq + 1 entries; the hits
  * of query i are hits[hit_offsets[i] .. hit_offsets[i+1]) in the reference's SA-row order. */
 gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
@@ -272,6 +346,28 @@ gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, co
                                 uint64_t n, uint64_t *hit_offsets, gdx_hit **hits,
                                 uint64_t *num_hits);
 void gdx_free_hits(const gdx_index *idx, gdx_hit *hits);
+
+/* ---- one batch over several replicas (the drop-in for src/lib.rs:155-185 on a multi-GPU box) ---
+ * The batch is cut into n_shards contiguous ranges (gdx_shard_range); this process owns the shards
+ * [first_shard, first_shard + n_local) and searches shard first_shard + k on replicas[k], one host thread and
+ * one pinned staging arena per GPU, no collective.  Results are written straight into the caller's arrays at
+ * the queries' own positions (input order); entries of ranges owned by other processes are not touched.
+ * Single process: first_shard = 0, n_local = n_shards = number of GPUs.  One process per GPU (MPI / torchrun):
+ * n_local = 1, first_shard = rank, n_shards = world size. */
+void gdx_shard_range(uint64_t n_items, uint32_t shard, uint32_t n_shards, uint64_t *begin, uint64_t *end);
+gdx_status gdx_count_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                  uint32_t n_shards, const gdx_queries *queries, uint64_t *counts);
+gdx_status gdx_cursors_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                    uint32_t n_shards, const gdx_queries *queries, uint64_t *starts,
+                                    uint64_t *ends);
+/* Hits come back per shard (no concatenation copy): shard_hits[k] (release with gdx_free_hits(replicas[k], ..))
+ * holds the hits of local shard k, shard_first_hit[k] the number of hits of the local shards before it
+ * (n_local + 1 entries).  hit_offsets (nq + 1 entries, the owned ranges and the entry after the last owned
+ * query are written) index the concatenation of the local shards: the hits of query i of local shard k are
+ * shard_hits[k][hit_offsets[i] - shard_first_hit[k] .. hit_offsets[i + 1] - shard_first_hit[k]). */
+gdx_status gdx_locate_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                   uint32_t n_shards, const gdx_queries *queries, uint64_t *hit_offsets,
+                                   gdx_hit **shard_hits, uint64_t *shard_first_hit);
 /* Cursor::extend_query_front (src/cursor.rs:34-51) for many cursors: in-place on starts/ends.  On an error
  * status the contents of pinned starts/ends are unspecified (the reference panics); pageable arrays are
  * left untouched. */

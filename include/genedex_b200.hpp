@@ -144,7 +144,7 @@ struct Packed {
         }
         if (bytes.empty()) bytes.push_back(0);  // keep a valid pointer
     }
-    gdx_queries view() const { return gdx_queries{bytes.data(), offsets.data(), 0, offsets.size() - 1}; }
+    gdx_queries view() const { return gdx_queries{bytes.data(), offsets.data(), 0, offsets.size() - 1, GDX_QUERIES_IO_BYTES, 0}; }
 };
 struct Handle {
     gdx_index *p = nullptr;
@@ -300,7 +300,7 @@ private:
         return *this;
     }
     // config.rs:72-82 defaults: sampling rate 4, lookup depth 0, Balanced
-    gdx_config cfg_{I::storage, 4, 0, (uint32_t)PerformancePriority::Balanced, GDX_CONSTRUCT_AUTO, -1, 0};
+    gdx_config cfg_{I::storage, 4, 0, (uint32_t)PerformancePriority::Balanced, GDX_CONSTRUCT_AUTO, -1, 0, 0};
 };
 
 }  // namespace gdx

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(gdx):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} is declared in the header but not exported"
     assert declared == set(gdx._lib.PROTOTYPES), "Python prototypes and header disagree"
-    assert lib.gdx_abi_version() == 1
+    assert lib.gdx_abi_version() == gdx._lib.GDX_ABI_VERSION == 2
     assert lib.gdx_index_header_bytes() > 256
 
 
@@ -274,3 +274,112 @@ def test_concat_texts_equals_oracle_also_multithreaded(gdx):
     assert lib.gdx_concat_texts(bad.ctypes.data, offs.ctypes.data, 2, C.byref(alph), dense.ctypes.data, sent.ctypes.data,
                                 count.ctypes.data) == gdx._lib.GDX_ERR_INVALID_SYMBOL
     assert lib.gdx_last_error_query() == 1
+
+
+# ---- host packer (genedex_b200/csrc/host_pack.cpp): the stage that cuts the PCIe bytes of a batch to a quarter ----
+def _pack_reference(alphabet, data):
+    """numpy restatement: code = dense - 1 for searchable symbols, exceptions elsewhere (packed as 0)."""
+    tab = np.frombuffer(bytes(alphabet.io_to_dense_table), dtype=np.uint8)
+    ns = alphabet.num_searchable_dense_symbols()
+    dense = tab[data]
+    ok = (dense >= 1) & (dense <= ns)
+    code = np.where(ok, dense - 1, 0).astype(np.uint8)
+    pad = (-code.size) % 4
+    code = np.concatenate([code, np.zeros(pad, dtype=np.uint8)]).reshape(-1, 4)
+    packed = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
+    return packed.astype(np.uint8), np.flatnonzero(~ok).astype(np.uint64)
+
+
+def _pack_library(gdx, alphabet, data):
+    from genedex_b200.index import _alphabet_struct
+    lib = gdx._lib.load()
+    a = _alphabet_struct(alphabet)
+    out = np.full((data.size + 3) // 4 + 8, 0xEE, dtype=np.uint8)
+    exc = np.zeros(max(data.size, 1), dtype=np.uint64)
+    n_exc = C.c_uint64()
+    rc = lib.gdx_pack_symbols(C.byref(a), data.ctypes.data, data.size, out.ctypes.data, exc.ctypes.data, exc.size,
+                              C.byref(n_exc))
+    assert rc == 0, lib.gdx_last_error_message()
+    assert np.all(out[(data.size + 3) // 4:] == 0xEE), "the packer wrote past its output"
+    return out[: (data.size + 3) // 4], exc[: n_exc.value]
+
+
+@pytest.mark.parametrize("size", [0, 1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 1000, 262_144, 262_147, 3_000_001])
+def test_pack_symbols_matches_numpy(size):
+    import genedex_b200 as gdx
+    rng = np.random.default_rng(size)
+    for name in ("ascii_dna", "ascii_dna_with_n"):
+        alphabet = getattr(gdx.alphabet, name)()
+        clean = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, size)]
+        dirty = clean.copy()
+        if size:
+            bad = rng.integers(0, size, max(1, size // 50))
+            dirty[bad] = rng.integers(0, 256, bad.size).astype(np.uint8)
+        for data in (clean, dirty, rng.integers(0, 256, size).astype(np.uint8)):
+            want, want_exc = _pack_reference(alphabet, data)
+            got, got_exc = _pack_library(gdx, alphabet, np.ascontiguousarray(data))
+            assert np.array_equal(got, want)
+            assert np.array_equal(got_exc, want_exc)
+
+
+def test_pack_symbols_alphabets_without_a_nibble_split():
+    """searchable bytes whose code is not a function of the low nibble take the scalar packer; more than four
+    searchable symbols are refused."""
+    import genedex_b200 as gdx
+    lib = gdx._lib.load()
+    rng = np.random.default_rng(5)
+    odd = gdx.alphabet.Alphabet.from_io_symbols(bytes([0x11, 0x21, 0x31, 0x41]), 0)  # same low nibble, four codes
+    data = np.array([0x11, 0x21, 0x31, 0x41, 0x51, 0x01], dtype=np.uint8)[rng.integers(0, 6, 100_003)]
+    want, want_exc = _pack_reference(odd, data)
+    got, got_exc = _pack_library(gdx, odd, np.ascontiguousarray(data))
+    assert np.array_equal(got, want) and np.array_equal(got_exc, want_exc)
+    from genedex_b200.index import _alphabet_struct
+    a = _alphabet_struct(gdx.alphabet.ascii_amino_acid())
+    out = np.zeros(16, dtype=np.uint8)
+    n_exc = C.c_uint64()
+    assert lib.gdx_pack_symbols(C.byref(a), out.ctypes.data, 4, out.ctypes.data, None, 0, C.byref(n_exc)) \
+        == gdx._lib.GDX_ERR_UNSUPPORTED
+
+
+def test_host_pool_runs_concurrent_jobs():
+    """several host threads submit staging jobs at once (a sharded call has one per GPU): every job sees only its
+    own pieces (the old pool could hand a piece of the next job to a worker leaving the previous one)"""
+    import threading
+
+    import genedex_b200 as gdx
+    alphabet = gdx.alphabet.ascii_dna()
+    rng = np.random.default_rng(11)
+    datas = [np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+             for n in (5_000_000, 700_001, 3_000_000, 1_500_003)]
+    wants = [_pack_reference(alphabet, d)[0] for d in datas]
+    errors = []
+
+    def worker(i):
+        try:
+            for _ in range(6):
+                got, exc = _pack_library(gdx, alphabet, datas[i])
+                assert exc.size == 0 and np.array_equal(got, wants[i])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(datas))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
+def test_shard_range_is_contiguous_and_balanced():
+    import genedex_b200 as gdx
+    lib = gdx._lib.load()
+    for n in (0, 1, 7, 8, 1001, 60_000_000, 2 ** 40 + 3):
+        for world in (1, 2, 3, 4, 8):
+            prev_end, sizes = 0, []
+            for r in range(world):
+                b, e = C.c_uint64(), C.c_uint64()
+                lib.gdx_shard_range(n, r, world, C.byref(b), C.byref(e))
+                assert b.value == prev_end
+                prev_end = e.value
+                sizes.append(e.value - b.value)
+            assert prev_end == n and max(sizes) - min(sizes) <= 1

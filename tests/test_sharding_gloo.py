@@ -1,6 +1,7 @@
-"""world_size-2 gloo test (CPU) of the multi-process plumbing of the N > 1 path: query sharding by
-contiguous ranges, broadcast of an index image from rank 0 (bytes stand in for the device image),
-and order-preserving gather of per-rank results.  The per-rank "search" here is the CPU oracle --
+"""world_size-2 gloo test (CPU) of the multi-process plumbing of the N > 1 path: query sharding by the
+library's contiguous ranges (gdx_shard_range), the out-of-band hand-over of the 128-byte NCCL unique id
+that gdx_index_broadcast needs (torch_share_id; the broadcast itself needs GPUs: tests/test_gpu_multi.py),
+and the order-preserving gather of per-rank results.  The per-rank "search" here is the CPU oracle --
 the product's search needs a GPU -- so this checks the host logic around the C ABI only."""
 import os
 import socket
@@ -30,12 +31,10 @@ def _worker(rank, world, port, tmpdir):
     from oracle import oracle as O
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        # 1. "image" broadcast: rank 0 owns the bytes, everyone ends up with the same bytes
-        rng = np.random.default_rng(123)
-        image = rng.integers(0, 256, 3_000_001, dtype=np.uint8)
-        buf = torch.from_numpy(image.copy()) if rank == 0 else torch.zeros(image.size, dtype=torch.uint8)
-        R.broadcast_bytes(buf, 0, chunk=1 << 20)
-        assert np.array_equal(buf.numpy(), image)
+        # 1. the unique id of the root reaches every rank unchanged
+        uid = bytes(np.random.default_rng(123).integers(0, 256, 128, dtype=np.uint8))
+        got_uid = R.torch_share_id(rank)(uid if rank == 0 else None)
+        assert got_uid == uid
         # 2. every rank searches its contiguous shard on its own replica, rank 0 gathers in order
         trng = np.random.default_rng(7)
         text = np.frombuffer(b"ACGT", dtype=np.uint8)[trng.integers(0, 4, 50_000)].tobytes()
