@@ -100,6 +100,7 @@ PROTOTYPES = {
     "gdx_index_get_info": (C.c_int, [_vp, _P(gdx_index_info)]),
     "gdx_index_set_dense_suffix_array": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_set_seed_table_depth": (C.c_int, [_vp, C.c_int32]),
+    "gdx_index_set_text_verification": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_save_to_file": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "gdx_index_load_from_file": (C.c_int, [C.c_char_p, _i32, _P(_vp), _vp, _u64, _P(_u64)]),
     "gdx_index_header_bytes": (_u64, []),
@@ -128,6 +129,7 @@ PROTOTYPES = {
     "gdx_cursors_many_device": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp, _vp, _vp]),
     "gdx_count_many_device": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp, _vp]),
     "gdx_locate_intervals_device": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "gdx_host_pool_resize": (_u32, [_u32]),
     "gdx_host_alloc": (C.c_int, [_u64, _P(_vp)]),
     "gdx_host_free": (None, [_vp]),
     "gdx_get_stats": (C.c_int, [_P(gdx_stats)]),

@@ -309,6 +309,7 @@ struct gdx_index {
     uint64_t dense_sa_bytes = 0;
     void *seed_lut = nullptr;      // accelerator outside the image (gdx_index_set_seed_table_depth)
     uint64_t seed_lut_bytes = 0;
+    bool verify = true;            // finish one-row intervals through the text section (gdx_index_set_text_verification)
     PackTable pack;                // io byte -> 2-bit code (host packer, host_pack.h)
     // host-buffer queries hold this shared for the whole call; (re)building or freeing an accelerator needs it
     // exclusively and reports GDX_ERR_BUSY instead of pulling memory from under a running kernel
@@ -531,8 +532,10 @@ gdx_status validate_header(const ImageHeader &h) {
 }
 
 // run-time overrides of kernel parameters (measurements only)
+bool verify_enabled();
 gdx_status init_policies(gdx_index *idx) {
     build_pack_table(idx->h.io_to_dense, idx->h.ns, idx->pack);
+    idx->verify = verify_enabled();
     if (const char *vm = getenv("GDX_VERIFY_MIN"))
         if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
     return GDX_OK;
@@ -872,6 +875,7 @@ extern "C" gdx_status gdx_get_stats(gdx_stats *out) {
     *out = t_stats;
     return GDX_OK;
 }
+extern "C" uint32_t gdx_host_pool_resize(uint32_t threads) { return HostPool::get().resize(threads); }
 extern "C" gdx_status gdx_host_alloc(uint64_t bytes, void **out) {
     if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
     CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));
@@ -1392,6 +1396,14 @@ extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t dep
     return build_seed_table(idx, (uint32_t)depth);
 }
 
+extern "C" gdx_status gdx_index_set_text_verification(gdx_index *idx, int32_t on) {
+    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index");
+    idx->verify = on != 0;
+    return GDX_OK;
+}
+
 extern "C" gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on) {
     if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
     std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
@@ -1664,7 +1676,7 @@ void launch_search(const gdx_index *idx, const DevQueries &dq, uint64_t *a, uint
                    const uint32_t *slot_map, cudaStream_t stream) {
     if (dq.nq == 0) return;
     const unsigned grid = (unsigned)div_up(dq.nq, 256);
-    const bool verify = idx->dev.text && verify_enabled();
+    const bool verify = idx->dev.text && idx->verify;
     const int mf = mode | (narrow ? kModeNarrow : 0);
 #define GDX_LAUNCH(V, C, P) k_search<L, V, C, P><<<grid, 256, 0, stream>>>(idx->dev, dq, a, b, mf, qbase, err, steps, perm, slot_map)
     if (dq.packed) {

@@ -74,13 +74,26 @@ static unsigned usable_cpus() {
     return h ? h : 1;
 }
 
-HostPool::HostPool() : impl_(new Impl()) {
-    // GDX_HOST_THREADS = total threads working on one staging job (default: the CPUs this process may run
-    // on, at most 32); bench.py gives every rank of a multi-process run its own share of the cores first
-    unsigned total = std::min(32u, usable_cpus());
-    if (const char *e = getenv("GDX_HOST_THREADS"))
-        if (atoi(e) > 0) total = (unsigned)atoi(e);
+HostPool::HostPool() : impl_(new Impl()) { resize(0); }
+
+// total = threads that work on one staging job incl. the caller; 0 = GDX_HOST_THREADS, else the CPUs the
+// calling thread may run on (new workers inherit its affinity), at most 32.  Not while jobs are running.
+unsigned HostPool::resize(unsigned total) {
+    {
+        std::lock_guard<std::mutex> lk(impl_->mu);
+        impl_->stop = true;
+    }
+    impl_->cv.notify_all();
+    for (auto &t : impl_->workers) t.join();
+    impl_->workers.clear();
+    impl_->stop = false;
+    if (total == 0) {
+        total = std::min(32u, usable_cpus());
+        if (const char *e = getenv("GDX_HOST_THREADS"))
+            if (atoi(e) > 0) total = (unsigned)atoi(e);
+    }
     for (unsigned i = 1; i < total; ++i) impl_->workers.emplace_back([this] { impl_->loop(); });
+    return threads();
 }
 
 HostPool::~HostPool() {

@@ -25,6 +25,7 @@ class HostPool {
 public:
     static HostPool &get();
     unsigned threads() const;  // workers + the calling thread
+    unsigned resize(unsigned total);  // see host_pack.cpp; returns threads()
     // fn(piece) for every piece in [0, pieces); the caller works too; returns when all pieces are done
     void parallel_for(uint64_t pieces, const std::function<void(uint64_t)> &fn);
     void copy(void *dst, const void *src, uint64_t bytes);

@@ -207,6 +207,10 @@ class FmIndex:
         """(Re)build the seed table accelerator at this depth now (raises if it does not fit); 0 frees it."""
         _check(self._lib.gdx_index_set_seed_table_depth(self._h, int(depth)))
 
+    def set_text_verification(self, on: bool = True) -> None:
+        """Finish one-row intervals through the text (default) or run every LF step like the reference."""
+        _check(self._lib.gdx_index_set_text_verification(self._h, 1 if on else 0))
+
     def num_texts(self) -> int:
         return int(self.info().num_texts)
 

@@ -267,6 +267,13 @@ gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
  * GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  GDX_ERR_BUSY as above. */
 gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth);
 
+/* Text verification (needs the text section of the image, i.e. no GDX_FLAG_NO_TEXT): count / locate finish an
+ * interval that has narrowed to one row by resolving SA[row] and comparing the rest of the query with the
+ * text instead of one LF step per remaining symbol.  On by default (GDX_VERIFY=0 changes the default);
+ * on == 0 makes every query run every LF step, exactly the reference's sequence of rank queries
+ * (batch_computed_cursors.rs:62-70).  Results are identical either way.  GDX_ERR_BUSY as above. */
+gdx_status gdx_index_set_text_verification(gdx_index *idx, int32_t on);
+
 /* ---- index files: FmIndex::save_to_file / load_from_file (src/lib.rs:296-327) -------------------------
  * The crate serialises its host structs with the `savefile` crate (schema version 0); that byte format
  * is owned by an un-vendored dependency and no reference test pins it, so this is an own versioned
@@ -393,6 +400,12 @@ gdx_status gdx_locate_intervals_device(const gdx_index *idx, const uint64_t *d_s
                                        const uint64_t *d_ends, uint64_t n,
                                        const uint64_t *d_hit_offsets, uint64_t num_hits,
                                        gdx_hit *d_hits, void *stream);
+
+/* The staging thread pool (packing, copies between caller memory and pinned buffers) is created at first use
+ * with GDX_HOST_THREADS threads, default: the CPUs the creating thread may run on, at most 32.  This call
+ * re-creates it with `threads` threads (0 = the default rule, evaluated for the calling thread now); the new
+ * workers inherit the caller's CPU affinity.  Must not run concurrently with searches.  Returns the new size. */
+uint32_t gdx_host_pool_resize(uint32_t threads);
 
 /* pinned host memory helpers (full-speed asynchronous H2D/D2H) */
 gdx_status gdx_host_alloc(uint64_t bytes, void **out);

@@ -1072,3 +1072,166 @@ int gdxo_locate_many(const gdxo_index *idx, const uint8_t *qbytes, const uint64_
 }
 
 void gdxo_free_hits(gdxo_hit *hits) { free(hits); }
+
+/* ------------------------------------------------------------------------------------------------
+ * independent check of an index that was built from parts (gdx_oracle.h: gdxo_verify_against_text)
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct {
+    const gdxo_index *idx;
+    const uint8_t *T;
+    uint64_t n;
+    uint64_t *pos;     /* boundary positions, ascending */
+    uint64_t *row;     /* their rows, ~0 = not known */
+    uint64_t nb;
+    uint64_t *bitmap;  /* one bit per row */
+    uint64_t violations, visited;
+    pthread_mutex_t mu;
+} verify_ctx;
+
+/* order of two suffixes of T by plain comparison; the end of the text is smaller than any symbol
+ * (the libsais convention, construction/mod.rs:88-103) */
+static const uint8_t *g_sort_text;
+static uint64_t g_sort_n;
+static int suffix_cmp(const void *pa, const void *pb) {
+    uint64_t a = *(const uint64_t *)pa, b = *(const uint64_t *)pb;
+    if (a == b) return 0;
+    while (a < g_sort_n && b < g_sort_n) {
+        if (g_sort_text[a] != g_sort_text[b]) return g_sort_text[a] < g_sort_text[b] ? -1 : 1;
+        ++a;
+        ++b;
+    }
+    return a == g_sort_n ? -1 : 1;
+}
+
+/* row of the suffix starting at p by backward search of the sentinel-free symbols that follow
+ * (lib.rs:248-271 over dense symbols); ~0 when they are not unique before the next sentinel */
+static uint64_t row_by_search(const gdxo_index *idx, const uint8_t *T, uint64_t n, uint64_t p) {
+    for (uint64_t L = 32; L <= (1u << 16); L *= 2) {
+        uint64_t end = p + L < n ? p + L : n, stop = p;
+        while (stop < end && T[stop] != 0) ++stop;
+        if (stop == p) return ~0ull;
+        uint64_t s = 0, e = idx->n;
+        for (uint64_t r = stop; r-- > p && s != e;) extend_front_dense(idx, T[r], &s, &e);
+        if (e - s == 1) return s;
+        if (stop < end || end == n) return ~0ull; /* ran into a sentinel: longer patterns do not exist */
+    }
+    return ~0ull;
+}
+
+static void verify_search_range(uint64_t b, uint64_t e, int tid, void *vctx) {
+    (void)tid;
+    verify_ctx *c = (verify_ctx *)vctx;
+    for (uint64_t k = b; k < e; ++k)
+        if (c->row[k] == ~0ull && c->T[c->pos[k]] != 0) c->row[k] = row_by_search(c->idx, c->T, c->n, c->pos[k]);
+}
+
+static void verify_walk_range(uint64_t b, uint64_t e, int tid, void *vctx) {
+    (void)tid;
+    verify_ctx *c = (verify_ctx *)vctx;
+    const gdxo_index *idx = c->idx;
+    uint64_t bad = 0, seen = 0;
+    for (uint64_t k = b; k < e; ++k) {
+        if (c->row[k] == ~0ull) continue; /* no row of its own: covered by the walk from the boundary above */
+        uint64_t p = c->pos[k], row = c->row[k];
+        /* the next boundary below with a row of its own ends this walk */
+        uint64_t kb = k;
+        while (kb > 0 && c->row[kb - 1] == ~0ull) --kb;
+        const int has_lower = kb > 0;
+        const uint64_t lower_pos = has_lower ? c->pos[kb - 1] : 0, lower_row = has_lower ? c->row[kb - 1] : 0;
+        for (;;) {
+            if (row >= c->n) { ++bad; break; }
+            uint64_t old = __atomic_fetch_or(&c->bitmap[row >> 6], 1ull << (row & 63), __ATOMIC_RELAXED);
+            if (old & (1ull << (row & 63))) ++bad; /* a second suffix claims this row */
+            ++seen;
+            if (idx->samples.p && row % idx->sampling_rate == 0 &&
+                iarray_get(&idx->samples, row / idx->sampling_rate) != p)
+                ++bad; /* sampled_suffix_array.rs:27-54 */
+            const uint8_t sym = gdxo_rank_symbol_at(idx->rank, row);
+            const uint8_t want = p > 0 ? c->T[p - 1] : c->T[c->n - 1]; /* bwt.rs:96-105 */
+            if (sym != want) { ++bad; break; }
+            if (sym == 0) { /* a text starts here: bwt.rs:108-116 */
+                if (idx->n_border && border_lookup(idx, row) != p) ++bad;
+                break;
+            }
+            const uint64_t next = lf_mapping_step(idx, sym, row);
+            if (has_lower && p - 1 == lower_pos) {
+                if (next != lower_row) ++bad; /* the chain of walks must close on the searched rows */
+                break;
+            }
+            row = next;
+            --p;
+        }
+    }
+    pthread_mutex_lock(&c->mu);
+    c->violations += bad;
+    c->visited += seen;
+    pthread_mutex_unlock(&c->mu);
+}
+
+static int u64_cmp(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+int gdxo_verify_against_text(const gdxo_index *idx, const uint8_t *dense_text, uint64_t n, int nthreads,
+                             uint64_t *violations, uint64_t *rows_visited) {
+    if (violations) *violations = 0;
+    if (rows_visited) *rows_visited = 0;
+    if (n != idx->n || n == 0) {
+        if (violations) *violations = 1;
+        return GDXO_OK;
+    }
+    const uint64_t seg = n / 8192 > 4096 ? n / 8192 : 4096;
+    const uint64_t ncand = n / seg + 1;
+    verify_ctx c;
+    memset(&c, 0, sizeof c);
+    c.idx = idx;
+    c.T = dense_text;
+    c.n = n;
+    c.pos = (uint64_t *)malloc(8 * (size_t)(ncand + idx->ntexts));
+    c.row = (uint64_t *)malloc(8 * (size_t)(ncand + idx->ntexts));
+    c.bitmap = (uint64_t *)calloc((size_t)(n / 64 + 1), 8);
+    uint64_t *starts = (uint64_t *)malloc(8 * (size_t)idx->ntexts);
+    if (!c.pos || !c.row || !c.bitmap || !starts) {
+        free(c.pos); free(c.row); free(c.bitmap); free(starts);
+        return GDXO_ERR_ALLOC;
+    }
+    pthread_mutex_init(&c.mu, NULL);
+    /* rows of the sentinel suffixes, straight from the definition of the suffix order: the last sentinel is
+     * followed by the end of the text and sorts first, the others sort by the text that follows them */
+    uint64_t nstarts = 0;
+    for (uint64_t t = 0; t + 1 < idx->ntexts; ++t) starts[nstarts++] = idx->sentinels[t] + 1;
+    g_sort_text = dense_text;
+    g_sort_n = n;
+    qsort(starts, (size_t)nstarts, 8, suffix_cmp);
+    uint64_t nb = 0;
+    for (uint64_t k = 0; k < nstarts; ++k) {
+        c.pos[nb] = starts[k] - 1;
+        c.row[nb++] = 1 + k;
+    }
+    c.pos[nb] = n - 1;
+    c.row[nb++] = 0;
+    for (uint64_t k = 1; k * seg < n; ++k) {
+        if (dense_text[k * seg] == 0) continue;
+        c.pos[nb] = k * seg;
+        c.row[nb++] = ~0ull;
+    }
+    /* sort boundaries by position, carrying the rows along (pack both into pairs) */
+    uint64_t *pairs = (uint64_t *)malloc(16 * (size_t)nb);
+    if (!pairs) { free(c.pos); free(c.row); free(c.bitmap); free(starts); return GDXO_ERR_ALLOC; }
+    for (uint64_t k = 0; k < nb; ++k) { pairs[2 * k] = c.pos[k]; pairs[2 * k + 1] = c.row[k]; }
+    qsort(pairs, (size_t)nb, 16, u64_cmp);
+    for (uint64_t k = 0; k < nb; ++k) { c.pos[k] = pairs[2 * k]; c.row[k] = pairs[2 * k + 1]; }
+    free(pairs);
+    c.nb = nb;
+    parallel_ranges(nthreads, nb, 1, verify_search_range, &c);
+    /* the topmost boundary must own a row (it is the last sentinel, n - 1): every position is then covered */
+    parallel_ranges(nthreads, nb, 1, verify_walk_range, &c);
+    if (c.visited != n) c.violations += 1; /* some row was never reached */
+    if (violations) *violations = c.violations;
+    if (rows_visited) *rows_visited = c.visited;
+    pthread_mutex_destroy(&c.mu);
+    free(c.pos); free(c.row); free(c.bitmap); free(starts);
+    return GDXO_OK;
+}

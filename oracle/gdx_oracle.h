@@ -132,6 +132,18 @@ void gdxo_free_hits(gdxo_hit *hits);
 
 int gdxo_online_cores(void);
 
+/* Independent check of an index made with gdxo_from_parts (its BWT, suffix-array samples and border map come
+ * from somewhere else, e.g. from the product's device construction): are they the ones of `dense_text`
+ * (construction/mod.rs:255-308 output, n symbols incl. sentinels)?  The text is cut at every sentinel and every
+ * ~n/8192 symbols; the row of the suffix at each cut is found with the index' own backward search (sentinel
+ * rows: from the definition of the suffix order), then LF-walked down to the cut below.  Every row's BWT
+ * symbol must be the text symbol in front of the walked position (bwt.rs:93-105), every sampled row must hold
+ * that position (sampled_suffix_array.rs:27-54), every border row too (bwt.rs:108-116), every walk must land
+ * on the searched row of the cut below, and all n rows must be visited exactly once -- which pins the BWT and
+ * the samples to the text without trusting whoever built them.  O(n) LF steps, parallel over the cuts. */
+int gdxo_verify_against_text(const gdxo_index *idx, const uint8_t *dense_text, uint64_t n, int nthreads,
+                             uint64_t *violations, uint64_t *rows_visited);
+
 #ifdef __cplusplus
 }
 #endif

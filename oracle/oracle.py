@@ -105,6 +105,7 @@ def lib() -> C.CDLL:
         L.gdxo_locate_many.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, vp, C.POINTER(vp), u64p]
         L.gdxo_free_hits.argtypes = [vp]
         L.gdxo_online_cores.restype = C.c_int
+        L.gdxo_verify_against_text.argtypes = [vp, vp, C.c_uint64, C.c_int, u64p, u64p]
         _lib = L
     return _lib
 
@@ -252,6 +253,14 @@ class OracleIndex:
         if getattr(self, "h", None):
             lib().gdxo_free(self.h)
             self.h = None
+
+    def verify_against_text(self, dense_text: np.ndarray, nthreads: int = 0) -> tuple[int, int]:
+        """gdxo_verify_against_text -> (violations, rows visited): 0 and text_len for an index whose BWT,
+        samples and border map really belong to `dense_text`."""
+        t = np.ascontiguousarray(dense_text, dtype=np.uint8)
+        bad, seen = C.c_uint64(), C.c_uint64()
+        _check(lib().gdxo_verify_against_text(self.h, _ptr(t), t.size, nthreads, C.byref(bad), C.byref(seen)))
+        return int(bad.value), int(seen.value)
 
     # -- introspection
     @property

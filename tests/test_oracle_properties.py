@@ -6,6 +6,7 @@ src/text_with_rank_support/mod.rs:194-246, src/sampled_suffix_array.rs:181-195.
 import random
 
 import numpy as np
+import pytest
 from hypothesis import HealthCheck, given, settings
 from hypothesis import strategies as st
 
@@ -154,3 +155,46 @@ def test_from_parts_equals_build():
     qs = [bytes(rng.choice(b"ACGT") for _ in range(rng.randrange(12))) for _ in range(300)]
     assert a.locate_many(qs) == b.locate_many(qs, nthreads=4)
     assert a.count_many(qs).tolist() == b.count_many(qs, nthreads=3).tolist()
+
+
+# ---- gdxo_verify_against_text: the check that makes bench.py's CPU arm independent of whoever built its BWT ----
+def _parts_index(texts, alph, s=4, corrupt=None):
+    oa = O.ALPHABETS[alph]()
+    full = O.OracleIndex.build(texts, oa, "u32", sampling_rate=s, lookup_depth=0)
+    bwt = full.bwt().copy()
+    samples = full.samples().copy()
+    rows, pos = full.border()
+    if corrupt == "bwt":  # swap two different neighbouring symbols: same counts, wrong order
+        i = next(i for i in range(len(bwt) - 1) if bwt[i] != bwt[i + 1] and bwt[i] and bwt[i + 1])
+        bwt[i], bwt[i + 1] = bwt[i + 1], bwt[i]
+    if corrupt == "sample":
+        samples[len(samples) // 2] += 1
+    if corrupt == "border":
+        pos = pos.copy()
+        pos[0] += 1
+    part = O.OracleIndex.from_parts(bwt, oa, full.count_array(), full.sentinel_indices(), samples, s, rows, pos,
+                                    lookup_depth=0, storage="u32", nthreads=2)
+    return part, full.dense_text()
+
+
+@pytest.mark.parametrize("texts", [
+    [b"cccaaagggttt"], [b"ACGT" * 300], [b"", b"ACGTN", b"", b"ACGTN", b"GATTACA" * 40],
+    [bytes(random.Random(3).choice(b"ACGTN") for _ in range(30_000)), bytes(random.Random(4).choice(b"ACGT") for _ in range(9_000))],
+])
+def test_verify_against_text_accepts_the_true_index(texts):
+    part, dense = _parts_index(texts, "ascii_dna_with_n")
+    bad, seen = part.verify_against_text(dense, nthreads=3)
+    assert (bad, seen) == (0, len(dense))
+
+
+@pytest.mark.parametrize("corrupt", ["bwt", "sample", "border"])
+def test_verify_against_text_rejects_a_wrong_index(corrupt):
+    rng = random.Random(9)
+    texts = [bytes(rng.choice(b"ACGT") for _ in range(20_000)), bytes(rng.choice(b"ACGTN") for _ in range(5_000))]
+    part, dense = _parts_index(texts, "ascii_dna_with_n", corrupt=corrupt)
+    bad, _ = part.verify_against_text(dense, nthreads=2)
+    assert bad > 0
+    other = np.array(dense).copy()  # the right index against another text
+    other[100] = 1 + (other[100] % 4)
+    good, _ = _parts_index(texts, "ascii_dna_with_n")
+    assert good.verify_against_text(other, nthreads=2)[0] > 0
