@@ -22,6 +22,7 @@ GDX_FLAG_NO_INVERSE_SAMPLES = 4
 GDX_FLAG_NO_DENSE_SUFFIX_ARRAY = 8
 GDX_FLAG_NO_SEED_TABLE = 16
 GDX_QUERIES_IO_BYTES, GDX_QUERIES_PACKED_2BIT = 0, 1
+GDX_RANK_CONDENSED, GDX_RANK_FLAT = 0, 1
 GDX_NCCL_UNIQUE_ID_BYTES = 128
 GDX_ABI_VERSION = 2
 
@@ -55,7 +56,8 @@ class gdx_parts(C.Structure):
                 ("text_border_positions", C.c_void_p), ("num_text_borders", C.c_uint64),
                 ("sentinel_indices", C.c_void_p), ("num_texts", C.c_uint64),
                 ("lookup_table_depth", C.c_uint32), ("sampled_suffix_array_u32", C.c_void_p),
-                ("flags", C.c_uint32), ("accelerator_budget_bytes", C.c_uint64)]
+                ("flags", C.c_uint32), ("accelerator_budget_bytes", C.c_uint64),
+                ("rank_variant", C.c_uint32), ("block_bits", C.c_uint32)]
 
 
 class gdx_index_info(C.Structure):

@@ -1076,22 +1076,27 @@ extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_
     int device;
     GDX_TRY(resolve_device(device_req, &device));
     DeviceGuard guard(device);
-    // reference planes -> dense BWT on the device (condensed.rs:343-362), then the common path
-    const uint32_t nplanes = choose_layout(parts->alphabet.num_dense_symbols).planes;
-    const uint64_t nwords = div_up(src.n + 1, 64) * nplanes;
+    // the reference's blocks -> dense BWT on the device (symbol_at of the variant), then the common path
+    const uint32_t block_bits = parts->block_bits ? parts->block_bits : 64;
+    if ((block_bits != 64 && block_bits != 512) || parts->rank_variant > GDX_RANK_FLAT)
+        return fail(GDX_ERR_BAD_ARG, "rank_variant must be GDX_RANK_CONDENSED or GDX_RANK_FLAT, block_bits 64 or 512");
+    const bool flat = parts->rank_variant == GDX_RANK_FLAT;
+    const uint32_t words = block_bits / 64, used = block_bits - (flat ? 16 : 0);
+    const uint32_t units = flat ? parts->alphabet.num_dense_symbols : choose_layout(parts->alphabet.num_dense_symbols).planes;
+    const uint64_t nwords = div_up(src.n + 1, used) * units * words;
     uint64_t *d_blocks = nullptr;
     uint8_t *d_bwt = nullptr;
     CUDA_TRY(cudaMalloc(&d_blocks, nwords * 8));
     cudaError_t e = cudaMalloc(&d_bwt, src.n ? src.n : 1);
     if (e == cudaSuccess) e = cudaMemcpy(d_blocks, parts->interleaved_blocks, nwords * 8, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && src.n) {
-        k_planes_to_bwt<<<(unsigned)div_up(src.n, 256), 256>>>(d_blocks, nplanes, src.n, d_bwt);
+        k_ref_blocks_to_bwt<<<(unsigned)div_up(src.n, 256), 256>>>(d_blocks, flat ? 1u : 0u, words, units, src.n, d_bwt);
         e = cudaGetLastError();
     }
     cudaFree(d_blocks);
     if (e != cudaSuccess) {
         if (d_bwt) cudaFree(d_bwt);
-        return fail(GDX_ERR_CUDA, "plane upload failed: %s", cudaGetErrorString(e));
+        return fail(GDX_ERR_CUDA, "block upload failed: %s", cudaGetErrorString(e));
     }
     src.d_bwt = d_bwt;
     gdx_status st = build_image(src, device, out);

@@ -15,7 +15,7 @@
 //   k_pack_*        BWT -> rank records (+ per-superblock totals)        (condensed.rs:59-124,365-415)
 //   k_pack_text     dense text -> 4/8-bit text section
 //   k_lut_fill      lookup level d from level d-1            (lookup_table.rs:163-258)
-//   k_planes_to_bwt reference bit planes -> dense BWT        (condensed.rs:343-362)
+//   k_ref_blocks_to_bwt  the reference's block arrays (condensed / flat, Block64 / Block512) -> dense BWT
 //   k_records_to_bwt device records -> dense BWT (export)
 //   k_densify       SA[row] for every row from the sampled suffix array (accelerator)
 //   k_lut_extend    one level of the seed table (accelerator: a deeper lookup level outside the image)
@@ -1021,14 +1021,24 @@ k_lut_extend(const __grid_constant__ DevIndex ix, const void *__restrict__ prev,
         reinterpret_cast<uint2 *>(out)[i] = make_uint2((uint32_t)s, (uint32_t)e);
 }
 
-// condensed.rs:343-362 symbol_at over the reference's own plane array: [block][plane] u64
-__global__ void k_planes_to_bwt(const uint64_t *__restrict__ blocks, uint32_t nplanes, uint64_t n,
-                                uint8_t *__restrict__ bwt) {
+// symbol_at over the reference's own block arrays, any of its four rank variants (lib.rs:104-113):
+// condensed (condensed.rs:343-362): [group][plane] Blocks of `words` u64, bit j of the group = position j;
+// flat (flat.rs:248-267): [group][symbol] one-hot Blocks, position j at bit j + 16 (block.rs:3), `used` = NUM_BITS - 16
+__global__ void k_ref_blocks_to_bwt(const uint64_t *__restrict__ blocks, uint32_t flat, uint32_t words, uint32_t units,
+                                    uint64_t n, uint8_t *__restrict__ bwt) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint64_t *pl = blocks + (i >> 6) * nplanes;
+    const uint32_t used = words * 64 - (flat ? 16 : 0);
+    const uint64_t g = i / used;
+    const uint32_t bit = (uint32_t)(i % used) + (flat ? 16 : 0);
+    const uint64_t *grp = blocks + g * units * words + bit / 64;
     uint32_t s = 0;
-    for (uint32_t p = 0; p < nplanes; ++p) s |= (uint32_t)((pl[p] >> (i & 63)) & 1u) << p;
+    if (flat) {
+        for (uint32_t c = 0; c < units; ++c)
+            if ((grp[(uint64_t)c * words] >> (bit & 63)) & 1u) s = c;
+    } else {
+        for (uint32_t p = 0; p < units; ++p) s |= (uint32_t)((grp[(uint64_t)p * words] >> (bit & 63)) & 1u) << p;
+    }
     bwt[i] = (uint8_t)s;
 }
 

@@ -150,7 +150,19 @@ typedef struct gdx_parts {
     const uint32_t *sampled_suffix_array_u32;
     uint32_t flags;                       /* GDX_FLAG_NO_DENSE_SUFFIX_ARRAY | GDX_FLAG_NO_SEED_TABLE */
     uint64_t accelerator_budget_bytes;    /* as gdx_config.accelerator_budget_bytes                */
+    /* Which TextWithRankSupport `interleaved_blocks` comes from (the crate's four type aliases, lib.rs:104-113):
+     *   GDX_RANK_CONDENSED: [position group][bit plane] Blocks, NUM_BITS positions per group (condensed.rs:24-47);
+     *   GDX_RANK_FLAT:      [position group][dense symbol] one-hot Blocks, NUM_BITS - 16 positions per group, the
+     *                       bit of position j at index j + 16 of the Block, low 16 bits = block offset
+     *                       (flat.rs:24-52, block.rs:3,122-134).
+     * block_bits = Block::NUM_BITS: 64 (Block64) or 512 (Block512 = eight little-endian u64, block.rs:66-134);
+     * 0 means 64.  Every variant answers every rank identically (tests/text_with_rank_support.rs:69-75), so all
+     * of them become the same device records; block / superblock offsets are recomputed on the device. */
+    uint32_t rank_variant;
+    uint32_t block_bits;
 } gdx_parts;
+
+typedef enum gdx_rank_variant { GDX_RANK_CONDENSED = 0, GDX_RANK_FLAT = 1 } gdx_rank_variant;
 
 typedef struct gdx_index gdx_index;
 

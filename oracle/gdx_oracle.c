@@ -1074,6 +1074,153 @@ int gdxo_locate_many(const gdxo_index *idx, const uint8_t *qbytes, const uint64_
 void gdxo_free_hits(gdxo_hit *hits) { free(hits); }
 
 /* ------------------------------------------------------------------------------------------------
+ * the other TextWithRankSupport variants: Condensed<Block512>, Flat<Block64>, Flat<Block512>
+ * (lib.rs:104-113; block.rs:66-192; flat.rs; condensed.rs generic over B).  Restated by definition, in
+ * the reference's own array layouts, so that the product's ingestion of those arrays can be tested.
+ * ---------------------------------------------------------------------------------------------- */
+struct gdxo_vrank {
+    int variant;              /* GDXO_RANK_CONDENSED / GDXO_RANK_FLAT */
+    uint32_t block_bits, W;   /* Block::NUM_BITS (block.rs:29), NUM_U64 (:33) */
+    uint64_t text_len;
+    uint32_t sigma, planes;
+    uint64_t used_bits;       /* positions per block: NUM_BITS (condensed.rs:39-41) or NUM_BITS - 16 (flat.rs:43-45) */
+    uint64_t superblock_size; /* 65536 (condensed.rs:34) or (65536 / used) * used (flat.rs:76-77) */
+    uint64_t units;           /* blocks per position group: planes (condensed) or sigma (flat) */
+    uint64_t *blocks;         /* [group][unit][W] */
+    uint64_t n_block_words;
+    uint16_t *block_offsets;  /* condensed only: [group][symbol] */
+    uint64_t n_block_offsets;
+    iarray superblock_offsets;
+};
+
+static inline void vblock_set_bit(uint64_t *blk, uint64_t idx) { blk[idx / 64] |= 1ull << (idx % 64); } /* block.rs:104-108 */
+static inline uint32_t vblock_get_bit(const uint64_t *blk, uint64_t idx) { return (uint32_t)((blk[idx / 64] >> (idx % 64)) & 1u); }
+/* block.rs:110-120 + BLOCK512_MASKS (:194-226): ones in bits [0, idx) */
+static inline uint64_t vblock_count_ones_before(const uint64_t *blk, uint32_t W, uint64_t idx) {
+    uint64_t sum = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint64_t mask = idx >= 64ull * (w + 1) ? ~0ull : (idx > 64ull * w ? ~(~0ull << (idx - 64ull * w)) : 0ull);
+        sum += (uint64_t)__builtin_popcountll(blk[w] & mask);
+    }
+    return sum;
+}
+
+gdxo_vrank *gdxo_vrank_construct(const uint8_t *text, uint64_t n, uint32_t sigma, int storage, int variant,
+                                 uint32_t block_bits) {
+    if (sigma < 2 || (block_bits != 64 && block_bits != 512) || (variant != GDXO_RANK_CONDENSED && variant != GDXO_RANK_FLAT))
+        return NULL;
+    gdxo_vrank *r = (gdxo_vrank *)calloc(1, sizeof(*r));
+    if (!r) return NULL;
+    r->variant = variant;
+    r->block_bits = block_bits;
+    r->W = block_bits / 64;
+    r->text_len = n;
+    r->sigma = sigma;
+    r->planes = ilog2_ceil_for_nonzero(sigma);
+    r->used_bits = variant == GDXO_RANK_FLAT ? block_bits - 16 : block_bits;
+    r->superblock_size = variant == GDXO_RANK_FLAT ? (65536 / r->used_bits) * r->used_bits : 65536;
+    r->units = variant == GDXO_RANK_FLAT ? sigma : r->planes;
+    const uint64_t len = n + 1; /* condensed.rs:69, flat.rs:73: rank(idx) is defined for idx <= text_len */
+    const uint64_t groups = div_ceil(len, r->used_bits), nsb = div_ceil(len, r->superblock_size);
+    r->n_block_words = groups * r->units * r->W;
+    r->blocks = (uint64_t *)calloc(r->n_block_words ? r->n_block_words : 1, 8);
+    if (variant == GDXO_RANK_CONDENSED) {
+        r->n_block_offsets = groups * sigma;
+        r->block_offsets = (uint16_t *)calloc(r->n_block_offsets ? r->n_block_offsets : 1, 2);
+    }
+    uint64_t *in_sb = (uint64_t *)calloc(sigma, 8), *total = (uint64_t *)calloc(sigma, 8);
+    if (!r->blocks || iarray_alloc(&r->superblock_offsets, nsb * sigma, storage) || !in_sb || !total ||
+        (variant == GDXO_RANK_CONDENSED && !r->block_offsets)) {
+        free(in_sb);
+        free(total);
+        gdxo_vrank_free(r);
+        return NULL;
+    }
+    /* position by position: offsets are "how many c since the superblock began" at every group start, the
+     * superblock table "how many c before the superblock" (condensed.rs:104-116, flat.rs:107-118) */
+    for (uint64_t g = 0; g < groups; ++g) {
+        const uint64_t p0 = g * r->used_bits;
+        if (p0 % r->superblock_size == 0) {
+            for (uint32_t c = 0; c < sigma; ++c) {
+                iarray_set(&r->superblock_offsets, (p0 / r->superblock_size) * sigma + c, total[c]);
+                in_sb[c] = 0;
+            }
+        }
+        for (uint32_t c = 0; c < sigma; ++c) {
+            if (variant == GDXO_RANK_CONDENSED) r->block_offsets[g * sigma + c] = (uint16_t)in_sb[c];
+            else r->blocks[(g * sigma + c) * r->W] = in_sb[c]; /* block.rs:122-124 integrate_block_offset */
+        }
+        for (uint64_t j = 0; j < r->used_bits && p0 + j < n; ++j) {
+            const uint8_t sym = text[p0 + j];
+            in_sb[sym] += 1;
+            total[sym] += 1;
+            if (variant == GDXO_RANK_CONDENSED) {
+                for (uint32_t p = 0; p < r->planes; ++p)
+                    if ((sym >> p) & 1u) vblock_set_bit(r->blocks + (g * r->planes + p) * r->W, j); /* condensed.rs:393-396 */
+            } else {
+                vblock_set_bit(r->blocks + (g * sigma + sym) * r->W, j + 16); /* flat.rs:291 */
+            }
+        }
+    }
+    free(in_sb);
+    free(total);
+    return r;
+}
+
+void gdxo_vrank_free(gdxo_vrank *r) {
+    if (!r) return;
+    free(r->blocks);
+    free(r->block_offsets);
+    free(r->superblock_offsets.p);
+    free(r);
+}
+
+uint64_t gdxo_vrank_query(const gdxo_vrank *r, uint8_t symbol, uint64_t idx) {
+    const uint64_t sb = iarray_get(&r->superblock_offsets, (idx / r->superblock_size) * r->sigma + symbol);
+    const uint64_t g = idx / r->used_bits, in_block = idx % r->used_bits;
+    if (r->variant == GDXO_RANK_FLAT) { /* flat.rs:221-246 */
+        uint64_t blk[8];
+        memcpy(blk, r->blocks + (g * r->sigma + symbol) * r->W, 8 * r->W);
+        const uint64_t off = blk[0] & 0xffffull; /* block.rs:126-134 extract_block_offset_and_then_zeroize_it */
+        blk[0] &= ~0xffffull;
+        return sb + off + vblock_count_ones_before(blk, r->W, in_block + 16);
+    }
+    /* condensed.rs:291-341 */
+    uint64_t acc[8];
+    for (uint32_t w = 0; w < r->W; ++w) acc[w] = ~0ull;
+    uint32_t s = symbol;
+    for (uint32_t p = 0; p < r->planes; ++p, s >>= 1) {
+        const uint64_t *blk = r->blocks + (g * r->planes + p) * r->W;
+        for (uint32_t w = 0; w < r->W; ++w) acc[w] &= (s & 1u) ? blk[w] : ~blk[w];
+    }
+    return sb + r->block_offsets[g * r->sigma + symbol] + vblock_count_ones_before(acc, r->W, in_block);
+}
+
+uint8_t gdxo_vrank_symbol_at(const gdxo_vrank *r, uint64_t idx) {
+    const uint64_t g = idx / r->used_bits, in_block = idx % r->used_bits;
+    if (r->variant == GDXO_RANK_FLAT) { /* flat.rs:248-267 */
+        for (uint32_t c = 0; c < r->sigma; ++c)
+            if (vblock_get_bit(r->blocks + (g * r->sigma + c) * r->W, in_block + 16)) return (uint8_t)c;
+        return 0xff; /* unreachable!() in the reference */
+    }
+    uint32_t sym = 0; /* condensed.rs:343-362 */
+    for (uint32_t p = 0; p < r->planes; ++p) sym |= vblock_get_bit(r->blocks + (g * r->planes + p) * r->W, in_block) << p;
+    return (uint8_t)sym;
+}
+
+const uint64_t *gdxo_vrank_blocks(const gdxo_vrank *r, uint64_t *len_words) {
+    *len_words = r->n_block_words;
+    return r->blocks;
+}
+const uint16_t *gdxo_vrank_block_offsets(const gdxo_vrank *r, uint64_t *len) {
+    *len = r->n_block_offsets;
+    return r->block_offsets;
+}
+uint64_t gdxo_vrank_num_superblock_offsets(const gdxo_vrank *r) { return r->superblock_offsets.len; }
+uint64_t gdxo_vrank_superblock_offset(const gdxo_vrank *r, uint64_t k) { return iarray_get(&r->superblock_offsets, k); }
+uint64_t gdxo_vrank_superblock_size(const gdxo_vrank *r) { return r->superblock_size; }
+
+/* ------------------------------------------------------------------------------------------------
  * independent check of an index that was built from parts (gdx_oracle.h: gdxo_verify_against_text)
  * ---------------------------------------------------------------------------------------------- */
 

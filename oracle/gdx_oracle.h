@@ -98,6 +98,21 @@ uint8_t gdxo_rank_symbol_at(const gdxo_rank *r, uint64_t idx);              /* c
 void gdxo_rank_batch(const gdxo_rank *r, const uint8_t *symbols, uint64_t *starts, uint64_t *ends,
                      uint32_t nq);
 
+/* ---- the other rank variants behind the same trait (lib.rs:104-113): Condensed / Flat x Block64 / Block512,
+ * in the reference's own array layouts (condensed.rs:24-30, flat.rs:24-30, block.rs:66-192) --------------- */
+enum { GDXO_RANK_CONDENSED = 0, GDXO_RANK_FLAT = 1 };
+typedef struct gdxo_vrank gdxo_vrank;
+gdxo_vrank *gdxo_vrank_construct(const uint8_t *dense_text, uint64_t n, uint32_t sigma, int storage,
+                                 int variant, uint32_t block_bits /* 64 or 512 */);
+void gdxo_vrank_free(gdxo_vrank *r);
+uint64_t gdxo_vrank_query(const gdxo_vrank *r, uint8_t symbol, uint64_t idx); /* condensed.rs:291-341, flat.rs:221-246 */
+uint8_t gdxo_vrank_symbol_at(const gdxo_vrank *r, uint64_t idx);              /* condensed.rs:343-362, flat.rs:248-267 */
+const uint64_t *gdxo_vrank_blocks(const gdxo_vrank *r, uint64_t *len_words);  /* interleaved_blocks as u64 words */
+const uint16_t *gdxo_vrank_block_offsets(const gdxo_vrank *r, uint64_t *len); /* condensed only */
+uint64_t gdxo_vrank_num_superblock_offsets(const gdxo_vrank *r);
+uint64_t gdxo_vrank_superblock_offset(const gdxo_vrank *r, uint64_t k);
+uint64_t gdxo_vrank_superblock_size(const gdxo_vrank *r);
+
 /* ---- text id tree alone (text_id_search_tree.rs) ---------------------------------------------- */
 uint64_t gdxo_tree_lookup(const uint64_t *sentinel_indices, uint64_t ntexts, uint64_t pos);
 

@@ -95,6 +95,22 @@ def lib() -> C.CDLL:
         L.gdxo_rank_symbol_at.argtypes = [vp, C.c_uint64]
         L.gdxo_rank_symbol_at.restype = C.c_uint8
         L.gdxo_rank_batch.argtypes = [vp, vp, vp, vp, C.c_uint32]
+        L.gdxo_vrank_construct.argtypes = [vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_uint32]
+        L.gdxo_vrank_construct.restype = vp
+        L.gdxo_vrank_free.argtypes = [vp]
+        L.gdxo_vrank_query.argtypes = [vp, C.c_uint8, C.c_uint64]
+        L.gdxo_vrank_query.restype = C.c_uint64
+        L.gdxo_vrank_symbol_at.argtypes = [vp, C.c_uint64]
+        L.gdxo_vrank_symbol_at.restype = C.c_uint8
+        L.gdxo_vrank_blocks.argtypes = [vp, u64p]
+        L.gdxo_vrank_blocks.restype = u64p
+        L.gdxo_vrank_block_offsets.argtypes = [vp, u64p]
+        L.gdxo_vrank_block_offsets.restype = u16p
+        for name in ("gdxo_vrank_num_superblock_offsets", "gdxo_vrank_superblock_size"):
+            getattr(L, name).argtypes = [vp]
+            getattr(L, name).restype = C.c_uint64
+        L.gdxo_vrank_superblock_offset.argtypes = [vp, C.c_uint64]
+        L.gdxo_vrank_superblock_offset.restype = C.c_uint64
         L.gdxo_tree_lookup.argtypes = [vp, C.c_uint64, C.c_uint64]
         L.gdxo_tree_lookup.restype = C.c_uint64
         L.gdxo_cursor_for_query.argtypes = [vp, vp, C.c_uint64, u64p, u64p]
@@ -208,6 +224,49 @@ class OracleRank:
     def __del__(self):
         if getattr(self, "h", None):
             lib().gdxo_rank_free(self.h)
+            self.h = None
+
+
+class OracleVariantRank:
+    """TextWithRankSupport in any of the crate's four variants (lib.rs:104-113): variant "condensed" | "flat",
+    block_bits 64 | 512, arrays in the reference's own layout."""
+
+    def __init__(self, dense_text, sigma: int, storage: str = "i32", variant: str = "condensed", block_bits: int = 64):
+        t = np.ascontiguousarray(np.asarray(dense_text, dtype=np.uint8))
+        self.n, self.sigma, self.variant, self.block_bits = int(t.size), sigma, variant, block_bits
+        self.h = lib().gdxo_vrank_construct(_ptr(t) if t.size else None, t.size, sigma, STORAGE[storage],
+                                            0 if variant == "condensed" else 1, block_bits)
+        if not self.h:
+            raise ValueError("bad rank variant parameters")
+
+    def rank(self, symbol: int, idx: int) -> int:
+        return int(lib().gdxo_vrank_query(self.h, symbol, idx))
+
+    def symbol_at(self, idx: int) -> int:
+        return int(lib().gdxo_vrank_symbol_at(self.h, idx))
+
+    def blocks(self) -> np.ndarray:
+        n = C.c_uint64()
+        p = lib().gdxo_vrank_blocks(self.h, C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[: n.value].copy()
+
+    def block_offsets(self) -> np.ndarray:
+        n = C.c_uint64()
+        p = lib().gdxo_vrank_block_offsets(self.h, C.byref(n))
+        if not n.value:
+            return np.zeros(0, dtype=np.uint16)
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+
+    def superblock_offsets(self) -> np.ndarray:
+        k = int(lib().gdxo_vrank_num_superblock_offsets(self.h))
+        return np.array([lib().gdxo_vrank_superblock_offset(self.h, i) for i in range(k)], dtype=np.uint64)
+
+    def superblock_size(self) -> int:
+        return int(lib().gdxo_vrank_superblock_size(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().gdxo_vrank_free(self.h)
             self.h = None
 
 

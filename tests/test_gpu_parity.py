@@ -243,6 +243,49 @@ def test_from_reference_parts(gdx):
         util.assert_same_results(oidx, gdx.FmIndex(h2, util.product_alphabet(gdx, alph)), qs)
 
 
+@pytest.mark.parametrize("variant,block_bits", [("condensed", 64), ("condensed", 512), ("flat", 64), ("flat", 512)])
+def test_from_reference_parts_all_rank_variants(gdx, variant, block_bits):
+    """FmIndexCondensed64/512 and FmIndexFlat64/512 (lib.rs:104-113) hand over their own
+    interleaved_blocks (condensed.rs:24-30, flat.rs:24-30, block.rs:66-192; here made by the oracle's restatement
+    of those layouts) and the 32-bit suffix array samples as they are (sampled_suffix_array.rs:18-23)."""
+    rng = random.Random(block_bits + len(variant))
+    L = gdx._lib
+    for alph in ("ascii_dna_with_n", "protein20", "ascii_dna"):
+        oa = util.oracle_alphabet(alph)
+        texts = util.random_texts(rng, oa, 3, 70_000 if alph == "ascii_dna" else 6000)
+        oidx = O.OracleIndex.build(texts, oa, "u32", sampling_rate=3, lookup_depth=1)
+        vr = O.OracleVariantRank(oidx.bwt(), oa.sigma, "u32", variant, block_bits)
+        parts = L.gdx_parts()
+        C.memmove(parts.alphabet.io_to_dense, oa.io_to_dense.tobytes(), 256)
+        parts.alphabet.num_dense_symbols = oa.sigma
+        parts.alphabet.num_searchable_dense_symbols = oa.num_searchable
+        parts.storage = L.GDX_U32
+        parts.text_len = oidx.text_len
+        keep = dict(count=oidx.count_array(), blocks=vr.blocks(), ssa32=oidx.samples().astype(np.uint32),
+                    sent=oidx.sentinel_indices())
+        keep["rows"], keep["pos"] = oidx.border()
+        parts.count = keep["count"].ctypes.data
+        parts.interleaved_blocks = keep["blocks"].ctypes.data
+        parts.sampled_suffix_array_u32 = keep["ssa32"].ctypes.data
+        parts.sampling_rate = 3
+        parts.text_border_rows = keep["rows"].ctypes.data
+        parts.text_border_positions = keep["pos"].ctypes.data
+        parts.num_text_borders = keep["rows"].size
+        parts.sentinel_indices = keep["sent"].ctypes.data
+        parts.num_texts = keep["sent"].size
+        parts.lookup_table_depth = 1
+        parts.rank_variant = L.GDX_RANK_FLAT if variant == "flat" else L.GDX_RANK_CONDENSED
+        parts.block_bits = block_bits
+        parts.flags = L.GDX_FLAG_NO_SEED_TABLE
+        h = C.c_void_p()
+        assert L.load().gdx_index_create_from_parts(C.byref(parts), -1, C.byref(h)) == 0, L.load().gdx_last_error_message()
+        pidx = gdx.FmIndex(h, util.product_alphabet(gdx, alph))
+        assert pidx.info().seed_table_depth == 0  # the accelerator policy of the parts is honoured
+        assert np.array_equal(pidx.download_bwt(), oidx.bwt())
+        qs = util.random_queries(rng, oa, texts, 200, 100, 16, searchable_only=True)
+        util.assert_same_results(oidx, pidx, qs)
+
+
 def test_wide_intervals_and_cursor_batches(gdx):
     rng = random.Random(2)
     texts = [bytes(rng.choice(b"AC") for _ in range(20_000)), b"A" * 3000]

@@ -221,3 +221,49 @@ def test_invalid_symbol_panics_lazily():
     assert list(idx.count_many([b"XTT", b"ACG"])) == [0, 2]
     with pytest.raises(O.OraclePanic):
         idx.count_many([b"ACG", b"XGT"])
+
+
+# ---- the other three rank variants (lib.rs:104-113), same tests as the reference runs for all four:
+#      tests/text_with_rank_support.rs:69-119 test_different_block_sizes_against_naive ------------------------
+VARIANTS = [("condensed", 64, "i32"), ("condensed", 512, "u32"), ("flat", 64, "i64"), ("flat", 512, "i32")]
+
+
+def _check_variant_against_naive(text, sigma, variant, block_bits, storage):
+    r = O.OracleVariantRank(text, sigma, storage, variant, block_bits)
+    for i, s in enumerate(text):
+        assert r.symbol_at(i) == s
+    for symbol in range(sigma):
+        count = 0
+        for idx in range(len(text) + 1):
+            assert r.rank(symbol, idx) == count, (variant, block_bits, symbol, idx)
+            if idx < len(text) and text[idx] == symbol:
+                count += 1
+
+
+@pytest.mark.parametrize("variant,block_bits,storage", VARIANTS)
+def test_rank_variants_reference_kats(variant, block_bits, storage):
+    _check_variant_against_naive([], 2, variant, block_bits, storage)                 # :77-83 empty
+    _check_variant_against_naive(RANDOM_LENGTH_512, 27, variant, block_bits, storage)  # :91-119 random_length_512
+    r = O.OracleVariantRank([0] * 65536, 2, storage, variant, block_bits)              # :85-89 superblock_size_text...
+    for idx in list(range(0, 65537, 97)) + [65535, 65536]:
+        assert r.rank(0, idx) == idx and r.rank(1, idx) == 0
+
+
+def test_rank_variant_layouts():
+    """array shapes of the reference's own constructors (condensed.rs:69-77, flat.rs:73-83; block.rs:3,29-33)"""
+    rng = np.random.default_rng(1)
+    idx = O.OracleIndex.build([bytes(rng.choice(list(b"ACGTN"), 70_000).astype(np.uint8))],
+                              O.ALPHABETS["ascii_dna_with_n"](), "u32", 4, 0)
+    text = list(idx.bwt())
+    c64 = O.OracleVariantRank(text, 6, "u32", "condensed", 64)
+    assert np.array_equal(c64.blocks(), idx.blocks())  # == the pinned Block64 restatement inside the index
+    assert np.array_equal(c64.block_offsets(), idx.block_offsets())
+    assert np.array_equal(c64.superblock_offsets(), idx.superblock_offsets())
+    n1 = len(text) + 1
+    c512 = O.OracleVariantRank(text, 6, "u32", "condensed", 512)
+    assert c512.blocks().size == -(-n1 // 512) * 3 * 8 and c512.block_offsets().size == -(-n1 // 512) * 6
+    f64 = O.OracleVariantRank(text, 6, "u32", "flat", 64)
+    assert f64.superblock_size() == (65536 // 48) * 48 and f64.blocks().size == -(-n1 // 48) * 6
+    assert f64.superblock_offsets().size == -(-n1 // f64.superblock_size()) * 6 and f64.block_offsets().size == 0
+    f512 = O.OracleVariantRank(text, 6, "u32", "flat", 512)
+    assert f512.superblock_size() == (65536 // 496) * 496 and f512.blocks().size == -(-n1 // 496) * 6 * 8

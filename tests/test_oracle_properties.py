@@ -198,3 +198,20 @@ def test_verify_against_text_rejects_a_wrong_index(corrupt):
     other[100] = 1 + (other[100] % 4)
     good, _ = _parts_index(texts, "ascii_dna_with_n")
     assert good.verify_against_text(other, nthreads=2)[0] > 0
+
+
+# ---- tests/text_with_rank_support.rs:121-136 correctness_random_texts, for all four variants (:69-75) ----------
+@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(st.integers(1, 255).flatmap(lambda mx: st.tuples(st.lists(st.integers(0, mx), max_size=300), st.just(mx + 1))))
+def test_rank_variants_against_naive(case):
+    text, sigma = case
+    for variant, bits, storage in (("condensed", 64, "i32"), ("condensed", 512, "u32"), ("flat", 64, "i64"),
+                                   ("flat", 512, "i32")):
+        r = O.OracleVariantRank(text, sigma, storage, variant, bits)
+        occ = [0] * sigma
+        for idx in range(len(text) + 1):
+            for symbol in {0, sigma - 1, text[idx - 1] if idx else 0, text[idx] if idx < len(text) else 0}:
+                assert r.rank(symbol, idx) == occ[symbol], (variant, bits, symbol, idx)
+            if idx < len(text):
+                assert r.symbol_at(idx) == text[idx]
+                occ[text[idx]] += 1
