@@ -22,10 +22,11 @@ fn check(status: ffi::gdx_status) {
 }
 
 /// Drain `impl IntoIterator<Item = Q: AsRef<[u8]>>` into (bytes, offsets): the only host-side work.
-/// (Shown with `Vec` for brevity.  For full speed the shim packs into arenas from `gdx_host_alloc`
-/// -- pinned memory, reused across calls -- and passes pinned output buffers: the library then
-/// overlaps H2D, kernels and D2H chunk by chunk.  Pageable buffers work too: the library stages them
-/// through its own pinned buffers with a few host threads, at roughly 1.8x the pinned end-to-end time.)
+/// Plain `Vec`s are the intended form: for DNA alphabets the library packs the bytes to 2 bits per symbol
+/// with its own thread pool while it stages them into pinned memory (a quarter of the PCIe bytes), sends the
+/// offsets chunk-relative as u32 and brings counts back as u32 -- pinned caller buffers buy nothing there.
+/// Callers that already hold 2-bit packed reads set `encoding: GDX_QUERIES_PACKED_2BIT` (ideally in memory
+/// from `gdx_host_alloc`) and skip the packing stage.
 fn pack<Q: AsRef<[u8]>>(queries: impl IntoIterator<Item = Q>) -> (Vec<u8>, Vec<u64>) {
     let (mut bytes, mut offsets) = (Vec::new(), vec![0u64]);
     for q in queries { bytes.extend_from_slice(q.as_ref()); offsets.push(bytes.len() as u64); }
@@ -40,7 +41,8 @@ impl<I: IndexStorage, R: TextWithRankSupport<I>> FmIndex<I, R> {
         let (bytes, offsets) = pack(queries);
         let nq = offsets.len() - 1;
         let (mut starts, mut ends) = (vec![0u64; nq], vec![0u64; nq]);
-        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64 };
+        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64,
+                                   encoding: ffi::GDX_QUERIES_IO_BYTES, first_symbol: 0 };
         check(unsafe { ffi::gdx_cursors_many(self.device.0 .0, &q, starts.as_mut_ptr(), ends.as_mut_ptr()) });
         starts.into_iter().zip(ends).map(move |(s, e)| Cursor {
             index: self, interval: HalfOpenInterval { start: s as usize, end: e as usize } })
@@ -51,7 +53,8 @@ impl<I: IndexStorage, R: TextWithRankSupport<I>> FmIndex<I, R> {
         let (bytes, offsets) = pack(queries);
         let nq = offsets.len() - 1;
         let mut counts = vec![0u64; nq];
-        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64 };
+        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64,
+                                   encoding: ffi::GDX_QUERIES_IO_BYTES, first_symbol: 0 };
         check(unsafe { ffi::gdx_count_many(self.device.0 .0, &q, counts.as_mut_ptr()) });
         counts.into_iter().map(|c| c as usize)
     }
@@ -64,7 +67,8 @@ impl<I: IndexStorage, R: TextWithRankSupport<I>> FmIndex<I, R> {
         let nq = offsets.len() - 1;
         let mut hit_offsets = vec![0u64; nq + 1];
         let (mut hits, mut n) = (std::ptr::null_mut(), 0u64);
-        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64 };
+        let q = ffi::gdx_queries { bytes: bytes.as_ptr(), offsets: offsets.as_ptr(), fixed_len: 0, nq: nq as u64,
+                                   encoding: ffi::GDX_QUERIES_IO_BYTES, first_symbol: 0 };
         check(unsafe { ffi::gdx_locate_many(self.device.0 .0, &q, hit_offsets.as_mut_ptr(), &mut hits, &mut n) });
         let owned: Vec<Hit> = unsafe { std::slice::from_raw_parts(hits, n as usize) }
             .iter().map(|h| Hit { text_id: h.text_id as usize, position: h.position as usize }).collect();

@@ -7,6 +7,7 @@ import os
 import random
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -383,3 +384,19 @@ def test_shard_range_is_contiguous_and_balanced():
                 prev_end = e.value
                 sizes.append(e.value - b.value)
             assert prev_end == n and max(sizes) - min(sizes) <= 1
+
+
+def test_rust_binding_is_generated_from_the_header():
+    """rust/src/gpu/ffi.rs (the reference-side `extern "C"` block of INTEGRATION.md) is generated from
+    include/genedex_b200.h: the file on disk must be the generator's output and name every exported symbol."""
+    import genedex_b200 as gdx
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rust = open(os.path.join(ROOT, "rust", "src", "gpu", "ffi.rs")).read()
+    declared_in_rust = set(re.findall(r"pub fn (gdx_\w+)\(", rust))
+    assert declared_in_rust == set(gdx._lib.PROTOTYPES), declared_in_rust ^ set(gdx._lib.PROTOTYPES)
+    # the wrapper module only calls functions the binding declares
+    used = set(re.findall(r"ffi::(gdx_\w+)\(", open(os.path.join(ROOT, "rust", "src", "gpu", "mod.rs")).read()))
+    assert used and used <= declared_in_rust
+    integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert set(re.findall(r"ffi::(gdx_\w+)\(", integ)) <= declared_in_rust
