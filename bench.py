@@ -382,7 +382,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- data: the whole batch is ONE array; a rank fills (and reads) only the range it owns ------------
     t_setup = time.perf_counter()
     text = make_text_on_device(args.text_len, args.n_fraction, dev)
-    q_all = np.empty(nq * m, dtype=np.uint8)          # ordinary host memory, like a Rust Vec<u8>
+    q_all = torch.empty(nq * m, dtype=torch.uint8).pin_memory().numpy()   # pinned host memory (the contract's e2e)
     origins = np.zeros(nq, dtype=np.int64)
     need_all = rank == 0 and world > 1 and not args.no_extras   # rank 0 also drives the single-process arm
     fill_query_range(text, q_all, origins, 0 if need_all else b, nq if need_all else e, m, dev)
@@ -447,8 +447,8 @@ def run_ours(args, rank, world, local_rank):
     kernel_ms, step_ms = device_steps(d_q, snq, m, steps)
     counts_device_path = d_counts[:snq].cpu().numpy().astype(np.uint64)
 
-    # ---- e2e: the whole batch through gdx_count_many_sharded from ordinary host memory ------------------
-    counts_all = np.zeros(nq, dtype=np.uint64)
+    # ---- e2e: the whole batch through gdx_count_many_sharded, pinned host buffers in and out ----------------
+    counts_all = torch.zeros(nq, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 
     def host_steps(fn, n_steps, n_warm=warm):
         for _ in range(n_warm):
@@ -476,12 +476,27 @@ def run_ours(args, rank, world, local_rank):
     d2h = reduce(float(st.d2h_bytes), "sum")
     e2e = {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": e2e_ms, "kernel_ms_inside": st.kernel_ms_search,
-           "host_buffers": "pageable (numpy); queries packed to 2 bits by the library's host thread pool inside the call",
+           "host_buffers": "pinned IO bytes in, pinned uint64 counts out; inside the call the library's host thread pool "
+                           "packs chunks to 2 bits while the PCIe link is busy and sends chunks as they are when it is idle",
            "packed_queries_per_step": int(reduce(float(st.packed_queries), "sum")),
            "host_pool_threads_per_rank": host_cores,
            "ms_per_step_by_rank_numa_cores": e2e_by_rank, "gpu_launches_per_step": int(reduce(float(st.kernel_launches), "sum"))}
 
     extras = not args.no_extras
+    # ---- e2e from ordinary (pageable) memory in and out: every byte is packed by the host pool ----------------
+    if extras and snq:
+        q_page = q_all[b * m:e * m].copy()
+        c_page = np.zeros(snq, dtype=np.uint64)
+        pg_ms, _ = host_steps(lambda: pidx.count_many_packed(q_page, None, m, snq, out=c_page), max(3, steps // 2), 2)
+        gst = pidx.stats()
+        assert np.array_equal(c_page, counts_all[b:e])
+        e2e["pageable"] = {"value": nq / (pg_ms * 1e-3), "unit": "queries/s", "ms_per_step": pg_ms,
+                           "h2d_bytes_per_step": int(reduce(float(gst.h2d_bytes), "sum")),
+                           "d2h_bytes_per_step": int(reduce(float(gst.d2h_bytes), "sum")),
+                           "packed_queries_per_step": int(reduce(float(gst.packed_queries), "sum")),
+                           "host_buffers": "ordinary numpy arrays in and out (a Rust Vec): all bytes packed by the host pool, "
+                                           "uint32 counts widened into the caller's array"}
+        del q_page, c_page
     # ---- e2e from pre-packed pinned reads (callers that keep their reads 2-bit packed) --------------------
     if extras and (b * m) % 4 == 0 and snq:
         packed_all = torch.empty((nq * m + 3) // 4 + 16, dtype=torch.uint8).pin_memory().numpy()

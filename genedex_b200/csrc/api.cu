@@ -217,6 +217,7 @@ struct Slot {
     std::vector<cudaEvent_t> ev_loc;  // pairs (begin, end) around the locate kernels of the current call
     size_t ev_loc_used = 0;
     cudaEvent_t ev_h2d = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_link = nullptr;  // the chunk's query upload has left the PCIe link
     bool h2d_pending = false;
     std::vector<cudaEvent_t> ev;  // pairs (begin, end) around the kernels of the current call
     size_t ev_used = 0;
@@ -241,6 +242,7 @@ struct Workspace {
             if (cudaEventCreateWithFlags(&s.ev_total, cudaEventDisableTiming) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming) != cudaSuccess) return false;
             if (cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&s.ev_link, cudaEventDisableTiming) != cudaSuccess) return false;
         }
         if (cudaMallocHost(&small.h, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
         if (cudaMalloc(&small.d, 16 * sizeof(uint64_t)) != cudaSuccess) return false;
@@ -261,6 +263,7 @@ struct Workspace {
             if (s.ev_total) cudaEventDestroy(s.ev_total);
             if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
             if (s.ev_out) cudaEventDestroy(s.ev_out);
+            if (s.ev_link) cudaEventDestroy(s.ev_link);
             for (HBuf *b : {&s.h_in, &s.h_off, &s.h_out_a, &s.h_out_b, &s.h_x}) b->release();
             s.xbuf.release();
             for (auto e : s.ev) cudaEventDestroy(e);
@@ -1822,6 +1825,20 @@ const uint64_t kPackMinBytes = env_bytes("GDX_PACK_MIN_BYTES", 1ull << 20);
 gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out, uint64_t *cap_out);
 void release_pinned_hits(const gdx_index *idx, void *p);
 
+// K3 + K4 over `n_hits` rows.  With a sampled suffix array (walks of geometric length) the compacting kernel
+// keeps every lane busy; with the dense array (one load per row) the plain one-thread-per-hit kernel is the
+// shorter program.  GDX_LOCATE_COMPACT=0/1 forces either for A/B runs.
+template <class L>
+void launch_locate_walk(const gdx_index *idx, const uint64_t *rows, uint64_t n_hits, ulonglong2 *hits,
+                        unsigned long long *d_walk, cudaStream_t stream) {
+    static const int forced = getenv("GDX_LOCATE_COMPACT") ? atoi(getenv("GDX_LOCATE_COMPACT")) : -1;
+    const bool compact = forced >= 0 ? forced != 0 : idx->dev.sampling_rate > 1;
+    if (compact)
+        k_locate_walk_compact<L><<<(unsigned)div_up(n_hits, kWalkSlice), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk);
+    else
+        k_locate_walk<L><<<(unsigned)div_up(n_hits, 256), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk);
+}
+
 // State of a pipelined gdx_locate_many: every chunk of the search pipeline continues, on its own
 // stream, with counts -> scan -> expand -> walk -> D2H of its hits, so that the locate kernels and the
 // hit copies of chunk k overlap the query upload of the later chunks.
@@ -1921,8 +1938,7 @@ struct LocatePipe {
             }
             unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 10);
             GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-                k_locate_walk<decltype(L)><<<(unsigned)div_up(n_hits, 256), 256, 0, sl.stream>>>(
-                    idx->dev, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk);
+                launch_locate_walk<decltype(L)>(idx, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk, sl.stream);
                 return GDX_OK;
             }));
             CUDA_TRY(cudaGetLastError());
@@ -1983,13 +1999,24 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     // thread pool; while they are staged, IO bytes of a <= 4-symbol alphabet are packed to 2 bits (a quarter
     // of the PCIe bytes) -- that pays for pinned caller buffers too.
     bool pack_on = nq && !prepacked && idx->pack.usable && pack_enabled() && total_in >= kPackMinBytes;
-    const bool stage_in = nq && total_in >= kStageMinBytes && !is_pinned(qs->bytes);
+    const bool src_pinned = nq && is_pinned(qs->bytes);
+    const bool stage_in = nq && total_in >= kStageMinBytes && !src_pinned;
+    // Pinned IO bytes can also cross the link as they are, by DMA, without any CPU work.  The host packer and
+    // the link then share the batch: a chunk is packed while the link is still busy with earlier chunks (the
+    // CPU has time to shrink it to a quarter) and goes raw when the link has run dry (waiting for the packer
+    // would idle it).  That balances itself on any mix of host cores and PCIe bandwidth.  GDX_PACK_HYBRID=0: off.
+    static const bool hybrid_enabled = env_flag("GDX_PACK_HYBRID", true);
+    const bool hybrid = pack_on && src_pinned && hybrid_enabled;
+    cudaEvent_t last_link = nullptr;
+    uint64_t raw_queries = 0;
     const bool stage_off = nq && qs->offsets && nq * 8 >= kStageMinBytes && !is_pinned(qs->offsets);
     const bool to_host = nq && !dev_a && !lp;
     const bool large_out = nq * 8 >= kStageMinBytes;
     // results as uint32 on the device: always for the u32 entry points, for large batches of the u64 ones
     // (widened by the pool while they are handed to the caller)
-    const bool narrow = to_host && !idx->h.wide && (out_elem == 4 || (large_out && narrow_enabled()));
+    // (pinned uint64 result arrays are filled by DMA without any CPU work: they stay 64-bit on the wire)
+    const bool narrow = to_host && !idx->h.wide &&
+                        (out_elem == 4 || (large_out && narrow_enabled() && !(is_pinned(out_a) && (mode != 0 || is_pinned(out_b)))));
     const bool widen = narrow && out_elem == 8;
     const bool stage_out = to_host && (widen || (large_out && !is_pinned(out_a)));
     const uint32_t dev_elem = narrow ? 4 : 8;
@@ -2022,7 +2049,9 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     while (q0 < nq) {
         // chunk [q0, q1): about `budget` input bytes (packed bytes count four-fold: the budget is PCIe time),
         // at least one query
-        const uint64_t unit = (pack_on || prepacked) ? 4 : 1;
+        bool pack_chunk = pack_on;
+        if (hybrid && pack_on && (!last_link || cudaEventQuery(last_link) == cudaSuccess)) pack_chunk = false;  // link idle
+        const uint64_t unit = (pack_chunk || prepacked) ? 4 : 1;
         const uint64_t remaining = sym_end - query_bytes_end(qs, q0);
         uint64_t want = budget * unit;
         if (remaining <= want) want = remaining > 2 * kChunkTail * unit ? remaining - kChunkTail * unit : remaining;
@@ -2072,7 +2101,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         bool used_staging = false;
         uint64_t nx = 0;  // queries of this chunk that go through the IO-byte kernel after the packed one
         bool chunk_packed = false;
-        if (nsym && pack_on) {
+        if (nsym && pack_chunk) {
             CUDA_TRY(sl.h_in.reserve((nsym + 3) / 4 + 8));
             pack2_parallel(idx->pack, qs->bytes + sym0, nsym, (uint8_t *)sl.h_in.p, exc);
             exc_q.clear();
@@ -2191,6 +2220,9 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             x_slots = reinterpret_cast<const uint32_t *>(sl.xbuf.as<uint8_t>() + off_slots);
             used_staging = true;
         }
+        CUDA_TRY(cudaEventRecord(sl.ev_link, sl.stream));
+        last_link = sl.ev_link;
+        if (!chunk_packed && !prepacked) raw_queries += cq;
         const double stage_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_stage0).count();
         uint64_t *a, *b;
         if (dev_a) {
@@ -2372,8 +2404,7 @@ gdx_status locate_device_intervals(const gdx_index *idx, Workspace *ws, const ui
         }
         unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 10);
         gdx_status s2 = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-            k_locate_walk<decltype(L)><<<(unsigned)div_up(total, 256), 256, 0, st>>>(
-                idx->dev, ws->rows.as<uint64_t>(), total, ws->hits.as<ulonglong2>(), d_walk);
+            launch_locate_walk<decltype(L)>(idx, ws->rows.as<uint64_t>(), total, ws->hits.as<ulonglong2>(), d_walk, st);
             return GDX_OK;
         });
         GDX_TRY(s2);
@@ -2937,8 +2968,7 @@ extern "C" gdx_status gdx_locate_intervals_device(const gdx_index *idx, const ui
         k_expand_big_rows<<<grid, 256, 0, st>>>(d_starts, d_ends, d_hit_offsets, big + 2, rows);
     }
     GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-        k_locate_walk<decltype(L)><<<(unsigned)div_up(num_hits, 256), 256, 0, st>>>(
-            idx->dev, rows, num_hits, reinterpret_cast<ulonglong2 *>(d_hits), nullptr);
+        launch_locate_walk<decltype(L)>(idx, rows, num_hits, reinterpret_cast<ulonglong2 *>(d_hits), nullptr, st);
         return GDX_OK;
     }));
     CUDA_TRY(cudaGetLastError());

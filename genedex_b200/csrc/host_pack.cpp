@@ -256,10 +256,46 @@ __attribute__((target("avx2"))) static void pack2_avx2(const PackTable &t, const
     if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
 }
 
+// the same 64 bytes at a time: in-lane nibble shuffles, a mask register for the validity, vpmovdb for the gather
+__attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackTable &t, const uint8_t *src, uint64_t n,
+                                                                     uint8_t *dst, uint64_t pos0, std::vector<uint64_t> &exc) {
+    const __m512i lo_tab = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)t.lo_class));
+    const __m512i hi_tab = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)t.hi_class));
+    const __m512i code_tab = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)t.code_lo));
+    const __m512i nib = _mm512_set1_epi8(0x0f);
+    const __m512i mul_1_4 = _mm512_set1_epi16(0x0401), mul_1_16 = _mm512_set1_epi32(0x00100001);
+    uint64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        const __m512i x = _mm512_loadu_si512((const void *)(src + i));
+        const __m512i lo = _mm512_and_si512(x, nib);
+        const __m512i hi = _mm512_and_si512(_mm512_srli_epi16(x, 4), nib);
+        const __m512i cls = _mm512_and_si512(_mm512_shuffle_epi8(lo_tab, lo), _mm512_shuffle_epi8(hi_tab, hi));
+        const __mmask64 valid = _mm512_test_epi8_mask(cls, cls);
+        __m512i code = _mm512_shuffle_epi8(code_tab, lo);
+        if (valid != ~(__mmask64)0) {
+            code = _mm512_maskz_mov_epi8(valid, code);
+            for (uint64_t mm = ~(uint64_t)valid; mm; mm &= mm - 1) exc.push_back(pos0 + i + (uint64_t)__builtin_ctzll(mm));
+        }
+        const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(code, mul_1_4), mul_1_16);
+        _mm_storeu_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
+    }
+    if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
+}
+
 void pack2_serial(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t pos0,
                   std::vector<uint64_t> &exceptions) {
-    static const bool have_avx2 = __builtin_cpu_supports("avx2") && !(getenv("GDX_PACK_SCALAR") && atoi(getenv("GDX_PACK_SCALAR")));
-    if (t.simd_ok && have_avx2) pack2_avx2(t, src, n, dst, pos0, exceptions);
+    // GDX_PACK_ISA = scalar | avx2 | avx512 caps the instruction set (tests, A/B runs); GDX_PACK_SCALAR=1 = scalar
+    static const int level = [] {
+        int lvl = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+        if (const char *e = getenv("GDX_PACK_ISA")) {
+            const int cap = !strcmp(e, "scalar") ? 0 : (!strcmp(e, "avx2") ? 1 : 2);
+            lvl = std::min(lvl, cap);
+        }
+        if (getenv("GDX_PACK_SCALAR") && atoi(getenv("GDX_PACK_SCALAR"))) lvl = 0;
+        return lvl;
+    }();
+    if (t.simd_ok && level == 2) pack2_avx512(t, src, n, dst, pos0, exceptions);
+    else if (t.simd_ok && level == 1) pack2_avx2(t, src, n, dst, pos0, exceptions);
     else pack2_scalar(t, src, n, dst, pos0, exceptions);
 }
 

@@ -893,6 +893,92 @@ k_locate_walk(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ 
     }
 }
 
+// The same with warp-level compaction of finished walks (north-star (3)): with row sampling a walk takes a
+// geometric number of LF steps (mean rate - 1, long tail), so in the one-thread-per-hit kernel most lanes of a
+// warp idle while its slowest walk finishes.  Here a lane that has finished takes the next unresolved hit of
+// its CTA's slice at once (one warp-aggregated atomic per refill), so every lane issues a record fetch in every
+// iteration; every hit is still written to its own slot, so the order of the results does not change.
+constexpr uint32_t kWalkSlice = 2048;  // hits per CTA slice
+template <class L>
+__global__ void __launch_bounds__(256)
+k_locate_walk_compact(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ rows, uint64_t nh,
+                      ulonglong2 *__restrict__ hits, unsigned long long *stat_steps) {
+    __shared__ uint32_t next;  // next unclaimed hit of the slice
+    const uint64_t slice0 = (uint64_t)blockIdx.x * kWalkSlice;
+    const uint32_t slice_n = (uint32_t)(nh - slice0 < kWalkSlice ? nh - slice0 : kWalkSlice);
+    if (threadIdx.x == 0) next = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    uint64_t h = 0, row = 0;
+    uint32_t steps = 0, total_steps = 0;
+    bool active = false;
+    for (;;) {
+        // refill idle lanes
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle) {
+            uint32_t base = 0;
+            if (lane == (uint32_t)(__ffs(idle) - 1)) base = atomicAdd(&next, (uint32_t)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, __ffs(idle) - 1);
+            if (!active) {
+                const uint32_t k = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                if (k < slice_n) {
+                    h = slice0 + k;
+                    row = rows[h];
+                    steps = 0;
+                    active = true;
+                }
+            }
+            if (__ballot_sync(0xffffffffu, active) == 0) break;  // slice exhausted and every walk finished
+        }
+        if (active) {
+            // one step of resolve_row (sampled_suffix_array.rs:110-138)
+            uint64_t pos = 0;
+            bool done = false;
+            if (row & kResolvedBit) {
+                pos = row & ~kResolvedBit;
+                done = true;
+            } else {
+                const bool sampled = ix.sampling_shift != 0xffffffffu ? (row & ((1ull << ix.sampling_shift) - 1)) == 0
+                                                                      : (row % ix.sampling_rate) == 0;
+                if (sampled) {
+                    const uint64_t k = ix.sampling_shift != 0xffffffffu ? row >> ix.sampling_shift : row / ix.sampling_rate;
+                    pos = (ix.wide ? __ldg(reinterpret_cast<const uint64_t *>(ix.samples) + k)
+                                   : (uint64_t)__ldg(reinterpret_cast<const uint32_t *>(ix.samples) + k)) + steps;
+                    done = true;
+                } else {
+                    typename L::Planes pl = L::load_planes_once(ix, row);
+                    const uint32_t c = L::symbol_at(pl, row);
+                    if (c == 0) {  // :121-126 text_border_lookup[&i]
+                        const uint64_t k = lower_bound_u64(ix.border_rows, ix.n_border, row);
+                        pos = __ldg(ix.border_pos + k) + steps;
+                        done = true;
+                    } else {
+                        if (c > ix.noff) {
+                            row = L::lf_derived(ix, row);
+                        } else {
+                            typename L::Rec r = L::with_offset(ix, pl, row, c);
+                            row = sbc_load(ix, row, c) + L::local_rank(r, c, row);
+                        }
+                        ++steps;
+                        ++total_steps;
+                    }
+                }
+            }
+            if (done) {
+                uint64_t id = lower_bound_u64(ix.sentinels, ix.ntexts, pos);  // text_id_search_tree.rs:35-64
+                if (id >= ix.ntexts) id = ix.ntexts - 1;
+                const uint64_t base = id == 0 ? 0 : __ldg(ix.sentinels + id - 1) + 1;
+                hits[h] = make_ulonglong2(id, pos - base);
+                active = false;
+            }
+        }
+    }
+    if (stat_steps) {
+        const uint32_t tot = __reduce_add_sync(0xffffffffu, total_steps);
+        if (lane == 0 && tot) atomicAdd(stat_steps, (unsigned long long)tot);
+    }
+}
+
 // ---- construction of the derived structures on the device --------------------------------------------
 // One CTA per superblock (65536 positions); thread t packs block t.  sb_tot[sb*noff + c-1] receives
 // the number of c in the superblock; k_sb_scan turns that into sbc (exclusive prefix + count[c]).

@@ -54,7 +54,7 @@ def test_replicate_over_nccl_and_sharded_search():
         assert r.info().seed_table_depth == pidx.info().seed_table_depth
     data, off = O.pack(qs)
     nq = len(qs)
-    want_s, want_e = oidx.cursors_many_packed(data, off, nthreads=0)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
     got = rs.count_many_packed(data, off)
     assert np.array_equal(got, want_e - want_s)
     assert rs.stats().shards == ndev

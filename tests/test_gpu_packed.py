@@ -58,7 +58,7 @@ def test_packed_host_path_matches_oracle(gdx, dna_case):
     c = dna_case
     oidx, pidx, data, off = c["oidx"], c["pidx"], c["data"], c["off"]
     nq = off.size - 1
-    want_s, want_e = oidx.cursors_many_packed(data, off, nthreads=0)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
     got = pidx.count_many_packed(data, off)
     st = pidx.stats()
     assert np.array_equal(got, want_e - want_s)
@@ -69,7 +69,7 @@ def test_packed_host_path_matches_oracle(gdx, dna_case):
     gs, ge = pidx.cursors_many_packed(data, off)
     assert np.array_equal(gs, want_s) and np.array_equal(ge, want_e)
     sub = 120_000
-    ooff, ohits = oidx.locate_many_packed(data[: int(off[sub])], off[: sub + 1], nthreads=0)
+    ooff, ohits = oidx.locate_many_packed(data[: int(off[sub])], off[: sub + 1])
     poff, phits = pidx.locate_many_packed(data[: int(off[sub])], off[: sub + 1])
     assert np.array_equal(ooff, poff) and np.array_equal(ohits, phits)
     assert pidx.stats().packed_queries == sub
@@ -79,7 +79,7 @@ def test_uint32_results(gdx, dna_case):
     c = dna_case
     oidx, pidx, data, off = c["oidx"], c["pidx"], c["data"], c["off"]
     nq = off.size - 1
-    want_s, want_e = oidx.cursors_many_packed(data, off, nthreads=0)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
     c32 = np.full(nq, 0xDEADBEEF, dtype=np.uint32)
     pidx.count_many_packed(data, off, out=c32)
     assert np.array_equal(c32.astype(np.uint64), want_e - want_s)
@@ -103,7 +103,7 @@ def test_packed_batch_reports_invalid_symbols_lazily(gdx, dna_case):
     absent = b"ACGT" * 12 + b"!!"          # '!' is left of where the interval of this random 48-mer is long empty...
     qs[30_000] = b"!" + b"ACGT" * 12 + b"A"   # ... so an invalid byte at the far left of an absent query is never reached
     data, off = O.pack(qs)
-    want = oidx.count_many_packed(data, off, nthreads=0)
+    want = oidx.count_many_packed(data, off)
     assert want[30_000] == 0
     assert np.array_equal(pidx.count_many_packed(data, off), want)
     assert pidx.stats().exception_queries == 1
@@ -112,7 +112,7 @@ def test_packed_batch_reports_invalid_symbols_lazily(gdx, dna_case):
     qs[59_999] = absent
     data, off = O.pack(qs)
     with pytest.raises(O.OraclePanic):
-        oidx.count_many_packed(data, off, nthreads=0)
+        oidx.count_many_packed(data, off)
     for call in (lambda: pidx.count_many_packed(data, off), lambda: pidx.cursors_many_packed(data, off),
                  lambda: pidx.locate_many_packed(data, off)):
         with pytest.raises(gdx.InvalidSymbolError) as ei:
@@ -126,7 +126,7 @@ def test_mostly_unencodable_batch_falls_back_to_io_bytes(gdx, dna_case):
     prng = random.Random(9)
     qs = [bytes(prng.choice(b"ACGTNN") for _ in range(40)) for _ in range(60_000)]
     data, off = O.pack(qs)
-    want = oidx.count_many_packed(data, off, nthreads=0)
+    want = oidx.count_many_packed(data, off)
     assert np.array_equal(pidx.count_many_packed(data, off), want)
     st = pidx.stats()
     assert st.packed_queries == 0 and st.exception_queries == 0
@@ -146,7 +146,7 @@ def test_prepacked_input_host_and_device(gdx, dna_case):
             qs.append(q)
     data, off = O.pack(qs)
     nq = len(qs)
-    want_s, want_e = oidx.cursors_many_packed(data, off, nthreads=0)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
     packed, first_bad = pidx.pack_queries_2bit(data, off)
     assert first_bad is None and packed.size == (int(off[-1]) + 3) // 4 + (-((int(off[-1]) + 3) // 4)) % 4
     enc = gdx._lib.GDX_QUERIES_PACKED_2BIT
@@ -155,7 +155,7 @@ def test_prepacked_input_host_and_device(gdx, dna_case):
     assert st.packed_queries == nq and st.exception_queries == 0 and st.h2d_bytes < data.size // 2
     gs, ge = pidx.cursors_many_packed(packed, off, encoding=enc)
     assert np.array_equal(gs, want_s) and np.array_equal(ge, want_e)
-    ooff, ohits = oidx.locate_many_packed(data, off, nthreads=0)
+    ooff, ohits = oidx.locate_many_packed(data, off)
     poff, phits = pidx.locate_many_packed(packed, off, encoding=enc)
     assert np.array_equal(ooff, poff) and np.array_equal(ohits, phits)
     # a batch with an unencodable byte is refused by the packer's report, not silently mis-searched
@@ -169,7 +169,7 @@ def test_prepacked_input_host_and_device(gdx, dna_case):
     fixed = [q for q in fixed if b"N" not in q][:120_001]
     fdata = np.frombuffer(b"".join(fixed), dtype=np.uint8)
     foff = np.arange(len(fixed) + 1, dtype=np.uint64) * m
-    fwant = oidx.count_many_packed(fdata, foff, nthreads=0)
+    fwant = oidx.count_many_packed(fdata, foff)
     fpacked, _ = pidx.pack_queries_2bit(fdata, None, m, len(fixed))
     assert np.array_equal(pidx.count_many_packed(fpacked, None, m, len(fixed), encoding=enc), fwant)
     # device-resident packed batch
@@ -195,7 +195,7 @@ def test_sharded_calls_on_one_device(gdx, dna_case):
     nq = off.size - 1
     rs = ReplicaSet.replicate(pidx, [0, 0])
     assert len(rs.replicas) == 3 and all(r.info().device == 0 for r in rs.replicas)
-    want_s, want_e = oidx.cursors_many_packed(data, off, nthreads=0)
+    want_s, want_e = oidx.cursors_many_packed(data, off)
     got = rs.count_many_packed(data, off)
     assert np.array_equal(got, want_e - want_s)
     st = rs.stats()
@@ -204,7 +204,7 @@ def test_sharded_calls_on_one_device(gdx, dna_case):
     assert np.array_equal(gs, want_s) and np.array_equal(ge, want_e)
     sub = 150_001
     sdata, soff = data[: int(off[sub])], off[: sub + 1]
-    ooff, ohits = oidx.locate_many_packed(sdata, soff, nthreads=0)
+    ooff, ohits = oidx.locate_many_packed(sdata, soff)
     hit_off, views, first, release = rs.locate_many_view(sdata, soff)
     try:
         assert np.array_equal(hit_off, ooff)

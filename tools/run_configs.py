@@ -46,6 +46,51 @@ def make_protein_text(n, dev, seed):
     return out
 
 
+def make_repeat_rich_text(n, dev, seed=0x5EED0011):
+    """hg38-like repeat content on top of bench.make_text_on_device's iid text: ~40 % of the symbols come from
+    repeat families -- Alu-like (300 bp, 10 subfamilies, ~29 % of the text), L1-like (6 kbp, 5 subfamilies, ~10 %)
+    and segmental duplications (20 kbp copies of other text at 1-2 % divergence, ~1.3 %) -- every copy with its
+    own substitution rate drawn from 5-15 %.  Returns (text, fraction of symbols written by a repeat copy)."""
+    torch = _torch()
+    import bench
+    text = bench.make_text_on_device(n, 0.05, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=dev)
+    covered = torch.zeros(n, dtype=torch.bool, device=dev)
+
+    def plant(unit_len, n_sub, n_copies, dmin, dmax, source=None):
+        cons = lut[torch.randint(0, 4, (n_sub, unit_len), generator=g, device=dev)]
+        ar = torch.arange(unit_len, device=dev)
+        batch = max(1, (1 << 26) // unit_len)
+        for b0 in range(0, n_copies, batch):
+            k = min(batch, n_copies - b0)
+            pos = torch.randint(0, n - unit_len, (k,), generator=g, device=dev)
+            if source is None:
+                data = cons[torch.randint(0, n_sub, (k,), generator=g, device=dev)]
+            else:  # copies of existing text (segmental duplications)
+                src = torch.randint(0, n - unit_len, (k,), generator=g, device=dev)
+                data = text[src[:, None] + ar[None, :]]
+                data = torch.where(data == bench.N_CODE, lut[0], data)
+            d = dmin + (dmax - dmin) * torch.rand((k, 1), generator=g, device=dev)
+            mut = torch.rand((k, unit_len), generator=g, device=dev) < d
+            rnd = lut[torch.randint(0, 4, (k, unit_len), generator=g, device=dev)]
+            data = torch.where(mut, rnd, data)
+            idx = (pos[:, None] + ar[None, :]).reshape(-1)
+            text[idx] = data.reshape(-1)
+            covered[idx] = True
+            del data, mut, rnd, idx
+
+    scale = n / 3_100_000_000
+    plant(300, 10, int(3_000_000 * scale), 0.05, 0.15)
+    plant(6000, 5, int(50_000 * scale), 0.05, 0.15)
+    plant(20_000, 1, int(2_000 * scale), 0.01, 0.02, source=True)
+    frac = float(covered.float().mean().item())
+    del covered
+    torch.cuda.empty_cache()
+    return text, frac
+
+
 def sample_windows(text, text_offsets, nq, m, seed, dev, forbidden=None):
     """nq windows of length m that lie inside one text and do not contain `forbidden`;
     returns (query bytes [nq*m], text ids, positions in text)."""
@@ -160,9 +205,25 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
     res = {"config": name, "text_len": int(info.text_len), "num_texts": int(info.num_texts), "queries": nq,
            "query_len": m, "lookup_depth": depth, "sampling_rate": s, "sigma": int(info.num_dense_symbols),
            "rank_record_bytes": int(info.rank_record_bytes), "index_bytes": int(info.image_bytes),
-           "build_s": round(build_s, 2), "lf_steps": int(st.lf_steps),
+           "build_s": round(build_s, 2), "lf_steps": int(st.lf_steps), "verified_queries": int(st.verified_queries),
+           "verify_walk_steps": int(st.walk_steps), "seed_table_depth": int(info.seed_table_depth),
+           "dense_suffix_array_bytes": int(info.dense_suffix_array_bytes),
+           "packed_queries": int(st.packed_queries), "exception_queries": int(st.exception_queries),
+           "h2d_bytes": int(st.h2d_bytes), "d2h_bytes": int(st.d2h_bytes),
            "count_kernel_ms": round(kernel_ms, 3), "count_queries_per_s": nq / (kernel_ms * 1e-3),
            "count_e2e_ms": round(e2e_ms, 3), "count_e2e_queries_per_s": nq / (e2e_ms * 1e-3)}
+    # SURVEY 8d algorithmic bytes of the count launch: m + 8 [table entry] + 2*R*steps + 16 per query,
+    # + R per verify-walk step + 64 per text-verified query
+    R = int(info.rank_record_bytes)
+    tdepth = max(depth, int(info.seed_table_depth) if m >= int(info.seed_table_depth) else 0)
+    alg = nq * (m + 16 + (8 if tdepth else 0)) + 2 * R * int(st.lf_steps) + R * int(st.walk_steps) + 64 * int(st.verified_queries)
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    res["roofline"] = {"bound": "hbm", "algorithmic_bytes": alg, "achieved": alg / (kernel_ms * 1e-3) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": alg / (kernel_ms * 1e-3) / 1e9 / peak,
+                       "rank_queries_per_s": 2 * int(st.lf_steps) / (kernel_ms * 1e-3)}
     n_orig = 0 if origin is None else int(origin[0].size)
     if n_orig:
         assert int(counts[:n_orig].min()) >= 1, f"{name}: a query sampled from the text has count 0"
@@ -279,7 +340,24 @@ def run(configs, scale=1.0):
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     out = []
-    dna = [c for c in configs if c.startswith("c2") or c == "c3"]
+    if "c2r" in configs:  # repeat-rich variant of C2 (round-1 review: iid text is the shortcut's best case)
+        n = int(3_100_000_000 * scale)
+        nq, m = int(7_500_000 * scale), 50
+        text, frac = make_repeat_rich_text(n, dev)
+        host = text.cpu().numpy()
+        offs = np.array([0, n], dtype=np.int64)
+        q, tid, pos = sample_windows(text, offs, nq, m, bench.QUERY_SEED, dev, forbidden=bench.N_CODE)
+        origin = (tid.cpu().numpy(), pos.cpu().numpy())
+        del text
+        torch.cuda.empty_cache()
+        res = run_case("c2r", gdx, host, offs, gdx.alphabet.ascii_dna_with_n(), O.ALPHABETS["ascii_dna_with_n"](), q, m,
+                       nq, 0, 4, origin=origin, locate=True, verify_text=dna_fold)
+        res["repeat_fraction_of_text"] = round(frac, 3)
+        out.append(res)
+        yield res
+        del q, host
+        torch.cuda.empty_cache()
+    dna = [c for c in configs if (c.startswith("c2") and c != "c2r") or c == "c3"]
     if dna:
         n = int(3_100_000_000 * scale)
         nq, m = int(7_500_000 * scale), 50
