@@ -40,6 +40,9 @@
 
 #include "device_index.h"
 
+#ifndef GDX_KG5_VERIFY_MIN_BLOCKS
+#define GDX_KG5_VERIFY_MIN_BLOCKS 5
+#endif
 #ifndef GDX_K32_VERIFY_MIN_BLOCKS
 #define GDX_K32_VERIFY_MIN_BLOCKS 6
 #endif
@@ -205,31 +208,51 @@ struct K32 {
 template <int B>
 struct KG {
     static constexpr uint32_t kLog2P = 7;
-    static constexpr int kSearchMinBlocks = B <= 3 ? 5 : (B <= 5 ? 4 : 3);
-    static constexpr int kVerifyMinBlocks = kSearchMinBlocks;
+    static constexpr int kSearchMinBlocks = B <= 3 ? 5 : (B <= 5 ? 5 : 3);
+    static constexpr int kVerifyMinBlocks = B <= 3 ? 5 : (B <= 5 ? GDX_KG5_VERIFY_MIN_BLOCKS : 3);
+    // The record is fetched as whole 32 B sectors: kSectors 256-bit loads cover the B planes (16 B each) and the
+    // first u16 offsets behind them; an offset further back costs one more 2-byte load from the same line.
+    // (Protein, B = 5: 3 sector requests instead of five 128-bit ones + the offset -- the random-access ceiling
+    // of the part counts sector requests, profiles/r1_gather_ceiling.json.)
+    static constexpr int kSectors = (16 * B + 31) / 32;
+    static constexpr int kWords = 4 * kSectors;           // u64 words held in registers
+    static constexpr uint32_t kOffsetsInRegs = (32 * kSectors - 16 * B) / 2;  // offsets of symbols 1..this many
     struct Planes {
-        uint64_t lo[B], hi[B];
+        uint64_t w[kWords];
     };
     struct Rec {
-        uint64_t lo[B], hi[B];
+        uint64_t w[kWords];
         uint32_t off;
     };
     static __device__ __forceinline__ const uint8_t *rec_ptr(const DevIndex &ix, uint64_t i) {
         return ix.records + (i >> 7) * ix.stride;
     }
+    static __device__ __forceinline__ void load_words(const uint8_t *p, uint64_t *w) {
+#pragma unroll
+        for (int k = 0; k < kSectors; ++k) ldg256_na(p + 32 * k, w + 4 * k);
+    }
+    static __device__ __forceinline__ uint32_t offset_of(const uint8_t *p, const uint64_t *w, uint32_t c) {
+        if (kOffsetsInRegs > 0 && c <= kOffsetsInRegs) {
+            uint32_t v = 0;  // compile-time word indices only: a run-time index would push the record to local memory
+#pragma unroll
+            for (uint32_t j = 0; j < kOffsetsInRegs; ++j) {
+                const uint32_t byte = 16 * B + 2 * j;  // position of the offset inside the loaded sectors
+                if (c - 1 == j) v = (uint32_t)(w[byte >> 3] >> ((byte & 7) * 8)) & 0xffffu;
+            }
+            return v;
+        }
+        return __ldg(reinterpret_cast<const uint16_t *>(p + 16 * B) + (c - 1));
+    }
     static __device__ __forceinline__ Planes load_planes(const DevIndex &ix, uint64_t i) {
         Planes r;
-        const uint8_t *p = rec_ptr(ix, i);
-#pragma unroll
-        for (int k = 0; k < B; ++k) ldg128_na(p + 16 * k, r.lo[k], r.hi[k]);
+        load_words(rec_ptr(ix, i), r.w);
         return r;
     }
     static __device__ __forceinline__ Rec load(const DevIndex &ix, uint64_t i, uint32_t c) {
         Rec r;
         const uint8_t *p = rec_ptr(ix, i);
-#pragma unroll
-        for (int k = 0; k < B; ++k) ldg128_na(p + 16 * k, r.lo[k], r.hi[k]);
-        r.off = __ldg(reinterpret_cast<const uint16_t *>(p + 16 * B) + (c - 1));
+        load_words(p, r.w);
+        r.off = offset_of(p, r.w, c);
         return r;
     }
     static __device__ __forceinline__ Rec load_once(const DevIndex &ix, uint64_t i, uint32_t c) { return load(ix, i, c); }
@@ -238,18 +261,29 @@ struct KG {
                                                       uint32_t c) {
         Rec r;
 #pragma unroll
-        for (int k = 0; k < B; ++k) {
-            r.lo[k] = pl.lo[k];
-            r.hi[k] = pl.hi[k];
-        }
-        r.off = __ldg(reinterpret_cast<const uint16_t *>(rec_ptr(ix, i) + 16 * B) + (c - 1));
+        for (int k = 0; k < kWords; ++k) r.w[k] = pl.w[k];
+        r.off = offset_of(rec_ptr(ix, i), pl.w, c);
         return r;
     }
+    // plane p = words 2p (positions 0..63) and 2p + 1 (64..127)
     static __device__ __forceinline__ uint32_t symbol_at(const Planes &p, uint64_t i) {
-        return kg_symbol_at<B>(p.lo, p.hi, (uint32_t)(i & 127));
+        const uint32_t bit = (uint32_t)(i & 127), sh = bit & 63u, hi = bit >> 6;
+        uint32_t s = 0;
+#pragma unroll
+        for (int k = 0; k < B; ++k) s |= (uint32_t)(((hi ? p.w[2 * k + 1] : p.w[2 * k]) >> sh) & 1u) << k;
+        return s;
     }
     static __device__ __forceinline__ uint32_t local_rank(const Rec &r, uint32_t c, uint64_t i) {
-        return r.off + kg_block_count<B>(r.lo, r.hi, c, (uint32_t)(i & 127));
+        const uint32_t bit = (uint32_t)(i & 127);
+        uint64_t mlo = ~0ull, mhi = ~0ull;
+#pragma unroll
+        for (int k = 0; k < B; ++k) {
+            const bool one = (c >> k) & 1u;
+            mlo &= one ? r.w[2 * k] : ~r.w[2 * k];
+            mhi &= one ? r.w[2 * k + 1] : ~r.w[2 * k + 1];
+        }
+        const uint64_t masklo = below(bit), maskhi = bit > 64 ? below(bit - 64) : 0ull;
+        return r.off + (uint32_t)(popc64(mlo & masklo) + popc64(mhi & maskhi));
     }
     static __device__ __forceinline__ uint64_t lf_derived(const DevIndex &, uint64_t i) { return i; }
 };
