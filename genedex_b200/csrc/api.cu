@@ -541,6 +541,9 @@ gdx_status init_policies(gdx_index *idx) {
     idx->verify = verify_enabled();
     if (const char *vm = getenv("GDX_VERIFY_MIN"))
         if (atoi(vm) > 0) idx->dev.verify_min_remaining = (uint32_t)atoi(vm);
+    // count: also finish intervals of up to this many rows by text comparisons (A/B: profiles/README.md)
+    if (const char *vr = getenv("GDX_VERIFY_ROWS"))
+        if (atoi(vr) > 0) idx->dev.verify_max_rows = (uint32_t)std::min(atoi(vr), 64);
     return GDX_OK;
 }
 
@@ -2002,13 +2005,31 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     const bool src_pinned = nq && is_pinned(qs->bytes);
     const bool stage_in = nq && total_in >= kStageMinBytes && !src_pinned;
     // Pinned IO bytes can also cross the link as they are, by DMA, without any CPU work.  The host packer and
-    // the link then share the batch: a chunk is packed while the link is still busy with earlier chunks (the
-    // CPU has time to shrink it to a quarter) and goes raw when the link has run dry (waiting for the packer
-    // would idle it).  That balances itself on any mix of host cores and PCIe bandwidth.  GDX_PACK_HYBRID=0: off.
+    // the link then share the batch: before the pool starts on a packed chunk (which keeps the CPU busy for
+    // t_pack), a raw chunk is put on the link that is just large enough to keep it busy for that long on top of
+    // what is still queued there.  The queue is observed (events behind every upload), so a wrong guess of
+    // either rate corrects itself: too much raw data -> the backlog grows -> the next raw chunks shrink.
+    // GDX_PACK_HYBRID=0: every chunk is packed.  GDX_LINK_GBS: initial guess of the link rate (default 50).
     static const bool hybrid_enabled = env_flag("GDX_PACK_HYBRID", true);
+    static const double link_guess = (double)env_bytes("GDX_LINK_GBS", 50) * 1e6;  // bytes per ms
     const bool hybrid = pack_on && src_pinned && hybrid_enabled;
-    cudaEvent_t last_link = nullptr;
-    uint64_t raw_queries = 0;
+    struct Upload {
+        int slot;
+        uint64_t bytes;
+    };
+    std::vector<Upload> on_link;  // uploads issued, oldest first; retired when their event has fired
+    auto link_backlog = [&]() -> uint64_t {
+        size_t done = 0;
+        while (done < on_link.size() && cudaEventQuery(ws->slot[on_link[done].slot].ev_link) == cudaSuccess) ++done;
+        on_link.erase(on_link.begin(), on_link.begin() + done);
+        uint64_t b = 0;
+        for (const Upload &u : on_link) b += u.bytes;
+        return b;
+    };
+    double pack_rate = 4.0e6 * HostPool::get().threads();  // symbols per ms, refined from every packed chunk
+    bool raw_next = hybrid;                                  // the link is idle at the start: open with a raw chunk
+    uint64_t raw_want = kChunkFirst;
+
     const bool stage_off = nq && qs->offsets && nq * 8 >= kStageMinBytes && !is_pinned(qs->offsets);
     const bool to_host = nq && !dev_a && !lp;
     const bool large_out = nq * 8 >= kStageMinBytes;
@@ -2050,10 +2071,10 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         // chunk [q0, q1): about `budget` input bytes (packed bytes count four-fold: the budget is PCIe time),
         // at least one query
         bool pack_chunk = pack_on;
-        if (hybrid && pack_on && (!last_link || cudaEventQuery(last_link) == cudaSuccess)) pack_chunk = false;  // link idle
+        if (hybrid && pack_on && raw_next) pack_chunk = false;
         const uint64_t unit = (pack_chunk || prepacked) ? 4 : 1;
         const uint64_t remaining = sym_end - query_bytes_end(qs, q0);
-        uint64_t want = budget * unit;
+        uint64_t want = (hybrid && pack_on && !pack_chunk) ? raw_want : budget * unit;
         if (remaining <= want) want = remaining > 2 * kChunkTail * unit ? remaining - kChunkTail * unit : remaining;
         uint64_t q1;
         if (qs->offsets) {
@@ -2065,7 +2086,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             q1 = q0 + (qs->fixed_len ? std::max<uint64_t>(1, want / qs->fixed_len) : kChunkMaxQueries);
         }
         q1 = std::min<uint64_t>(q1, std::min<uint64_t>(nq, q0 + kChunkMaxQueries));
-        budget = std::min<uint64_t>(budget * 2, kChunkMax);
+        if (pack_chunk || !(hybrid && pack_on)) budget = std::min<uint64_t>(budget * 2, kChunkMax);
         const uint64_t cq = q1 - q0;
         const uint64_t sym0 = query_bytes_end(qs, q0), sym1 = query_bytes_end(qs, q1), nsym = sym1 - sym0;
         Slot &sl = ws->slot[k % kSlots];
@@ -2115,7 +2136,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
                 }
                 if (exc_q.empty() || exc_q.back() != (uint32_t)q) exc_q.push_back((uint32_t)q);
             }
-            if (exc_q.size() * 8 > cq) {
+            if (exc_q.size() * 16 > cq) {
                 // this is not a batch of plain searchable symbols: IO bytes from here on
                 pack_on = false;
             } else {
@@ -2205,13 +2226,19 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             uint8_t *xb = (uint8_t *)sl.h_x.p + off_bytes;
             uint64_t acc = 0;
             for (uint64_t i = 0; i < nx; ++i) {
-                const uint64_t b0 = query_bytes_end(qs, q0 + exc_q[i]), b1 = query_bytes_end(qs, q0 + exc_q[i] + 1);
                 xo[i] = acc;
                 xs[i] = exc_q[i];
-                memcpy(xb + acc, qs->bytes + b0, b1 - b0);
-                acc += b1 - b0;
+                acc += query_bytes_end(qs, q0 + exc_q[i] + 1) - query_bytes_end(qs, q0 + exc_q[i]);
             }
             xo[nx] = acc;
+            constexpr uint64_t kPiece = 4096;  // queries per piece
+            HostPool::get().parallel_for(div_up(nx, kPiece), [&](uint64_t piece) {
+                const uint64_t lo = piece * kPiece, hi = std::min(nx, lo + kPiece);
+                for (uint64_t i = lo; i < hi; ++i) {
+                    const uint64_t b0 = query_bytes_end(qs, q0 + exc_q[i]);
+                    memcpy(xb + xo[i], qs->bytes + b0, xo[i + 1] - xo[i]);
+                }
+            });
             CUDA_TRY(cudaMemcpyAsync(sl.xbuf.p, sl.h_x.p, off_bytes + xbytes, cudaMemcpyHostToDevice, sl.stream));
             h2d_bytes += off_bytes + xbytes;
             xq.bytes = sl.xbuf.as<uint8_t>() + off_bytes;
@@ -2220,10 +2247,27 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             x_slots = reinterpret_cast<const uint32_t *>(sl.xbuf.as<uint8_t>() + off_slots);
             used_staging = true;
         }
-        CUDA_TRY(cudaEventRecord(sl.ev_link, sl.stream));
-        last_link = sl.ev_link;
-        if (!chunk_packed && !prepacked) raw_queries += cq;
         const double stage_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_stage0).count();
+        if (hybrid) {
+            // this slot's event is about to be re-recorded: its older upload has long left the link
+            for (size_t i = 0; i < on_link.size();)
+                if (on_link[i].slot == k % kSlots) on_link.erase(on_link.begin() + i);
+                else ++i;
+            CUDA_TRY(cudaEventRecord(sl.ev_link, sl.stream));
+            on_link.push_back(Upload{k % kSlots, chunk_packed ? (nsym + 3) / 4 : nsym});
+            if (chunk_packed && stage_ms > 0.02) pack_rate = 0.5 * pack_rate + 0.5 * (double)nsym / stage_ms;
+            if (chunk_packed) {
+                // how long will the pool need for the next packed chunk, and will the link last that long?
+                const double t_pack = (double)(budget * 4) / pack_rate;
+                const double have = (double)link_backlog();
+                const double need = t_pack * link_guess;
+                raw_next = pack_on && need - have >= (double)(2ull << 20);
+                raw_want = raw_next ? std::min<uint64_t>((uint64_t)(need - have), 4 * kChunkMax) : 0;
+            } else {
+                raw_next = false;  // a raw chunk is always followed by a packed one
+            }
+        }
+
         uint64_t *a, *b;
         if (dev_a) {
             a = dev_a + q0;

@@ -75,7 +75,8 @@ struct DevIndex {
     // array, or the dense accelerator (rate 1) once gdx_index_set_dense_suffix_array has built it
     uint32_t verify_min_remaining;  // text verification needs at least this many symbols left (8; 4 with the dense suffix array)
     uint32_t isa_rate;              // sampling rate of the inverse samples (= the configured rate)
-    uint32_t seed_depth, pad3;
+    uint32_t seed_depth;
+    uint32_t verify_max_rows;       // count: intervals of up to this many rows are finished by text comparisons (1 = one row only)
     uint64_t lut_level_off[kMaxLookupDepth + 1];
     uint64_t lut_pow[kMaxLookupDepth + 1];
     uint8_t io_to_dense[256];
@@ -111,7 +112,7 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.isa_rate = h.sampling_rate;
     d.seed_lookup = nullptr;
     d.seed_depth = 0;
-    d.pad3 = 0;
+    d.verify_max_rows = 1;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {
         uint32_t s = 0;
         while ((1u << s) < h.sampling_rate) ++s;

@@ -40,6 +40,9 @@
 
 #include "device_index.h"
 
+#ifndef GDX_MULTIROW
+#define GDX_MULTIROW 0
+#endif
 #ifndef GDX_KG5_VERIFY_MIN_BLOCKS
 #define GDX_KG5_VERIFY_MIN_BLOCKS 5
 #endif
@@ -743,6 +746,37 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         while (!bad && pos > 0 && s != e) {
             // mode 0 (cursors) must also produce the interval: possible with the sampled inverse suffix
             // array once at least sampling_rate symbols have matched (the ISA walk stays inside them)
+#if GDX_MULTIROW
+            // (A/B variant, tools/build_variant.sh multirow -DGDX_MULTIROW=1; measured in profiles/README.md)
+            // count only (mode 1): an interval of a few rows is finished the same way, one text comparison per
+            // candidate row (adjacent SA entries share a line); the count is the number of candidates that match,
+            // and an invalid symbol is reached exactly when some candidate matches up to it (cursor.rs:40-51)
+            if (VERIFY && !CURSORS && mode == 1 && e - s > 1 && e - s <= ix.verify_max_rows &&
+                pos >= (uint64_t)ix.verify_min_remaining * (e - s)) {
+                uint32_t matches = 0;
+                for (uint64_t r = s; r < e; ++r) {
+                    const uint64_t at = resolve_row<L>(ix, r, vsteps);
+                    uint64_t jm = 0;
+                    uint32_t cm = 0;
+                    int cmp;
+                    if constexpr (PACKED) {
+                        cmp = ix.text_bits == 4
+                                  ? compare_with_text<4, false>(ix, PackedQueryWords<4>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm)
+                                  : compare_with_text<8, false>(ix, PackedQueryWords<8>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm);
+                    } else {
+                        cmp = ix.text_bits == 4
+                                  ? compare_with_text<4, true>(ix, ByteQueryWords<4>{tab, sbytes, p, tail_begin}, pos, at, jm, cm)
+                                  : compare_with_text<8, true>(ix, ByteQueryWords<8>{tab, sbytes, p, tail_begin}, pos, at, jm, cm);
+                    }
+                    matches += cmp == 0;
+                    bad |= cmp == 2;
+                }
+                vrows = (uint32_t)(e - s);
+                s = 0;
+                e = matches;
+                break;
+            }
+#endif
             if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining &&
                 (!CURSORS || len - pos >= ix.isa_rate)) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)

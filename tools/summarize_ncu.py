@@ -26,12 +26,15 @@ KEYS = [
 ]
 
 
-def launches(src, dst):
+def launches(src, dst, exclude=None):
+    import re
     rows = [r for r in csv.reader(open(src)) if len(r) > 5]
     hdr = rows[0]
     iname, ival, iunit = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = OrderedDict()
     for r in rows[1:]:
+        if exclude and re.search(exclude, r[iname]):
+            continue
         v = float(r[ival].replace(",", ""))
         a = agg.setdefault(r[iname], [0, 0.0])
         a[0] += 1
@@ -39,6 +42,8 @@ def launches(src, dst):
     total = sum(t for _, t in agg.values())
     with open(dst, "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): {src}\n")
+        if exclude:
+            f.write(f"# launches matching /{exclude}/ left out (index construction during setup, not on the search path)\n")
         f.write(f"# per kernel: total {rows[1][iunit]}, share of all listed launches, launches, name\n")
         for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{t:16.0f} {100 * t / total:6.2f}% x{c:<5d} {n[:150]}\n")
@@ -59,4 +64,4 @@ def report(src, dst):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "report": report}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "report": report}[sys.argv[1]](*sys.argv[2:])
