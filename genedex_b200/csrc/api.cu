@@ -840,6 +840,13 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
     return GDX_OK;
 }
 
+gdx_status check_text_offsets(const uint64_t *text_offsets, uint64_t num_texts) {
+    for (uint64_t i = 0; i < num_texts; ++i)
+        if (text_offsets[i + 1] < text_offsets[i])
+            return fail(GDX_ERR_BAD_ARG, "text_offsets must be non-decreasing (text %llu)", (unsigned long long)i);
+    return GDX_OK;
+}
+
 gdx_status check_config(const gdx_config &c) {
     if (c.suffix_array_sampling_rate == 0)
         return fail(GDX_ERR_BAD_ARG, "suffix array sampling rate must be > 0 (config.rs:28)");
@@ -896,113 +903,116 @@ extern "C" void gdx_host_free(void *p) {
 // ================================================================================================
 extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text_offsets, uint64_t num_texts,
                                       const gdx_alphabet *alphabet, const gdx_config *config, gdx_index **out) {
-    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
-    *out = nullptr;
-    if (!text_offsets || !alphabet || !config) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    if (num_texts == 0) return fail(GDX_ERR_BAD_ARG, "there should be at least one text (construction/mod.rs:300)");
-    GDX_TRY(validate_alphabet(*alphabet));
-    GDX_TRY(check_config(*config));
-    int device;
-    GDX_TRY(resolve_device(config->device, &device));
-    DeviceGuard guard(device);
-
-    ConcatText ct;
-    uint64_t bad = 0;
-    gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
-    if (st != GDX_OK) {
-        t_error_query = bad;
-        return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
-                    (unsigned long long)bad);
-    }
-    const uint64_t n = ct.text.size();
-    if (n > storage_max(config->storage))
-        return fail(GDX_ERR_TEXT_TOO_LONG, "text length %llu exceeds the index storage type (construction/mod.rs:34)",
-                    (unsigned long long)n);
-
-    ImageSources src;
-    src.alphabet = alphabet;
-    src.storage = config->storage;
-    src.sampling_rate = config->suffix_array_sampling_rate;
-    src.lookup_depth = config->lookup_table_depth;
-    src.n = n;
-    src.count = ct.count.data();
-    src.sentinels = ct.sentinels.data();
-    src.ntexts = num_texts;
-    src.accel_flags = accel_flags_from_config(config->flags);
-    src.accel_budget = config->accelerator_budget_bytes;
-
-    // the dense text goes to the device once: input of the device suffix sort and source of the
-    // optional text section of the image
-    const bool keep_text = (config->flags & GDX_FLAG_NO_TEXT) == 0;
-    const bool keep_isa = keep_text && (config->flags & GDX_FLAG_NO_INVERSE_SAMPLES) == 0;
-    struct DevText {
-        uint8_t *p = nullptr;
-        ~DevText() {
-            if (p) cudaFree(p);
+    return guarded([&]() -> gdx_status {
+        if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+        *out = nullptr;
+        if (!text_offsets || !alphabet || !config) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        if (num_texts == 0) return fail(GDX_ERR_BAD_ARG, "there should be at least one text (construction/mod.rs:300)");
+        GDX_TRY(check_text_offsets(text_offsets, num_texts));
+        GDX_TRY(validate_alphabet(*alphabet));
+        GDX_TRY(check_config(*config));
+        int device;
+        GDX_TRY(resolve_device(config->device, &device));
+        DeviceGuard guard(device);
+    
+        ConcatText ct;
+        uint64_t bad = 0;
+        gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
+        if (st != GDX_OK) {
+            t_error_query = bad;
+            return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
+                        (unsigned long long)bad);
         }
-    } d_text;
-    uint32_t construction = config->construction;
-    if (construction == GDX_CONSTRUCT_AUTO) {  // device suffix sort when the text and its scratch fit
-        size_t free_b = 0, total_b = 0;
-        construction = GDX_CONSTRUCT_HOST;
-        if (n < 0xffffffffull && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 36 * n + (1ull << 30))
-            construction = GDX_CONSTRUCT_DEVICE;
-    }
-    if (keep_text || construction == GDX_CONSTRUCT_DEVICE) {
-        CUDA_TRY(cudaMalloc(&d_text.p, n ? n : 1));
-        CUDA_TRY(cudaMemcpy(d_text.p, ct.text.data(), n, cudaMemcpyHostToDevice));
-        if (keep_text) src.d_text = d_text.p;
-    }
-
-    if (construction == GDX_CONSTRUCT_DEVICE) {
-        DeviceBuildResult r;
-        const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
-        st = device_build_from_text(nullptr, d_text.p, n, alphabet->num_dense_symbols,
-                                    config->suffix_array_sampling_rate, r, t_error, false, verify, keep_isa);
-        if (st != GDX_OK) return st;
-        if (verify && r.verify_violations) {
+        const uint64_t n = ct.text.size();
+        if (n > storage_max(config->storage))
+            return fail(GDX_ERR_TEXT_TOO_LONG, "text length %llu exceeds the index storage type (construction/mod.rs:34)",
+                        (unsigned long long)n);
+    
+        ImageSources src;
+        src.alphabet = alphabet;
+        src.storage = config->storage;
+        src.sampling_rate = config->suffix_array_sampling_rate;
+        src.lookup_depth = config->lookup_table_depth;
+        src.n = n;
+        src.count = ct.count.data();
+        src.sentinels = ct.sentinels.data();
+        src.ntexts = num_texts;
+        src.accel_flags = accel_flags_from_config(config->flags);
+        src.accel_budget = config->accelerator_budget_bytes;
+    
+        // the dense text goes to the device once: input of the device suffix sort and source of the
+        // optional text section of the image
+        const bool keep_text = (config->flags & GDX_FLAG_NO_TEXT) == 0;
+        const bool keep_isa = keep_text && (config->flags & GDX_FLAG_NO_INVERSE_SAMPLES) == 0;
+        struct DevText {
+            uint8_t *p = nullptr;
+            ~DevText() {
+                if (p) cudaFree(p);
+            }
+        } d_text;
+        uint32_t construction = config->construction;
+        if (construction == GDX_CONSTRUCT_AUTO) {  // device suffix sort when the text and its scratch fit
+            size_t free_b = 0, total_b = 0;
+            construction = GDX_CONSTRUCT_HOST;
+            if (n < 0xffffffffull && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b > 36 * n + (1ull << 30))
+                construction = GDX_CONSTRUCT_DEVICE;
+        }
+        if (keep_text || construction == GDX_CONSTRUCT_DEVICE) {
+            CUDA_TRY(cudaMalloc(&d_text.p, n ? n : 1));
+            CUDA_TRY(cudaMemcpy(d_text.p, ct.text.data(), n, cudaMemcpyHostToDevice));
+            if (keep_text) src.d_text = d_text.p;
+        }
+    
+        if (construction == GDX_CONSTRUCT_DEVICE) {
+            DeviceBuildResult r;
+            const bool verify = (config->flags & GDX_FLAG_VERIFY_SUFFIX_ARRAY) != 0;
+            st = device_build_from_text(nullptr, d_text.p, n, alphabet->num_dense_symbols,
+                                        config->suffix_array_sampling_rate, r, t_error, false, verify, keep_isa);
+            if (st != GDX_OK) return st;
+            if (verify && r.verify_violations) {
+                r.release();
+                return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)",
+                            (unsigned long long)r.verify_violations);
+            }
+            src.border_rows = r.border_rows.data();
+            src.border_pos = r.border_pos.data();
+            src.n_border = r.border_rows.size();
+            src.d_bwt = r.d_bwt;
+            src.d_samples = r.d_samples;
+            src.d_samples_wide = false;
+            src.d_isa32 = r.d_isa_samples;
+            st = build_image(src, device, out);
             r.release();
-            return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)",
-                        (unsigned long long)r.verify_violations);
+            if (st == GDX_OK) {
+                auto_dense_sa(*out);
+                auto_seed_table(*out);
+            }
+            return st;
         }
-        src.border_rows = r.border_rows.data();
-        src.border_pos = r.border_pos.data();
-        src.n_border = r.border_rows.size();
-        src.d_bwt = r.d_bwt;
-        src.d_samples = r.d_samples;
-        src.d_samples_wide = false;
-        src.d_isa32 = r.d_isa_samples;
+    
+        HostParts hp;
+        host_parts_from_text(ct.text.data(), n, alphabet->num_dense_symbols, config->suffix_array_sampling_rate, hp);
+        uint8_t *d_bwt = nullptr;
+        CUDA_TRY(cudaMalloc(&d_bwt, n ? n : 1));
+        cudaError_t e = cudaMemcpy(d_bwt, hp.bwt.data(), n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_bwt);
+            return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
+        }
+        src.border_rows = hp.border_rows.data();
+        src.border_pos = hp.border_pos.data();
+        src.n_border = hp.border_rows.size();
+        src.d_bwt = d_bwt;
+        src.h_samples64 = hp.samples.data();
+        if (keep_isa) src.h_isa64 = hp.isa_samples.data();
         st = build_image(src, device, out);
-        r.release();
+        cudaFree(d_bwt);
         if (st == GDX_OK) {
             auto_dense_sa(*out);
             auto_seed_table(*out);
         }
         return st;
-    }
-
-    HostParts hp;
-    host_parts_from_text(ct.text.data(), n, alphabet->num_dense_symbols, config->suffix_array_sampling_rate, hp);
-    uint8_t *d_bwt = nullptr;
-    CUDA_TRY(cudaMalloc(&d_bwt, n ? n : 1));
-    cudaError_t e = cudaMemcpy(d_bwt, hp.bwt.data(), n, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
-        cudaFree(d_bwt);
-        return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
-    }
-    src.border_rows = hp.border_rows.data();
-    src.border_pos = hp.border_pos.data();
-    src.n_border = hp.border_rows.size();
-    src.d_bwt = d_bwt;
-    src.h_samples64 = hp.samples.data();
-    if (keep_isa) src.h_isa64 = hp.isa_samples.data();
-    st = build_image(src, device, out);
-    cudaFree(d_bwt);
-    if (st == GDX_OK) {
-        auto_dense_sa(*out);
-        auto_seed_table(*out);
-    }
-    return st;
+    });
 }
 
 static gdx_status sources_from_parts(const gdx_parts *parts, ImageSources &src,
@@ -1046,157 +1056,170 @@ static gdx_status sources_from_parts(const gdx_parts *parts, ImageSources &src,
 
 extern "C" gdx_status gdx_index_create_from_bwt(const uint8_t *bwt, const gdx_parts *parts, int32_t device_req,
                                                 gdx_index **out) {
-    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
-    *out = nullptr;
-    if (!bwt) return fail(GDX_ERR_BAD_ARG, "bwt is NULL");
-    ImageSources src;
-    std::vector<uint64_t> rows, pos;
-    GDX_TRY(sources_from_parts(parts, src, rows, pos));
-    int device;
-    GDX_TRY(resolve_device(device_req, &device));
-    DeviceGuard guard(device);
-    uint8_t *d_bwt = nullptr;
-    CUDA_TRY(cudaMalloc(&d_bwt, src.n ? src.n : 1));
-    cudaError_t e = cudaMemcpy(d_bwt, bwt, src.n, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) {
+    return guarded([&]() -> gdx_status {
+        if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+        *out = nullptr;
+        if (!bwt) return fail(GDX_ERR_BAD_ARG, "bwt is NULL");
+        ImageSources src;
+        std::vector<uint64_t> rows, pos;
+        GDX_TRY(sources_from_parts(parts, src, rows, pos));
+        int device;
+        GDX_TRY(resolve_device(device_req, &device));
+        DeviceGuard guard(device);
+        uint8_t *d_bwt = nullptr;
+        CUDA_TRY(cudaMalloc(&d_bwt, src.n ? src.n : 1));
+        cudaError_t e = cudaMemcpy(d_bwt, bwt, src.n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(d_bwt);
+            return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
+        }
+        src.d_bwt = d_bwt;
+        gdx_status st = build_image(src, device, out);
         cudaFree(d_bwt);
-        return fail(GDX_ERR_CUDA, "BWT upload failed: %s", cudaGetErrorString(e));
-    }
-    src.d_bwt = d_bwt;
-    gdx_status st = build_image(src, device, out);
-    cudaFree(d_bwt);
-    if (st == GDX_OK) {
-        auto_dense_sa(*out);
-        auto_seed_table(*out);
-    }
-    return st;
+        if (st == GDX_OK) {
+            auto_dense_sa(*out);
+            auto_seed_table(*out);
+        }
+        return st;
+    });
 }
 
 extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_t device_req, gdx_index **out) {
-    if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
-    *out = nullptr;
-    ImageSources src;
-    std::vector<uint64_t> rows, pos;
-    GDX_TRY(sources_from_parts(parts, src, rows, pos));
-    if (!parts->interleaved_blocks) return fail(GDX_ERR_BAD_ARG, "interleaved_blocks is NULL");
-    int device;
-    GDX_TRY(resolve_device(device_req, &device));
-    DeviceGuard guard(device);
-    // the reference's blocks -> dense BWT on the device (symbol_at of the variant), then the common path
-    const uint32_t block_bits = parts->block_bits ? parts->block_bits : 64;
-    if ((block_bits != 64 && block_bits != 512) || parts->rank_variant > GDX_RANK_FLAT)
-        return fail(GDX_ERR_BAD_ARG, "rank_variant must be GDX_RANK_CONDENSED or GDX_RANK_FLAT, block_bits 64 or 512");
-    const bool flat = parts->rank_variant == GDX_RANK_FLAT;
-    const uint32_t words = block_bits / 64, used = block_bits - (flat ? 16 : 0);
-    const uint32_t units = flat ? parts->alphabet.num_dense_symbols : choose_layout(parts->alphabet.num_dense_symbols).planes;
-    const uint64_t nwords = div_up(src.n + 1, used) * units * words;
-    uint64_t *d_blocks = nullptr;
-    uint8_t *d_bwt = nullptr;
-    CUDA_TRY(cudaMalloc(&d_blocks, nwords * 8));
-    cudaError_t e = cudaMalloc(&d_bwt, src.n ? src.n : 1);
-    if (e == cudaSuccess) e = cudaMemcpy(d_blocks, parts->interleaved_blocks, nwords * 8, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && src.n) {
-        k_ref_blocks_to_bwt<<<(unsigned)div_up(src.n, 256), 256>>>(d_blocks, flat ? 1u : 0u, words, units, src.n, d_bwt);
-        e = cudaGetLastError();
-    }
-    cudaFree(d_blocks);
-    if (e != cudaSuccess) {
-        if (d_bwt) cudaFree(d_bwt);
-        return fail(GDX_ERR_CUDA, "block upload failed: %s", cudaGetErrorString(e));
-    }
-    src.d_bwt = d_bwt;
-    gdx_status st = build_image(src, device, out);
-    cudaFree(d_bwt);
-    if (st == GDX_OK) {
-        auto_dense_sa(*out);
-        auto_seed_table(*out);
-    }
-    return st;
+    return guarded([&]() -> gdx_status {
+        if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
+        *out = nullptr;
+        ImageSources src;
+        std::vector<uint64_t> rows, pos;
+        GDX_TRY(sources_from_parts(parts, src, rows, pos));
+        if (!parts->interleaved_blocks) return fail(GDX_ERR_BAD_ARG, "interleaved_blocks is NULL");
+        int device;
+        GDX_TRY(resolve_device(device_req, &device));
+        DeviceGuard guard(device);
+        // the reference's blocks -> dense BWT on the device (symbol_at of the variant), then the common path
+        const uint32_t block_bits = parts->block_bits ? parts->block_bits : 64;
+        if ((block_bits != 64 && block_bits != 512) || parts->rank_variant > GDX_RANK_FLAT)
+            return fail(GDX_ERR_BAD_ARG, "rank_variant must be GDX_RANK_CONDENSED or GDX_RANK_FLAT, block_bits 64 or 512");
+        const bool flat = parts->rank_variant == GDX_RANK_FLAT;
+        const uint32_t words = block_bits / 64, used = block_bits - (flat ? 16 : 0);
+        const uint32_t units = flat ? parts->alphabet.num_dense_symbols : choose_layout(parts->alphabet.num_dense_symbols).planes;
+        const uint64_t nwords = div_up(src.n + 1, used) * units * words;
+        uint64_t *d_blocks = nullptr;
+        uint8_t *d_bwt = nullptr;
+        CUDA_TRY(cudaMalloc(&d_blocks, nwords * 8));
+        cudaError_t e = cudaMalloc(&d_bwt, src.n ? src.n : 1);
+        if (e == cudaSuccess) e = cudaMemcpy(d_blocks, parts->interleaved_blocks, nwords * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && src.n) {
+            k_ref_blocks_to_bwt<<<(unsigned)div_up(src.n, 256), 256>>>(d_blocks, flat ? 1u : 0u, words, units, src.n, d_bwt);
+            e = cudaGetLastError();
+        }
+        cudaFree(d_blocks);
+        if (e != cudaSuccess) {
+            if (d_bwt) cudaFree(d_bwt);
+            return fail(GDX_ERR_CUDA, "block upload failed: %s", cudaGetErrorString(e));
+        }
+        src.d_bwt = d_bwt;
+        gdx_status st = build_image(src, device, out);
+        cudaFree(d_bwt);
+        if (st == GDX_OK) {
+            auto_dense_sa(*out);
+            auto_seed_table(*out);
+        }
+        return st;
+    });
 }
 
 extern "C" gdx_status gdx_concat_texts(const uint8_t *texts, const uint64_t *text_offsets, uint64_t num_texts,
                                        const gdx_alphabet *alphabet, uint8_t *dense_out, uint64_t *sentinels_out,
                                        uint64_t *count_out) {
-    if (!text_offsets || !alphabet || !dense_out || !sentinels_out || !count_out || num_texts == 0)
-        return fail(GDX_ERR_BAD_ARG, "NULL argument or no texts");
-    GDX_TRY(validate_alphabet(*alphabet));
-    ConcatText ct;
-    uint64_t bad = 0;
-    gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
-    if (st != GDX_OK) {
-        t_error_query = bad;
-        return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
-                    (unsigned long long)bad);
-    }
-    memcpy(dense_out, ct.text.data(), ct.text.size());
-    memcpy(sentinels_out, ct.sentinels.data(), ct.sentinels.size() * 8);
-    memcpy(count_out, ct.count.data(), ct.count.size() * 8);
-    return GDX_OK;
+    return guarded([&]() -> gdx_status {
+        if (!text_offsets || !alphabet || !dense_out || !sentinels_out || !count_out || num_texts == 0)
+            return fail(GDX_ERR_BAD_ARG, "NULL argument or no texts");
+        GDX_TRY(check_text_offsets(text_offsets, num_texts));
+        GDX_TRY(validate_alphabet(*alphabet));
+        ConcatText ct;
+        uint64_t bad = 0;
+        gdx_status st = concat_texts(texts, text_offsets, num_texts, *alphabet, ct, &bad);
+        if (st != GDX_OK) {
+            t_error_query = bad;
+            return fail(st, "text %llu contains a symbol that is not in the alphabet (alphabet.rs:195-198)",
+                        (unsigned long long)bad);
+        }
+        memcpy(dense_out, ct.text.data(), ct.text.size());
+        memcpy(sentinels_out, ct.sentinels.data(), ct.sentinels.size() * 8);
+        memcpy(count_out, ct.count.data(), ct.count.size() * 8);
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_suffix_array(const uint8_t *dense_text, uint64_t n, uint32_t sigma, uint32_t where,
                                        int32_t device_req, uint64_t *sa_out) {
-    if (n == 0) return GDX_OK;
-    if (!dense_text || !sa_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    if (sigma < 2 || sigma > 256) return fail(GDX_ERR_BAD_ARG, "alphabet size must be in [2,256]");
-    for (uint64_t i = 0; i < n; ++i)
-        if (dense_text[i] >= sigma) return fail(GDX_ERR_BAD_ARG, "symbol %u at %llu is not dense", dense_text[i], (unsigned long long)i);
-    if (where == GDX_CONSTRUCT_HOST) {
-        std::vector<int64_t> sa;
-        suffix_array_sais(dense_text, n, sigma, sa);
-        for (uint64_t i = 0; i < n; ++i) sa_out[i] = (uint64_t)sa[i];
+    return guarded([&]() -> gdx_status {
+        if (n == 0) return GDX_OK;
+        if (!dense_text || !sa_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        if (sigma < 2 || sigma > 256) return fail(GDX_ERR_BAD_ARG, "alphabet size must be in [2,256]");
+        for (uint64_t i = 0; i < n; ++i)
+            if (dense_text[i] >= sigma) return fail(GDX_ERR_BAD_ARG, "symbol %u at %llu is not dense", dense_text[i], (unsigned long long)i);
+        if (where == GDX_CONSTRUCT_HOST) {
+            std::vector<int64_t> sa;
+            suffix_array_sais(dense_text, n, sigma, sa);
+            for (uint64_t i = 0; i < n; ++i) sa_out[i] = (uint64_t)sa[i];
+            return GDX_OK;
+        }
+        int device;
+        GDX_TRY(resolve_device(device_req, &device));
+        DeviceGuard guard(device);
+        DeviceBuildResult r;
+        gdx_status st = device_build_from_text(dense_text, nullptr, n, sigma, 1, r, t_error, true, true);
+        if (st != GDX_OK) return st;
+        std::vector<uint32_t> sa32(n);
+        cudaError_t e = cudaMemcpy(sa32.data(), r.d_sa, n * 4, cudaMemcpyDeviceToHost);
+        const uint64_t viol = r.verify_violations;
+        r.release();
+        if (e != cudaSuccess) return fail(GDX_ERR_CUDA, "suffix array download failed: %s", cudaGetErrorString(e));
+        for (uint64_t i = 0; i < n; ++i) sa_out[i] = sa32[i];
+        if (viol) return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)", (unsigned long long)viol);
         return GDX_OK;
-    }
-    int device;
-    GDX_TRY(resolve_device(device_req, &device));
-    DeviceGuard guard(device);
-    DeviceBuildResult r;
-    gdx_status st = device_build_from_text(dense_text, nullptr, n, sigma, 1, r, t_error, true, true);
-    if (st != GDX_OK) return st;
-    std::vector<uint32_t> sa32(n);
-    cudaError_t e = cudaMemcpy(sa32.data(), r.d_sa, n * 4, cudaMemcpyDeviceToHost);
-    const uint64_t viol = r.verify_violations;
-    r.release();
-    if (e != cudaSuccess) return fail(GDX_ERR_CUDA, "suffix array download failed: %s", cudaGetErrorString(e));
-    for (uint64_t i = 0; i < n; ++i) sa_out[i] = sa32[i];
-    if (viol) return fail(GDX_ERR_CUDA, "device suffix array failed verification (%llu violations)", (unsigned long long)viol);
-    return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_index_download_bwt(const gdx_index *idx, uint8_t *bwt_out) {
-    if (!idx || !bwt_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    DeviceGuard guard(idx->device);
-    const uint64_t n = idx->h.n, chunk = 256ull << 20;
-    uint8_t *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, std::min<uint64_t>(n ? n : 1, chunk)));
-    gdx_status st = GDX_OK;
-    for (uint64_t b = 0; b < n && st == GDX_OK; b += chunk) {
-        const uint64_t e = std::min<uint64_t>(n, b + chunk);
-        st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-            k_records_to_bwt<decltype(L)><<<(unsigned)div_up(e - b, 256), 256>>>(idx->dev, b, e, d);
-            return GDX_OK;
-        });
-        cudaError_t ce = cudaMemcpy(bwt_out + b, d, e - b, cudaMemcpyDeviceToHost);
-        if (st == GDX_OK && ce != cudaSuccess) st = fail(GDX_ERR_CUDA, "BWT download failed: %s", cudaGetErrorString(ce));
-    }
-    cudaFree(d);
-    return st;
+    return guarded([&]() -> gdx_status {
+        if (!idx || !bwt_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        DeviceGuard guard(idx->device);
+        const uint64_t n = idx->h.n, chunk = 256ull << 20;
+        uint8_t *d = nullptr;
+        CUDA_TRY(cudaMalloc(&d, std::min<uint64_t>(n ? n : 1, chunk)));
+        gdx_status st = GDX_OK;
+        for (uint64_t b = 0; b < n && st == GDX_OK; b += chunk) {
+            const uint64_t e = std::min<uint64_t>(n, b + chunk);
+            st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+                k_records_to_bwt<decltype(L)><<<(unsigned)div_up(e - b, 256), 256>>>(idx->dev, b, e, d);
+                return GDX_OK;
+            });
+            cudaError_t ce = cudaMemcpy(bwt_out + b, d, e - b, cudaMemcpyDeviceToHost);
+            if (st == GDX_OK && ce != cudaSuccess) st = fail(GDX_ERR_CUDA, "BWT download failed: %s", cudaGetErrorString(ce));
+        }
+        cudaFree(d);
+        return st;
+    });
 }
 
 extern "C" gdx_status gdx_index_download_samples(const gdx_index *idx, uint64_t *samples_out) {
-    if (!idx || !samples_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    DeviceGuard guard(idx->device);
-    const uint64_t ns = idx->h.n_samples;
-    const uint8_t *src = (const uint8_t *)idx->image + idx->h.off_samples;
-    if (idx->h.wide) {
-        CUDA_TRY(cudaMemcpy(samples_out, src, ns * 8, cudaMemcpyDeviceToHost));
-    } else {
-        // narrow samples land in the upper half of the output buffer and are widened in place
-        uint32_t *tmp = reinterpret_cast<uint32_t *>(samples_out) + ns;
-        CUDA_TRY(cudaMemcpy(tmp, src, ns * 4, cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < ns; ++i) samples_out[i] = tmp[i];
-    }
-    return GDX_OK;
+    return guarded([&]() -> gdx_status {
+        if (!idx || !samples_out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        DeviceGuard guard(idx->device);
+        const uint64_t ns = idx->h.n_samples;
+        const uint8_t *src = (const uint8_t *)idx->image + idx->h.off_samples;
+        if (idx->h.wide) {
+            CUDA_TRY(cudaMemcpy(samples_out, src, ns * 8, cudaMemcpyDeviceToHost));
+        } else {
+            // narrow samples land in the upper half of the output buffer and are widened in place
+            uint32_t *tmp = reinterpret_cast<uint32_t *>(samples_out) + ns;
+            CUDA_TRY(cudaMemcpy(tmp, src, ns * 4, cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < ns; ++i) samples_out[i] = tmp[i];
+        }
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_index_download_text_borders(const gdx_index *idx, uint64_t *rows_out, uint64_t *positions_out) {
@@ -1279,76 +1302,80 @@ struct FileCloser {
 
 extern "C" gdx_status gdx_index_save_to_file(const gdx_index *idx, const char *path, const void *user_data,
                                              uint64_t user_bytes) {
-    if (!idx || !path || (user_bytes && !user_data)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    DeviceGuard guard(idx->device);
-    FileCloser fc{fopen(path, "wb")};
-    if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s for writing", path);
-    FilePrefix p;
-    memcpy(p.magic, kFileMagic, 8);
-    p.header_bytes = sizeof(ImageHeader);
-    p.image_bytes = idx->h.image_bytes;
-    p.user_bytes = user_bytes;
-    if (fwrite(&p, sizeof p, 1, fc.f) != 1 || fwrite(&idx->h, sizeof(ImageHeader), 1, fc.f) != 1 ||
-        (user_bytes && fwrite(user_data, user_bytes, 1, fc.f) != 1))
-        return fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
-    const uint64_t chunk = 64ull << 20;
-    void *stage = nullptr;
-    CUDA_TRY(cudaMallocHost(&stage, chunk));
-    gdx_status st = GDX_OK;
-    for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
-        const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
-        cudaError_t e = cudaMemcpy(stage, (const uint8_t *)idx->image + off, nb, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) st = fail(GDX_ERR_CUDA, "image download failed: %s", cudaGetErrorString(e));
-        else if (fwrite(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
-    }
-    cudaFreeHost(stage);
-    return st;
+    return guarded([&]() -> gdx_status {
+        if (!idx || !path || (user_bytes && !user_data)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        DeviceGuard guard(idx->device);
+        FileCloser fc{fopen(path, "wb")};
+        if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s for writing", path);
+        FilePrefix p;
+        memcpy(p.magic, kFileMagic, 8);
+        p.header_bytes = sizeof(ImageHeader);
+        p.image_bytes = idx->h.image_bytes;
+        p.user_bytes = user_bytes;
+        if (fwrite(&p, sizeof p, 1, fc.f) != 1 || fwrite(&idx->h, sizeof(ImageHeader), 1, fc.f) != 1 ||
+            (user_bytes && fwrite(user_data, user_bytes, 1, fc.f) != 1))
+            return fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
+        const uint64_t chunk = 64ull << 20;
+        void *stage = nullptr;
+        CUDA_TRY(cudaMallocHost(&stage, chunk));
+        gdx_status st = GDX_OK;
+        for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
+            const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
+            cudaError_t e = cudaMemcpy(stage, (const uint8_t *)idx->image + off, nb, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) st = fail(GDX_ERR_CUDA, "image download failed: %s", cudaGetErrorString(e));
+            else if (fwrite(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "write to %s failed", path);
+        }
+        cudaFreeHost(stage);
+        return st;
+    });
 }
 
 extern "C" gdx_status gdx_index_load_from_file(const char *path, int32_t device_req, gdx_index **out,
                                                void *user_data_out, uint64_t user_capacity, uint64_t *user_bytes_out) {
-    if (!path || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    *out = nullptr;
-    FileCloser fc{fopen(path, "rb")};
-    if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s", path);
-    FilePrefix p;
-    ImageHeader h;
-    if (fread(&p, sizeof p, 1, fc.f) != 1 || memcmp(p.magic, kFileMagic, 8) != 0 || p.header_bytes != sizeof(ImageHeader) ||
-        fread(&h, sizeof h, 1, fc.f) != 1 || h.magic != kImageMagic || h.version != GDX_ABI_VERSION ||
-        h.image_bytes != p.image_bytes)
-        return fail(GDX_ERR_BAD_ARG, "%s is not a genedex_b200 index file of this version", path);
-    GDX_TRY(validate_header(h));
-    // the sizes in the prefix must add up to the size of the file before anything is allocated from them
-    const off_t here = ftello(fc.f);
-    if (here < 0 || fseeko(fc.f, 0, SEEK_END) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
-    const off_t file_size = ftello(fc.f);
-    if (fseeko(fc.f, here, SEEK_SET) != 0 || file_size < here || p.user_bytes > (uint64_t)(file_size - here) ||
-        p.image_bytes != (uint64_t)(file_size - here) - p.user_bytes)
-        return fail(GDX_ERR_BAD_ARG, "%s is truncated or corrupt (section sizes do not add up to the file size)", path);
-    if (user_bytes_out) *user_bytes_out = p.user_bytes;
-    if (p.user_bytes) {
-        const uint64_t keep = user_data_out ? std::min<uint64_t>(p.user_bytes, user_capacity) : 0;
-        if (keep && fread(user_data_out, keep, 1, fc.f) != 1) return fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
-        if (fseeko(fc.f, here + (off_t)p.user_bytes, SEEK_SET) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
-    }
-    int device;
-    GDX_TRY(resolve_device(device_req, &device));
-    DeviceGuard guard(device);
-    void *image = nullptr, *stage = nullptr;
-    CUDA_TRY(cudaMalloc(&image, p.image_bytes ? p.image_bytes : 1));
-    const uint64_t chunk = 64ull << 20;
-    cudaError_t e = cudaMallocHost(&stage, chunk);
-    gdx_status st = e == cudaSuccess ? GDX_OK : fail(GDX_ERR_OOM, "pinned staging allocation failed");
-    for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
-        const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
-        if (fread(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
-        else if ((e = cudaMemcpy((uint8_t *)image + off, stage, nb, cudaMemcpyHostToDevice)) != cudaSuccess)
-            st = fail(GDX_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
-    }
-    if (stage) cudaFreeHost(stage);
-    if (st == GDX_OK) st = gdx_index_adopt_image(&h, image, device, 1, out);
-    if (st != GDX_OK) cudaFree(image);
-    return st;
+    return guarded([&]() -> gdx_status {
+        if (!path || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        *out = nullptr;
+        FileCloser fc{fopen(path, "rb")};
+        if (!fc.f) return fail(GDX_ERR_BAD_ARG, "cannot open %s", path);
+        FilePrefix p;
+        ImageHeader h;
+        if (fread(&p, sizeof p, 1, fc.f) != 1 || memcmp(p.magic, kFileMagic, 8) != 0 || p.header_bytes != sizeof(ImageHeader) ||
+            fread(&h, sizeof h, 1, fc.f) != 1 || h.magic != kImageMagic || h.version != GDX_ABI_VERSION ||
+            h.image_bytes != p.image_bytes)
+            return fail(GDX_ERR_BAD_ARG, "%s is not a genedex_b200 index file of this version", path);
+        GDX_TRY(validate_header(h));
+        // the sizes in the prefix must add up to the size of the file before anything is allocated from them
+        const off_t here = ftello(fc.f);
+        if (here < 0 || fseeko(fc.f, 0, SEEK_END) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
+        const off_t file_size = ftello(fc.f);
+        if (fseeko(fc.f, here, SEEK_SET) != 0 || file_size < here || p.user_bytes > (uint64_t)(file_size - here) ||
+            p.image_bytes != (uint64_t)(file_size - here) - p.user_bytes)
+            return fail(GDX_ERR_BAD_ARG, "%s is truncated or corrupt (section sizes do not add up to the file size)", path);
+        if (user_bytes_out) *user_bytes_out = p.user_bytes;
+        if (p.user_bytes) {
+            const uint64_t keep = user_data_out ? std::min<uint64_t>(p.user_bytes, user_capacity) : 0;
+            if (keep && fread(user_data_out, keep, 1, fc.f) != 1) return fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
+            if (fseeko(fc.f, here + (off_t)p.user_bytes, SEEK_SET) != 0) return fail(GDX_ERR_BAD_ARG, "cannot seek in %s", path);
+        }
+        int device;
+        GDX_TRY(resolve_device(device_req, &device));
+        DeviceGuard guard(device);
+        void *image = nullptr, *stage = nullptr;
+        CUDA_TRY(cudaMalloc(&image, p.image_bytes ? p.image_bytes : 1));
+        const uint64_t chunk = 64ull << 20;
+        cudaError_t e = cudaMallocHost(&stage, chunk);
+        gdx_status st = e == cudaSuccess ? GDX_OK : fail(GDX_ERR_OOM, "pinned staging allocation failed");
+        for (uint64_t off = 0; off < p.image_bytes && st == GDX_OK; off += chunk) {
+            const uint64_t nb = std::min<uint64_t>(chunk, p.image_bytes - off);
+            if (fread(stage, nb, 1, fc.f) != 1) st = fail(GDX_ERR_BAD_ARG, "%s is truncated", path);
+            else if ((e = cudaMemcpy((uint8_t *)image + off, stage, nb, cudaMemcpyHostToDevice)) != cudaSuccess)
+                st = fail(GDX_ERR_CUDA, "image upload failed: %s", cudaGetErrorString(e));
+        }
+        if (stage) cudaFreeHost(stage);
+        if (st == GDX_OK) st = gdx_index_adopt_image(&h, image, device, 1, out);
+        if (st != GDX_OK) cudaFree(image);
+        return st;
+    });
 }
 
 // ================================================================================================
@@ -1367,32 +1394,34 @@ extern "C" gdx_status gdx_index_export(const gdx_index *idx, void *header_out, c
 
 extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_image, int32_t device_req,
                                             int32_t own_image, gdx_index **out) {
-    if (!header || !device_image || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    *out = nullptr;
-    ImageHeader h;
-    memcpy(&h, header, sizeof h);
-    GDX_TRY(validate_header(h));
-    int device;
-    GDX_TRY(resolve_device(device_req, &device));
-    gdx_index *idx = new (std::nothrow) gdx_index();
-    if (!idx) return fail(GDX_ERR_OOM, "out of host memory");
-    idx->h = h;
-    idx->image = device_image;
-    idx->own_image = own_image != 0;
-    idx->device = device;
-    idx->dev = make_dev_index(h, device_image);
-    {
-        DeviceGuard guard(device);
-        gdx_status st = init_policies(idx);
-        if (st != GDX_OK) {
-            delete idx;
-            return st;
+    return guarded([&]() -> gdx_status {
+        if (!header || !device_image || !out) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        *out = nullptr;
+        ImageHeader h;
+        memcpy(&h, header, sizeof h);
+        GDX_TRY(validate_header(h));
+        int device;
+        GDX_TRY(resolve_device(device_req, &device));
+        gdx_index *idx = new (std::nothrow) gdx_index();
+        if (!idx) return fail(GDX_ERR_OOM, "out of host memory");
+        idx->h = h;
+        idx->image = device_image;
+        idx->own_image = own_image != 0;
+        idx->device = device;
+        idx->dev = make_dev_index(h, device_image);
+        {
+            DeviceGuard guard(device);
+            gdx_status st = init_policies(idx);
+            if (st != GDX_OK) {
+                delete idx;
+                return st;
+            }
+            auto_dense_sa(idx);
+            auto_seed_table(idx);
         }
-        auto_dense_sa(idx);
-        auto_seed_table(idx);
-    }
-    *out = idx;
-    return GDX_OK;
+        *out = idx;
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth) {
@@ -2816,27 +2845,29 @@ extern "C" gdx_status gdx_locate_many_sharded(gdx_index *const *replicas, uint32
 
 extern "C" gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, const uint64_t *ends,
                                            uint64_t n, uint64_t *hit_offsets, gdx_hit **hits, uint64_t *num_hits) {
-    GDX_TRY(begin_call(idx, "gdx_locate_intervals"));
-    if (!hit_offsets || !hits || !num_hits || (n && (!starts || !ends))) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    *hits = nullptr;
-    *num_hits = 0;
-    for (uint64_t i = 0; i < n; ++i)
-        if (starts[i] > ends[i] || ends[i] > idx->h.n)
-            return fail(GDX_ERR_BAD_ARG, "interval %llu is not inside [0, text_len]", (unsigned long long)i);
-    DeviceGuard guard(idx->device);
-    WsLease lease(idx);
-    Workspace *ws = lease.w;
-    if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaStream_t st = ws->slot[0].stream;
-    CUDA_TRY(ws->starts.reserve((n + 1) * 8));
-    CUDA_TRY(ws->ends.reserve((n + 1) * 8));
-    if (n) {
-        CUDA_TRY(cudaMemcpyAsync(ws->starts.p, starts, n * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
-    }
-    uint64_t total = 0;
-    GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
-    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+    return guarded([&]() -> gdx_status {
+        GDX_TRY(begin_call(idx, "gdx_locate_intervals"));
+        if (!hit_offsets || !hits || !num_hits || (n && (!starts || !ends))) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        *hits = nullptr;
+        *num_hits = 0;
+        for (uint64_t i = 0; i < n; ++i)
+            if (starts[i] > ends[i] || ends[i] > idx->h.n)
+                return fail(GDX_ERR_BAD_ARG, "interval %llu is not inside [0, text_len]", (unsigned long long)i);
+        DeviceGuard guard(idx->device);
+        WsLease lease(idx);
+        Workspace *ws = lease.w;
+        if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaStream_t st = ws->slot[0].stream;
+        CUDA_TRY(ws->starts.reserve((n + 1) * 8));
+        CUDA_TRY(ws->ends.reserve((n + 1) * 8));
+        if (n) {
+            CUDA_TRY(cudaMemcpyAsync(ws->starts.p, starts, n * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
+        }
+        uint64_t total = 0;
+        GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
+        return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+    });
 }
 
 extern "C" void gdx_free_hits(const gdx_index *idx, gdx_hit *hits) {
@@ -2848,95 +2879,99 @@ extern "C" void gdx_free_hits(const gdx_index *idx, gdx_hit *hits) {
 
 extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, uint64_t *ends,
                                       const uint8_t *io_symbols, uint64_t n) {
-    GDX_TRY(begin_call(idx, "gdx_extend_many"));
-    if (n == 0) return GDX_OK;
-    if (!starts || !ends || !io_symbols) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    DeviceGuard guard(idx->device);
-    WsLease lease(idx);
-    Workspace *ws = lease.w;
-    if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
-    cudaStream_t st = ws->slot[0].stream;
-    CUDA_TRY(ws->starts.reserve(n * 8));
-    CUDA_TRY(ws->ends.reserve(n * 8));
-    CUDA_TRY(ws->symbols.reserve(n));
-    CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 16, st));  // [0] invalid symbol, [1] cursor out of bounds
-    CUDA_TRY(cudaStreamSynchronize(st));
-    // large pageable cursor arrays go through pinned staging (see search_host)
-    Slot &sl0 = ws->slot[0];
-    const bool stage = n * 8 >= kStageMinBytes && !(is_pinned(starts) && is_pinned(ends));
-    const uint64_t *src_s = starts, *src_e = ends;
-    if (stage) {
-        CUDA_TRY(sl0.h_out_a.reserve(n * 8));
-        CUDA_TRY(sl0.h_out_b.reserve(n * 8));
-        HostPool::get().copy(sl0.h_out_a.p, starts, n * 8);
-        HostPool::get().copy(sl0.h_out_b.p, ends, n * 8);
-        src_s = (const uint64_t *)sl0.h_out_a.p;
-        src_e = (const uint64_t *)sl0.h_out_b.p;
-    }
-    uint64_t *d_s = ws->starts.as<uint64_t>(), *d_e = ws->ends.as<uint64_t>();
-    uint8_t *d_c = ws->symbols.as<uint8_t>();
-    // chunks of 1 M cursors round-robin over the workspace streams: upload, kernel and download of
-    // neighbouring chunks overlap (PCIe is full duplex).  Results land in the staging buffers (pageable
-    // caller arrays: handed over only on success) or directly in the caller's pinned arrays (on error their
-    // contents are unspecified -- the reference panics in that case).
-    const uint64_t kChunk = 1ull << 20;
-    uint64_t launches = 0;
-    for (uint64_t off = 0, k = 0; off < n; off += kChunk, ++k) {
-        const uint64_t cn = std::min<uint64_t>(kChunk, n - off);
-        cudaStream_t cs = ws->slot[k % kSlots].stream;
-        CUDA_TRY(cudaMemcpyAsync(d_s + off, src_s + off, cn * 8, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(d_e + off, src_e + off, cn * 8, cudaMemcpyHostToDevice, cs));
-        CUDA_TRY(cudaMemcpyAsync(d_c + off, io_symbols + off, cn, cudaMemcpyHostToDevice, cs));
-        GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-            k_extend<decltype(L)><<<(unsigned)div_up(cn, 256), 256, 0, cs>>>(idx->dev, d_s + off, d_e + off, d_c + off, cn,
-                                                                           ws->small.d, off);
-            return GDX_OK;
-        }));
-        CUDA_TRY(cudaGetLastError());
-        ++launches;
-        uint64_t *dst_s = stage ? (uint64_t *)sl0.h_out_a.p : starts, *dst_e = stage ? (uint64_t *)sl0.h_out_b.p : ends;
-        CUDA_TRY(cudaMemcpyAsync(dst_s + off, d_s + off, cn * 8, cudaMemcpyDeviceToHost, cs));
-        CUDA_TRY(cudaMemcpyAsync(dst_e + off, d_e + off, cn * 8, cudaMemcpyDeviceToHost, cs));
-    }
-    for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(ws->slot[s2].stream));
-    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    t_stats.kernel_launches = launches;
-    if (ws->small.h[1] != kNoError)  // checked on the device: text_with_rank_support/mod.rs:106-110
-        return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)ws->small.h[1]);
-    if (ws->small.h[0] != kNoError) {
-        t_error_query = ws->small.h[0];
-        return fail(GDX_ERR_INVALID_SYMBOL, "cursor %llu: symbol in io representation should be valid (alphabet.rs:195-198)",
-                    (unsigned long long)ws->small.h[0]);
-    }
-    if (stage) {
-        HostPool::get().copy(starts, sl0.h_out_a.p, n * 8);
-        HostPool::get().copy(ends, sl0.h_out_b.p, n * 8);
-    }
-    return GDX_OK;
+    return guarded([&]() -> gdx_status {
+        GDX_TRY(begin_call(idx, "gdx_extend_many"));
+        if (n == 0) return GDX_OK;
+        if (!starts || !ends || !io_symbols) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        DeviceGuard guard(idx->device);
+        WsLease lease(idx);
+        Workspace *ws = lease.w;
+        if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaStream_t st = ws->slot[0].stream;
+        CUDA_TRY(ws->starts.reserve(n * 8));
+        CUDA_TRY(ws->ends.reserve(n * 8));
+        CUDA_TRY(ws->symbols.reserve(n));
+        CUDA_TRY(cudaMemsetAsync(ws->small.d, 0xff, 16, st));  // [0] invalid symbol, [1] cursor out of bounds
+        CUDA_TRY(cudaStreamSynchronize(st));
+        // large pageable cursor arrays go through pinned staging (see search_host)
+        Slot &sl0 = ws->slot[0];
+        const bool stage = n * 8 >= kStageMinBytes && !(is_pinned(starts) && is_pinned(ends));
+        const uint64_t *src_s = starts, *src_e = ends;
+        if (stage) {
+            CUDA_TRY(sl0.h_out_a.reserve(n * 8));
+            CUDA_TRY(sl0.h_out_b.reserve(n * 8));
+            HostPool::get().copy(sl0.h_out_a.p, starts, n * 8);
+            HostPool::get().copy(sl0.h_out_b.p, ends, n * 8);
+            src_s = (const uint64_t *)sl0.h_out_a.p;
+            src_e = (const uint64_t *)sl0.h_out_b.p;
+        }
+        uint64_t *d_s = ws->starts.as<uint64_t>(), *d_e = ws->ends.as<uint64_t>();
+        uint8_t *d_c = ws->symbols.as<uint8_t>();
+        // chunks of 1 M cursors round-robin over the workspace streams: upload, kernel and download of
+        // neighbouring chunks overlap (PCIe is full duplex).  Results land in the staging buffers (pageable
+        // caller arrays: handed over only on success) or directly in the caller's pinned arrays (on error their
+        // contents are unspecified -- the reference panics in that case).
+        const uint64_t kChunk = 1ull << 20;
+        uint64_t launches = 0;
+        for (uint64_t off = 0, k = 0; off < n; off += kChunk, ++k) {
+            const uint64_t cn = std::min<uint64_t>(kChunk, n - off);
+            cudaStream_t cs = ws->slot[k % kSlots].stream;
+            CUDA_TRY(cudaMemcpyAsync(d_s + off, src_s + off, cn * 8, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_e + off, src_e + off, cn * 8, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(d_c + off, io_symbols + off, cn, cudaMemcpyHostToDevice, cs));
+            GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+                k_extend<decltype(L)><<<(unsigned)div_up(cn, 256), 256, 0, cs>>>(idx->dev, d_s + off, d_e + off, d_c + off, cn,
+                                                                               ws->small.d, off);
+                return GDX_OK;
+            }));
+            CUDA_TRY(cudaGetLastError());
+            ++launches;
+            uint64_t *dst_s = stage ? (uint64_t *)sl0.h_out_a.p : starts, *dst_e = stage ? (uint64_t *)sl0.h_out_b.p : ends;
+            CUDA_TRY(cudaMemcpyAsync(dst_s + off, d_s + off, cn * 8, cudaMemcpyDeviceToHost, cs));
+            CUDA_TRY(cudaMemcpyAsync(dst_e + off, d_e + off, cn * 8, cudaMemcpyDeviceToHost, cs));
+        }
+        for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(ws->slot[s2].stream));
+        CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        t_stats.kernel_launches = launches;
+        if (ws->small.h[1] != kNoError)  // checked on the device: text_with_rank_support/mod.rs:106-110
+            return fail(GDX_ERR_BAD_ARG, "cursor %llu is outside [0, text_len]", (unsigned long long)ws->small.h[1]);
+        if (ws->small.h[0] != kNoError) {
+            t_error_query = ws->small.h[0];
+            return fail(GDX_ERR_INVALID_SYMBOL, "cursor %llu: symbol in io representation should be valid (alphabet.rs:195-198)",
+                        (unsigned long long)ws->small.h[0]);
+        }
+        if (stage) {
+            HostPool::get().copy(starts, sl0.h_out_a.p, n * 8);
+            HostPool::get().copy(ends, sl0.h_out_b.p, n * 8);
+        }
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_cursor_for_query(const gdx_index *idx, const uint8_t *query, uint64_t len, uint64_t *start,
                                            uint64_t *end) {
-    if (!idx || !start || !end || (len && !query)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    // single-query path of the reference (lib.rs:217-235): when the lookup-table interval is already
-    // empty, the next symbol to the left is still translated (and may panic) before the loop breaks.
-    const uint32_t D = idx->h.lookup_depth;
-    gdx_queries q = {query, nullptr, len, 1};
-    uint8_t dummy = 0;
-    if (len == 0) q.bytes = &dummy;
-    gdx_status st = gdx_cursors_many(idx, &q, start, end);
-    if (st != GDX_OK) return st;
-    if (D > 0 && len > D && *start == *end) {
-        gdx_queries suffix = {query + (len - D), nullptr, D, 1};
-        uint64_t s2 = 0, e2 = 0;
-        GDX_TRY(gdx_cursors_many(idx, &suffix, &s2, &e2));
-        if (s2 == e2 && idx->h.io_to_dense[query[len - D - 1]] == 0) {
-            t_error_query = 0;
-            return fail(GDX_ERR_INVALID_SYMBOL, "symbol in io representation should be valid (alphabet.rs:195-198)");
+    return guarded([&]() -> gdx_status {
+        if (!idx || !start || !end || (len && !query)) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        // single-query path of the reference (lib.rs:217-235): when the lookup-table interval is already
+        // empty, the next symbol to the left is still translated (and may panic) before the loop breaks.
+        const uint32_t D = idx->h.lookup_depth;
+        gdx_queries q = {query, nullptr, len, 1};
+        uint8_t dummy = 0;
+        if (len == 0) q.bytes = &dummy;
+        gdx_status st = gdx_cursors_many(idx, &q, start, end);
+        if (st != GDX_OK) return st;
+        if (D > 0 && len > D && *start == *end) {
+            gdx_queries suffix = {query + (len - D), nullptr, D, 1};
+            uint64_t s2 = 0, e2 = 0;
+            GDX_TRY(gdx_cursors_many(idx, &suffix, &s2, &e2));
+            if (s2 == e2 && idx->h.io_to_dense[query[len - D - 1]] == 0) {
+                t_error_query = 0;
+                return fail(GDX_ERR_INVALID_SYMBOL, "symbol in io representation should be valid (alphabet.rs:195-198)");
+            }
         }
-    }
-    return GDX_OK;
+        return GDX_OK;
+    });
 }
 
 // ================================================================================================

@@ -400,3 +400,24 @@ def test_rust_binding_is_generated_from_the_header():
     assert used and used <= declared_in_rust
     integ = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     assert set(re.findall(r"ffi::(gdx_\w+)\(", integ)) <= declared_in_rust
+
+
+def test_bad_arguments_return_codes_instead_of_crashing():
+    """nothing may unwind (or abort) across the C boundary; inconsistent sizes are GDX_ERR_BAD_ARG"""
+    import genedex_b200 as gdx
+    from genedex_b200.index import _alphabet_struct
+    lib = gdx._lib.load()
+    a = _alphabet_struct(gdx.alphabet.ascii_dna())
+    text = np.frombuffer(b"ACGTACGT", dtype=np.uint8)
+    bad_off = np.array([0, 8, 3], dtype=np.uint64)  # decreasing
+    dense, sent, cnt = np.zeros(64, dtype=np.uint8), np.zeros(4, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+    rc = lib.gdx_concat_texts(text.ctypes.data, bad_off.ctypes.data, 2, C.byref(a), dense.ctypes.data, sent.ctypes.data,
+                              cnt.ctypes.data)
+    assert rc == gdx._lib.GDX_ERR_BAD_ARG and b"non-decreasing" in lib.gdx_last_error_message()
+    cfg = gdx._lib.gdx_config(1, 4, 0, 1, 2, -1, 0, 0)
+    h = C.c_void_p()
+    assert lib.gdx_index_build(text.ctypes.data, bad_off.ctypes.data, 2, C.byref(a), C.byref(cfg), C.byref(h)) \
+        in (gdx._lib.GDX_ERR_BAD_ARG, gdx._lib.GDX_ERR_CUDA)
+    # a corrupt image header is refused before anything is allocated from it (no device needed to find out)
+    hdr = (C.c_uint8 * lib.gdx_index_header_bytes())()
+    assert lib.gdx_index_adopt_image(hdr, C.c_void_p(16), -1, 0, C.byref(h)) == gdx._lib.GDX_ERR_BAD_ARG
