@@ -360,6 +360,7 @@ def run_ours(args, rank, world, local_rank):
     import genedex_b200 as gdx
     from genedex_b200.replicate import ReplicaSet, broadcast_index, replicate_transport, shard_range, torch_share_id
     lib = gdx._lib.load()
+    pool_threads = int(lib.gdx_host_pool_resize(0))  # the library's default for the CPUs this rank may use
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     m, nq = args.query_len, args.queries
@@ -483,7 +484,7 @@ def run_ours(args, rank, world, local_rank):
            "host_buffers": "pinned IO bytes in, pinned uint64 counts out; inside the call the library's host thread pool "
                            "packs chunks to 2 bits while the PCIe link is busy and sends chunks as they are when it is idle",
            "packed_queries_per_step": int(reduce(float(st.packed_queries), "sum")),
-           "host_pool_threads_per_rank": host_cores,
+           "host_cores_per_rank": host_cores, "host_pool_threads_per_rank": pool_threads,
            "ms_per_step_by_rank_numa_cores": e2e_by_rank, "gpu_launches_per_step": int(reduce(float(st.kernel_launches), "sum"))}
 
     extras = not args.no_extras

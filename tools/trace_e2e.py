@@ -1,4 +1,4 @@
-"""Per-chunk timeline of gdx_count_many / gdx_locate_many (GDX_TRACE=1) on a 15 M-query batch from pageable memory."""
+"""Per-chunk timeline of gdx_count_many / gdx_locate_many (GDX_TRACE=1) on a 30 M-query batch, pinned buffers."""
 import os, sys, time
 os.environ["GDX_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,14 +6,14 @@ import numpy as np, torch
 import bench
 import genedex_b200 as gdx
 args = bench.parse_args()
-nq = min(args.queries, 15_000_000)
+nq = min(args.queries, 30_000_000)
 dev = torch.device("cuda", 0)
 text = bench.make_text_on_device(args.text_len, args.n_fraction, dev)
-qn = np.empty(nq * args.query_len, dtype=np.uint8)
+qn = torch.empty(nq * args.query_len, dtype=torch.uint8).pin_memory().numpy()
 bench.fill_query_range(text, qn, np.zeros(nq, dtype=np.int64), 0, nq, args.query_len, dev)
 text_host = text.cpu().numpy(); del text; torch.cuda.empty_cache()
 idx = gdx.FmIndexConfig("u32").construct_on_device(True).construct_index_packed(text_host, np.array([0, text_host.size], dtype=np.uint64), gdx.alphabet.ascii_dna_with_n())
-cn = np.zeros(nq, dtype=np.uint64)
+cn = torch.zeros(nq, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
 for i in range(3):
     t0 = time.perf_counter()
     idx.count_many_packed(qn, None, args.query_len, nq, out=cn)
