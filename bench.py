@@ -527,7 +527,7 @@ def run_ours(args, rank, world, local_rank):
     R = int(info.rank_record_bytes)
     locate_sample = None
     if not args.no_locate:
-        hit_off = np.zeros(nq + 1, dtype=np.uint64)
+        hit_off = torch.zeros(nq + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
         state = {}
 
         def loc():

@@ -8,6 +8,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <thread>
 #include <cstdarg>
 #include <cstdio>
@@ -52,10 +53,12 @@ gdx_status fail(gdx_status st, const char *fmt, ...) {
 #define CUDA_TRY(expr)                                                                           \
     do {                                                                                         \
         cudaError_t _e = (expr);                                                                 \
-        if (_e != cudaSuccess)                                                                   \
+        if (_e != cudaSuccess) {                                                                 \
+            cudaGetLastError(); /* a failed allocation must not fail the next call's error check */ \
             return fail(_e == cudaErrorMemoryAllocation ? GDX_ERR_OOM : GDX_ERR_CUDA,            \
                         "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,        \
                         __LINE__);                                                               \
+        }                                                                                        \
     } while (0)
 
 #define GDX_TRY(expr)                  \
@@ -1885,7 +1888,11 @@ struct LocatePipe {
         int slot;
         uint64_t q0, cq;
         bool valid = false;
-    } pending, pending_offsets;
+    } pending_offsets;
+    // chunks whose hit totals are on their way to the host, oldest first.  A chunk is finished two chunks after
+    // it was issued (kSlots - 1): by then its total has long arrived, so the issuing thread never waits for a
+    // search kernel -- and its slot is only reused by the chunk after that.
+    std::deque<Pending> pending;
     bool stage_offsets = false;  // the caller's hit_offsets array is pageable
 
     // hand the previous chunk's CSR offsets from the slot's pinned staging to the caller
@@ -1916,14 +1923,18 @@ struct LocatePipe {
         CUDA_TRY(cudaMemcpyAsync(sl.h_words, sl.local_off.as<uint64_t>() + cq, 8, cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(cudaMemcpyAsync(sl.h_words + 1, sl.d_words, 8, cudaMemcpyDeviceToHost, sl.stream));
         CUDA_TRY(cudaEventRecord(sl.ev_total, sl.stream));
-        pending = Pending{slot, q0, cq, true};
+        pending.push_back(Pending{slot, q0, cq, true});
         t_stats.kernel_launches += 2;
         return GDX_OK;
     }
 
-    Pending take_pending() {
-        Pending p = pending;
-        pending.valid = false;
+    // the oldest chunk once more than `keep` are waiting (keep = 0: the oldest one, if any)
+    Pending take_pending(size_t keep) {
+        Pending p;
+        if (pending.size() > keep) {
+            p = pending.front();
+            pending.pop_front();
+        }
         return p;
     }
 
@@ -2337,9 +2348,8 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         if (chunk_packed || prepacked) packed_queries += cq;
         exception_queries += nx;
         if (lp) {  // locate continues per chunk; the previous chunk is finished while this one runs
-            const LocatePipe::Pending prev = lp->take_pending();
             GDX_TRY(lp->stage_counts(sl, k % kSlots, q0, cq));
-            GDX_TRY(lp->finish(prev));
+            GDX_TRY(lp->finish(lp->take_pending(kSlots - 1)));
         } else if (stage_out) {  // results go to pinned staging; the previous chunk's are handed over meanwhile
             PendingOut prev = pend_out;
             CUDA_TRY(sl.h_out_a.reserve(cq * dev_elem));
@@ -2365,7 +2375,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         q0 = q1;
         ++k;
     }
-    if (lp) GDX_TRY(lp->finish(lp->take_pending()));
+    while (lp && !lp->pending.empty()) GDX_TRY(lp->finish(lp->take_pending(0)));
     if (lp) GDX_TRY(lp->flush_offsets());
     GDX_TRY(finish_out(pend_out));
     const double t_issue = trace ? std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count() : 0;
@@ -2514,6 +2524,7 @@ gdx_status acquire_pinned_hits(const gdx_index *idx, uint64_t bytes, void **out,
         cudaError_t e = cudaMallocHost(&best->p, want);
         if (e != cudaSuccess) {
             best->p = nullptr;
+            cudaGetLastError();
             return fail(GDX_ERR_OOM, "pinned host allocation of %llu bytes failed: %s", (unsigned long long)want,
                         cudaGetErrorString(e));
         }
@@ -2733,6 +2744,8 @@ gdx_status run_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t fi
     GDX_TRY(check_queries(replicas[0], queries));
     std::vector<ShardResult> res(n_local);
     auto run = [&](uint32_t k) {
+        const bool helps = HostPool::t_caller_helps;
+        if (n_local > 1) HostPool::t_caller_helps = false;  // the pool alone does the staging work of all shards
         uint64_t b = 0, e = 0;
         gdx_shard_range(queries->nq, first_shard + k, n_shards, &b, &e);
         ShardResult &r = res[k];
@@ -2742,6 +2755,7 @@ gdx_status run_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t fi
             r.error_query = b + t_error_query;
         }
         r.stats = t_stats;
+        HostPool::t_caller_helps = helps;
     };
     std::vector<std::thread> threads;
     for (uint32_t k = 1; k < n_local; ++k) threads.emplace_back(run, k);

@@ -110,6 +110,8 @@ HostPool::~HostPool() {
     delete impl_;
 }
 
+thread_local bool HostPool::t_caller_helps = true;
+
 HostPool &HostPool::get() {
     static HostPool pool;
     return pool;
@@ -119,7 +121,7 @@ unsigned HostPool::threads() const { return (unsigned)impl_->workers.size() + 1;
 
 void HostPool::parallel_for(uint64_t pieces, const std::function<void(uint64_t)> &fn) {
     if (pieces == 0) return;
-    if (pieces == 1 || impl_->workers.empty()) {
+    if (pieces == 1 || impl_->workers.empty() || (!t_caller_helps && pieces <= 2)) {
         for (uint64_t k = 0; k < pieces; ++k) fn(k);
         return;
     }
@@ -131,7 +133,7 @@ void HostPool::parallel_for(uint64_t pieces, const std::function<void(uint64_t)>
         impl_->queue.push_back(job);
     }
     impl_->cv.notify_all();
-    impl_->work(job);
+    if (t_caller_helps) impl_->work(job);
     std::unique_lock<std::mutex> lk(impl_->mu);
     impl_->done_cv.wait(lk, [&] { return job->done.load(std::memory_order_acquire) == job->pieces; });
 }

@@ -30,6 +30,9 @@ public:
     void parallel_for(uint64_t pieces, const std::function<void(uint64_t)> &fn);
     void copy(void *dst, const void *src, uint64_t bytes);
     void widen_u32(uint64_t *dst, const uint32_t *src, uint64_t n);
+    // false on the per-GPU threads of a sharded call: several callers at once would otherwise put more runnable
+    // threads on the machine than it has CPUs (each of them only waits for its job then)
+    static thread_local bool t_caller_helps;
 
 private:
     HostPool();

@@ -99,7 +99,8 @@ def test_packed_batch_reports_invalid_symbols_lazily(gdx, dna_case):
     c = dna_case
     oidx, pidx = c["oidx"], c["pidx"]
     text = c["texts"][0]
-    qs = [text[1000 + 40 * i: 1050 + 40 * i] for i in range(60_000)]  # 3 MB
+    qs = [text[1000 + 19 * i: 1050 + 19 * i] for i in range(60_000)]  # 3 MB of length-50 windows inside text 0
+    assert all(len(q) == 50 for q in qs)
     qs = [q if b"N" not in q else b"ACGTACGT" for q in qs]
     absent = b"ACGT" * 12 + b"!!"          # '!' is left of where the interval of this random 48-mer is long empty...
     qs[30_000] = b"!" + b"ACGT" * 12 + b"A"   # ... so an invalid byte at the far left of an absent query is never reached
@@ -231,3 +232,20 @@ def test_sharded_calls_on_one_device(gdx, dna_case):
     with pytest.raises(gdx.InvalidSymbolError) as ei:
         rs.count_many_packed(bdata, boff)
     assert ei.value.query == 70_000
+
+
+def test_a_result_that_cannot_fit_is_refused_and_leaves_the_index_usable(gdx, dna_case):
+    """30 000 empty queries match every row (lib.rs:202-210: the empty cursor is (0, n)): 6 * 10^10 hits.  The
+    library says GDX_ERR_OOM instead of dying, and the next call is not poisoned by the failed allocation."""
+    c = dna_case
+    pidx, oidx = c["pidx"], c["oidx"]
+    qs = [b""] * 30_000 + [b"ACGT"]
+    data, off = O.pack(qs)
+    n = pidx.total_text_len()
+    assert pidx.count_many_packed(data, off).tolist() == [n] * 30_000 + [int(oidx.count(b"ACGT"))]
+    with pytest.raises(MemoryError):
+        pidx.locate_many_packed(data, off)
+    data2, off2 = O.pack([b"ACGTAC", b"TTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"])
+    ooff, ohits = oidx.locate_many_packed(data2, off2)
+    poff, phits = pidx.locate_many_packed(data2, off2)
+    assert np.array_equal(ooff, poff) and np.array_equal(ohits, phits)
