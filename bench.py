@@ -368,10 +368,19 @@ def run_ours(args, rank, world, local_rank):
     snq = e - b
     PACKED = gdx._lib.GDX_QUERIES_PACKED_2BIT
 
+    # a second, CPU-only group: ranks that merely wait (while rank 0 drives every GPU by itself, or builds the
+    # oracle) must not sit in an NCCL kernel that spins on their GPU
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def reduce(x, op="max"):
         if world == 1:
@@ -638,7 +647,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- single process, all GPUs: ONE gdx_count_many_sharded call from rank 0 (the other ranks idle) -------
     single = None
     if world > 1 and extras:
-        barrier()
+        cpu_barrier()
         if rank == 0:
             t0 = time.perf_counter()
             all_rs = ReplicaSet.replicate(pidx, [d for d in range(world) if d != local_rank])
@@ -662,7 +671,7 @@ def run_ours(args, rank, world, local_rank):
                       "note": "one host process, one thread + staging arena per GPU, one shared staging pool; the other "
                               "ranks sit in a barrier meanwhile"}
             del all_rs
-        barrier()
+        cpu_barrier()
 
     # ---- oracle: parity on a sample of EVERY shard (+ CPU baseline at N = 1) -------------------------------
     cpu, parity = None, None
@@ -715,6 +724,7 @@ def run_ours(args, rank, world, local_rank):
                    "gpu_counts_equal_oracle_on_sample": True}
         del oidx
 
+    cpu_barrier()  # everyone leaves together (rank 0 was busy with the oracle meanwhile)
     if rank != 0:
         return
     out = assemble(args, world, info, st, kernel_ms, step_ms, e2e, locate, no_accel, single, cpu, parity, peaks, clock_info,
