@@ -682,7 +682,9 @@ void auto_seed_table(gdx_index *idx) {
         depth = (uint32_t)atoi(e);
     } else {
         if (idx->h.accel_flags & kAccelNoSeedTable) return;
-        while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= idx->h.n) ++depth;
+        // about two entries per text position at most: one level deeper than "ns^d <= n" removes one more LF step
+        // per query (3.1 Gbp: depth 16, 34 GB, 0.82 instead of 0.97 ms per 7.5 M queries; profiles/README.md)
+        while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= 2 * idx->h.n) ++depth;
         const uint64_t esz = idx->h.wide ? 16 : 8, room = accel_room(idx);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
@@ -744,7 +746,7 @@ gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
         gdx_status st = dispatch_layout(h.layout, [&](auto L) -> gdx_status {
             using LT = decltype(L);
             if constexpr (!std::is_same<LT, K32>::value) {
-                constexpr int B = sizeof(typename LT::Planes) / 16;
+                constexpr int B = LT::kPlanes;
                 k_pack_kg<B><<<(unsigned)h.n_superblocks, 512>>>(src.d_bwt, h.n, h.sigma, h.layout.stride,
                                                                  base + h.off_records, h.n_records, sbc);
             }

@@ -211,6 +211,7 @@ struct K32 {
 template <int B>
 struct KG {
     static constexpr uint32_t kLog2P = 7;
+    static constexpr int kPlanes = B;
     static constexpr int kSearchMinBlocks = B <= 3 ? 5 : (B <= 5 ? 5 : 3);
     static constexpr int kVerifyMinBlocks = B <= 3 ? 5 : (B <= 5 ? GDX_KG5_VERIFY_MIN_BLOCKS : 3);
     // The record is fetched as whole 32 B sectors: kSectors 256-bit loads cover the B planes (16 B each) and the
