@@ -766,8 +766,9 @@ def assemble(args, world, info, st, kernel_ms, step_ms, e2e, locate, no_accel, s
                                  args.sampling_rate, args.lookup_depth, int(info.rank_bytes) / 1e9, int(info.sample_bytes) / 1e9,
                                  int(info.text_bytes) / 1e9, int(info.inverse_sample_bytes) / 1e9,
                                  int(info.dense_suffix_array_bytes) / 1e9, seed_depth, int(info.seed_table_bytes) / 1e9)),
-                   "l2": "inputs larger than L2: 1.55 GB rank records + 12.4 GB suffix array + 8.6 GB seed table accessed at "
-                         "random, %.2f GB of queries per GPU" % (nq // world * m / 1e9),
+                   "l2": "inputs larger than L2: %.2f GB rank records + %.1f GB suffix array + %.1f GB seed table accessed at "
+                         "random, %.2f GB of queries per GPU" % (int(info.rank_bytes) / 1e9, int(info.dense_suffix_array_bytes) / 1e9,
+                                                                 int(info.seed_table_bytes) / 1e9, nq // world * m / 1e9),
                    "index_image_bytes": int(info.image_bytes), "dense_suffix_array_bytes": int(info.dense_suffix_array_bytes),
                    "seed_table_depth": seed_depth, "seed_table_bytes": int(info.seed_table_bytes), "rank_record_bytes": R,
                    "lf_steps_per_step": int(lf_steps), "verified_queries_per_step": int(verified),

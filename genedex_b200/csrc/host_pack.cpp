@@ -288,19 +288,60 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
     if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
 }
 
+// AVX-512 VBMI: the whole 256-entry table in four registers, two vpermi2b + one blend per 64 bytes (works for
+// any alphabet, no nibble split needed), 128 bytes per iteration.  Table value 0x80 = no code.
+#define GDX_VBMI __attribute__((target("avx512f,avx512bw,avx512vbmi"), always_inline)) static inline
+GDX_VBMI __m512i vbmi_lookup(__m512i x, __m512i t0, __m512i t1, __m512i t2, __m512i t3) {
+    const __m512i lo = _mm512_permutex2var_epi8(t0, x, t1);  // index bits 0..6 select among 128 entries
+    const __m512i hi = _mm512_permutex2var_epi8(t2, x, t3);
+    return _mm512_mask_blend_epi8(_mm512_movepi8_mask(x), lo, hi);  // bit 7 of the byte picks the upper half
+}
+GDX_VBMI __m128i vbmi_squeeze(__m512i code) {
+    const __m512i mul_1_4 = _mm512_set1_epi16(0x0401), mul_1_16 = _mm512_set1_epi32(0x00100001);
+    return _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(code, mul_1_4), mul_1_16));
+}
+__attribute__((target("avx512f,avx512bw,avx512vbmi"))) static void pack2_vbmi(const PackTable &t, const uint8_t *src, uint64_t n,
+                                                                              uint8_t *dst, uint64_t pos0,
+                                                                              std::vector<uint64_t> &exc) {
+    alignas(64) uint8_t tab[256];
+    for (int x = 0; x < 256; ++x) tab[x] = t.code[x] == 0xff ? 0x80 : t.code[x];
+    const __m512i t0 = _mm512_load_si512(tab), t1 = _mm512_load_si512(tab + 64), t2 = _mm512_load_si512(tab + 128),
+                  t3 = _mm512_load_si512(tab + 192);
+    uint64_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        __m512i c0 = vbmi_lookup(_mm512_loadu_si512((const void *)(src + i)), t0, t1, t2, t3);
+        __m512i c1 = vbmi_lookup(_mm512_loadu_si512((const void *)(src + i + 64)), t0, t1, t2, t3);
+        const __mmask64 bad0 = _mm512_movepi8_mask(c0), bad1 = _mm512_movepi8_mask(c1);
+        if (bad0 | bad1) {
+            c0 = _mm512_maskz_mov_epi8(~bad0, c0);
+            c1 = _mm512_maskz_mov_epi8(~bad1, c1);
+            for (uint64_t mm = bad0; mm; mm &= mm - 1) exc.push_back(pos0 + i + (uint64_t)__builtin_ctzll(mm));
+            for (uint64_t mm = bad1; mm; mm &= mm - 1) exc.push_back(pos0 + i + 64 + (uint64_t)__builtin_ctzll(mm));
+        }
+        _mm_storeu_si128((__m128i *)(dst + (i >> 2)), vbmi_squeeze(c0));
+        _mm_storeu_si128((__m128i *)(dst + (i >> 2) + 16), vbmi_squeeze(c1));
+    }
+    if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
+}
+
 void pack2_serial(const PackTable &t, const uint8_t *src, uint64_t n, uint8_t *dst, uint64_t pos0,
                   std::vector<uint64_t> &exceptions) {
-    // GDX_PACK_ISA = scalar | avx2 | avx512 caps the instruction set (tests, A/B runs); GDX_PACK_SCALAR=1 = scalar
+    // GDX_PACK_ISA = scalar | avx2 | avx512 | vbmi caps the instruction set (tests, A/B runs); GDX_PACK_SCALAR=1 = scalar
     static const int level = [] {
         int lvl = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512f") ? 2 : (__builtin_cpu_supports("avx2") ? 1 : 0);
+        if (lvl == 2 && __builtin_cpu_supports("avx512vbmi")) lvl = 3;
         if (const char *e = getenv("GDX_PACK_ISA")) {
-            const int cap = !strcmp(e, "scalar") ? 0 : (!strcmp(e, "avx2") ? 1 : 2);
+            const int cap = !strcmp(e, "scalar") ? 0 : (!strcmp(e, "avx2") ? 1 : (!strcmp(e, "avx512") ? 2 : 3));
             lvl = std::min(lvl, cap);
         }
         if (getenv("GDX_PACK_SCALAR") && atoi(getenv("GDX_PACK_SCALAR"))) lvl = 0;
         return lvl;
     }();
-    if (t.simd_ok && level == 2) pack2_avx512(t, src, n, dst, pos0, exceptions);
+    // the nibble-split AVX-512 loop is the fastest where the alphabet allows it (15.6 vs 14.6 GB/s per thread for the
+    // full-table VBMI loop, which in turn serves every other alphabet at SIMD speed); GDX_PACK_ISA=vbmi forces VBMI
+    static const bool force_vbmi = getenv("GDX_PACK_ISA") && !strcmp(getenv("GDX_PACK_ISA"), "vbmi");
+    if (level == 3 && (force_vbmi || !t.simd_ok)) pack2_vbmi(t, src, n, dst, pos0, exceptions);
+    else if (t.simd_ok && level >= 2) pack2_avx512(t, src, n, dst, pos0, exceptions);
     else if (t.simd_ok && level == 1) pack2_avx2(t, src, n, dst, pos0, exceptions);
     else pack2_scalar(t, src, n, dst, pos0, exceptions);
 }
