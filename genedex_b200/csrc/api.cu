@@ -682,9 +682,10 @@ void auto_seed_table(gdx_index *idx) {
         depth = (uint32_t)atoi(e);
     } else {
         if (idx->h.accel_flags & kAccelNoSeedTable) return;
-        // about two entries per text position at most: one level deeper than "ns^d <= n" removes one more LF step
-        // per query (3.1 Gbp: depth 16, 34 GB, 0.82 instead of 0.97 ms per 7.5 M queries; profiles/README.md)
-        while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= 2 * idx->h.n) ++depth;
+        // the deepest level with at most four entries per text position (then most k-mers of the text have one row
+        // and almost no LF step is left): 3.1 Gbp DNA -> depth 16 (34 GB; 0.82 instead of 0.97 ms per 7.5 M queries
+        // against depth 15), 500 M residues of protein -> depth 7 (10 GB); the budget below has the last word
+        while (seed_entries(idx->h.ns, depth + 1) && seed_entries(idx->h.ns, depth + 1) <= 4 * idx->h.n) ++depth;
         const uint64_t esz = idx->h.wide ? 16 : 8, room = accel_room(idx);
         size_t free_b = 0, total_b = 0;
         if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;

@@ -131,7 +131,7 @@ class FmIndexConfig:
 
     def seed_table(self, allow: bool = True) -> "FmIndexConfig":
         """Allow (default) or forbid the seed table accelerator: one level of a lookup table deeper than the
-        configured one (largest depth with ns^depth <= 2 * text length), built when device memory is ample
+        configured one (largest depth with ns^depth <= 4 * text length), built when device memory is ample
         (`FmIndex.set_seed_table_depth` forces a depth).  Results and error behaviour are identical."""
         self._flags = (self._flags & ~_lib.GDX_FLAG_NO_SEED_TABLE) | (0 if allow else _lib.GDX_FLAG_NO_SEED_TABLE)
         return self

@@ -273,7 +273,7 @@ gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
  * steps produce (also when it is empty), every other query takes the configured path.  Results, error
  * behaviour and reported lookup_table_depth are unchanged.
  * Built automatically after construction / load / adopt / replicate with the largest d such that
- * ns^d <= 2 * text length (about two entries per text position), under the same policy as the dense suffix array (GDX_FLAG_NO_SEED_TABLE,
+ * ns^d <= 4 * text length (at most four entries per text position), under the same policy as the dense suffix array (GDX_FLAG_NO_SEED_TABLE,
  * gdx_config.accelerator_budget_bytes, else a quarter of the free memory; GDX_SEED_TABLE=0 / =d overrides it
  * for measurements).  depth > configured depth (re)builds it at that depth now (GDX_ERR_OOM /
  * GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  GDX_ERR_BUSY as above. */

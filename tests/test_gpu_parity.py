@@ -777,8 +777,8 @@ def test_seed_table_accelerator_changes_no_result(gdx):
         n = pidx.total_text_len()
         if "GDX_SEED_TABLE" not in os.environ:
             auto = pidx.info().seed_table_depth
-            # the largest level with at most two entries per text position
-            assert 4 ** auto <= 2 * n < 4 ** (auto + 1) and pidx.info().seed_table_bytes in (8 * 4 ** auto, 16 * 4 ** auto)
+            # the largest level with at most four entries per text position
+            assert 4 ** auto <= 4 * n < 4 ** (auto + 1) and pidx.info().seed_table_bytes in (8 * 4 ** auto, 16 * 4 ** auto)
         valid, raising = [], []
         for _ in range(1500):
             t = rng.choice(texts)
