@@ -2104,6 +2104,27 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         return GDX_OK;
     };
     for (int s2 = 0; s2 < kSlots; ++s2) ws->slot[s2].h2d_pending = false;
+    // Large batches: size every slot once for the largest chunk this call can cut (the adaptive schedule cuts
+    // different chunks in every call; growing a buffer in mid-flight means cudaFree / cudaFreeHost + a new
+    // allocation, milliseconds each, with the streams drained).  The streams are idle here.
+    if (nq && total_in >= kStageMinBytes) {
+        const uint64_t max_sym = std::min<uint64_t>(total_syms, 4 * kChunkMax) + 64;
+        const uint64_t max_q = qs->fixed_len ? std::min<uint64_t>(nq, max_sym / qs->fixed_len + 1) : 0;
+        for (int s2 = 0; s2 < kSlots; ++s2) {
+            Slot &sl = ws->slot[s2];
+            CUDA_TRY(sl.bytes.reserve(max_sym));
+            if (pack_on) CUDA_TRY(sl.h_in.reserve(max_sym / 4 + 8));
+            else if (stage_in) CUDA_TRY(sl.h_in.reserve(std::min<uint64_t>(total_in, kChunkMax) + 64));
+            if (max_q && !dev_a) {
+                CUDA_TRY(sl.out_a.reserve(max_q * 8));
+                if (mode == 0 || lp) CUDA_TRY(sl.out_b.reserve(max_q * 8));
+                if (stage_out) {
+                    CUDA_TRY(sl.h_out_a.reserve(max_q * dev_elem));
+                    if (mode == 0) CUDA_TRY(sl.h_out_b.reserve(max_q * dev_elem));
+                }
+            }
+        }
+    }
     std::vector<uint64_t> exc;       // symbol positions (chunk relative) the packer could not encode
     std::vector<uint32_t> exc_q;     // the queries (chunk relative) that hold them
     uint64_t packed_queries = 0, exception_queries = 0, h2d_bytes = 0, d2h_bytes = 0;
