@@ -25,3 +25,13 @@ def test_config_at_full_size(config):
     res = list(run_configs.run([config], _scale()))
     assert len(res) == 1 and "parity" in res[0], res
     print(res[0])
+
+
+def test_repeat_rich_text_at_two_percent():
+    """C2r (tools/run_configs.py: a third of the text written by diverged repeat copies) at 2 % scale: intervals stay
+    wide for most of a query that falls into a repeat, hundreds of hits per query -- counts and hits against the
+    oracle, every sampled query located at its origin.  The full size runs in profiles/r2_configs.jsonl."""
+    import run_configs
+    res = list(run_configs.run(["c2r"], 0.02))
+    assert len(res) == 1 and "parity" in res[0], res
+    assert res[0]["hits"] > 20 * res[0]["queries"] and res[0]["lf_steps"] > 3 * res[0]["queries"]
