@@ -2782,8 +2782,14 @@ gdx_status run_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t fi
         HostPool::t_caller_helps = helps;
     };
     std::vector<std::thread> threads;
-    for (uint32_t k = 1; k < n_local; ++k) threads.emplace_back(run, k);
+    threads.reserve(n_local);
+    uint32_t started = 1;
+    try {
+        for (; started < n_local; ++started) threads.emplace_back(run, started);
+    } catch (const std::exception &) {  // could not start a thread: the shards without one run here, one after the other
+    }
     run(0);
+    for (uint32_t k = started; k < n_local; ++k) run(k);
     for (auto &t : threads) t.join();
     gdx_stats sum = {};
     gdx_status st = GDX_OK;
