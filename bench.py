@@ -555,8 +555,26 @@ def run_ours(args, rank, world, local_rank):
         ns_ = min(snq, 20_000)  # this shard's sample for the oracle comparison on rank 0
         o0 = int(hit_off[b])
         locate_sample = (hit_off[b:b + ns_ + 1] - np.uint64(o0), hits[: int(hit_off[b + ns_]) - o0].copy())
+        hits_head = hits[:1000].copy()
         state["release"]()
-        locate = {"value": nq / (loc_ms * 1e-3), "unit": "queries/s (e2e, host buffers)", "ms_per_step": loc_ms,
+        # the compact result form: u32 hits per query + (u32 text id, u32 position) hits
+        cnt32 = torch.zeros(nq, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        cstate = {}
+
+        def loc_compact():
+            if "release" in cstate:
+                cstate["release"]()
+            _, cstate["views"], cstate["release"] = rs.locate_many_compact_view(q_all, None, m, nq, hit_counts=cnt32)
+        locc_ms, _ = host_steps(loc_compact, reps, 2)
+        cst = rs.stats()
+        assert np.array_equal(cnt32[b:e].astype(np.uint64), counts_all[b:e])
+        assert np.array_equal(cstate["views"][0][:1000].astype(np.uint64), hits_head)
+        cstate["release"]()
+        compact = {"value": nq / (locc_ms * 1e-3), "unit": "queries/s (e2e, host buffers)", "ms_per_step": locc_ms,
+                   "d2h_bytes_per_step": int(reduce(float(cst.d2h_bytes), "sum")),
+                   "results": "gdx_locate_many_sharded_compact: u32 hits per query + gdx_hit32 hits (8 B)"}
+        del cnt32
+        locate = {"value": nq / (loc_ms * 1e-3), "unit": "queries/s (e2e, host buffers)", "ms_per_step": loc_ms, "compact": compact,
                   "hits_per_step": int(reduce(float(lst.hits), "sum")),
                   "locate_walk_steps": int(reduce(float(lst.locate_walk_steps), "sum")),
                   "kernel_ms_locate": reduce(lst.kernel_ms_locate), "kernel_ms_search": reduce(lst.kernel_ms_search),

@@ -124,6 +124,8 @@ PROTOTYPES = {
     "gdx_cursors_many": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp]),
     "gdx_count_many": (C.c_int, [_vp, _P(gdx_queries), _vp]),
     "gdx_locate_many": (C.c_int, [_vp, _P(gdx_queries), _vp, _P(_vp), _P(_u64)]),
+    "gdx_locate_many_compact": (C.c_int, [_vp, _P(gdx_queries), _vp, _P(_vp), _P(_u64)]),
+    "gdx_locate_many_sharded_compact": (C.c_int, [_P(_vp), _u32, _u32, _u32, _P(gdx_queries), _vp, _P(_vp), _P(_u64)]),
     "gdx_locate_intervals": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _P(_vp), _P(_u64)]),
     "gdx_free_hits": (None, [_vp, _vp]),
     "gdx_extend_many": (C.c_int, [_vp, _vp, _vp, _vp, _u64]),

@@ -1868,13 +1868,14 @@ void release_pinned_hits(const gdx_index *idx, void *p);
 // shorter program.  GDX_LOCATE_COMPACT=0/1 forces either for A/B runs.
 template <class L>
 void launch_locate_walk(const gdx_index *idx, const uint64_t *rows, uint64_t n_hits, ulonglong2 *hits,
-                        unsigned long long *d_walk, cudaStream_t stream) {
+                        unsigned long long *d_walk, cudaStream_t stream, bool hit32 = false) {
     static const int forced = getenv("GDX_LOCATE_COMPACT") ? atoi(getenv("GDX_LOCATE_COMPACT")) : -1;
-    const bool compact = forced >= 0 ? forced != 0 : idx->dev.sampling_rate > 1;
-    if (compact)
-        k_locate_walk_compact<L><<<(unsigned)div_up(n_hits, kWalkSlice), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk);
+    const bool compacting = forced >= 0 ? forced != 0 : idx->dev.sampling_rate > 1;
+    if (compacting)
+        k_locate_walk_compact<L><<<(unsigned)div_up(n_hits, kWalkSlice), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk,
+                                                                                           hit32 ? 1 : 0);
     else
-        k_locate_walk<L><<<(unsigned)div_up(n_hits, 256), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk);
+        k_locate_walk<L><<<(unsigned)div_up(n_hits, 256), 256, 0, stream>>>(idx->dev, rows, n_hits, hits, d_walk, hit32 ? 1 : 0);
 }
 
 // State of a pipelined gdx_locate_many: every chunk of the search pipeline continues, on its own
@@ -1883,7 +1884,9 @@ void launch_locate_walk(const gdx_index *idx, const uint64_t *rows, uint64_t n_h
 struct LocatePipe {
     const gdx_index *idx;
     Workspace *ws;
-    uint64_t *hit_offsets;  // caller's array, nq + 1 entries
+    uint64_t *hit_offsets;  // caller's array, nq + 1 entries (NULL in the compact form)
+    uint32_t *hit_counts = nullptr;  // compact form: hits per query, nq entries, instead of the CSR offsets
+    uint64_t hit_bytes = sizeof(gdx_hit);  // 16, or 8 for gdx_hit32
     void *pinned = nullptr; // library-owned pinned hit buffer (grows)
     uint64_t pinned_cap = 0;
     uint64_t total = 0;     // hits of all finished chunks
@@ -1904,7 +1907,8 @@ struct LocatePipe {
         pending_offsets.valid = false;
         Slot &ps = ws->slot[pending_offsets.slot];
         CUDA_TRY(cudaEventSynchronize(ps.ev_out));
-        HostPool::get().copy(hit_offsets + pending_offsets.q0, ps.h_out_a.p, pending_offsets.cq * 8);
+        if (hit_counts) HostPool::get().copy(hit_counts + pending_offsets.q0, ps.h_out_a.p, pending_offsets.cq * 4);
+        else HostPool::get().copy(hit_offsets + pending_offsets.q0, ps.h_out_a.p, pending_offsets.cq * 8);
         return GDX_OK;
     }
 
@@ -1949,13 +1953,13 @@ struct LocatePipe {
         CUDA_TRY(cudaEventSynchronize(sl.ev_total));
         const uint64_t n_hits = sl.h_words[0], nbig = sl.h_words[1], base = total;
         if (n_hits) {
-            if ((base + n_hits) * sizeof(gdx_hit) > pinned_cap) {  // grow the pinned result buffer (rare)
+            if ((base + n_hits) * hit_bytes > pinned_cap) {  // grow the pinned result buffer (rare)
                 for (int s2 = 0; s2 < kSlots; ++s2) CUDA_TRY(cudaStreamSynchronize(ws->slot[s2].stream));
                 void *bigger = nullptr;
                 uint64_t cap = 0;
-                GDX_TRY(acquire_pinned_hits(idx, 2 * (base + n_hits) * sizeof(gdx_hit), &bigger, &cap));
+                GDX_TRY(acquire_pinned_hits(idx, 2 * (base + n_hits) * hit_bytes, &bigger, &cap));
                 if (pinned) {
-                    memcpy(bigger, pinned, base * sizeof(gdx_hit));
+                    memcpy(bigger, pinned, base * hit_bytes);
                     release_pinned_hits(idx, pinned);
                 }
                 pinned = bigger;
@@ -1984,28 +1988,34 @@ struct LocatePipe {
             }
             unsigned long long *d_walk = reinterpret_cast<unsigned long long *>(ws->small.d + 10);
             GDX_TRY(dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
-                launch_locate_walk<decltype(L)>(idx, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk, sl.stream);
+                launch_locate_walk<decltype(L)>(idx, sl.rows.as<uint64_t>(), n_hits, sl.hits.as<ulonglong2>(), d_walk, sl.stream,
+                                                hit_bytes == 8);
                 return GDX_OK;
             }));
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(ev_end, sl.stream));
-            CUDA_TRY(cudaMemcpyAsync((gdx_hit *)pinned + base, sl.hits.p, n_hits * sizeof(gdx_hit),
+            CUDA_TRY(cudaMemcpyAsync((uint8_t *)pinned + base * hit_bytes, sl.hits.p, n_hits * hit_bytes,
                                      cudaMemcpyDeviceToHost, sl.stream));
-            t_stats.d2h_bytes += n_hits * sizeof(gdx_hit);
+            t_stats.d2h_bytes += n_hits * hit_bytes;
             t_stats.kernel_launches += 2 + (nbig ? 1 : 0);
         }
-        k_add_base<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.local_off.as<uint64_t>(), cq, base);
+        // per query: global CSR offsets (u64), or in the compact form just the number of hits (u32; the counts are
+        // narrowed into the offsets buffer, which the expansion above no longer needs)
+        const uint64_t per_q = hit_counts ? 4 : 8;
+        if (hit_counts) k_narrow_u64<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.counts.as<uint64_t>(), cq, sl.local_off.as<uint32_t>());
+        else k_add_base<<<(unsigned)div_up(cq, 256), 256, 0, sl.stream>>>(sl.local_off.as<uint64_t>(), cq, base);
         CUDA_TRY(cudaGetLastError());
+        void *dst = hit_counts ? (void *)(hit_counts + q0) : (void *)(hit_offsets + q0);
         if (stage_offsets) {
             GDX_TRY(flush_offsets());  // frees the staging of the chunk before
-            CUDA_TRY(sl.h_out_a.reserve(cq * 8));
-            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            CUDA_TRY(sl.h_out_a.reserve(cq * per_q));
+            CUDA_TRY(cudaMemcpyAsync(sl.h_out_a.p, sl.local_off.p, cq * per_q, cudaMemcpyDeviceToHost, sl.stream));
             CUDA_TRY(cudaEventRecord(sl.ev_out, sl.stream));
             pending_offsets = Pending{p.slot, q0, cq, true};
         } else {
-            CUDA_TRY(cudaMemcpyAsync(hit_offsets + q0, sl.local_off.p, cq * 8, cudaMemcpyDeviceToHost, sl.stream));
+            CUDA_TRY(cudaMemcpyAsync(dst, sl.local_off.p, cq * per_q, cudaMemcpyDeviceToHost, sl.stream));
         }
-        t_stats.d2h_bytes += cq * 8;
+        t_stats.d2h_bytes += cq * per_q;
         t_stats.kernel_launches += 1;
         total += n_hits;
         return GDX_OK;
@@ -2599,32 +2609,38 @@ gdx_status search_many_impl(const gdx_index *idx, const gdx_queries *queries, vo
 }
 
 // write_last = false: hit_offsets[nq] is left alone (it is the first entry of the next shard's range)
+// hit_counts != NULL: the compact form (gdx_hit32 hits, u32 hits per query, no offsets)
 gdx_status locate_many_impl(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets, gdx_hit **hits,
-                            uint64_t *num_hits, bool write_last = true) {
+                            uint64_t *num_hits, bool write_last = true, uint32_t *hit_counts = nullptr) {
     GDX_TRY(begin_call(idx, "gdx_locate_many"));
     GDX_TRY(check_queries(idx, queries));
-    if (!hit_offsets || !hits || !num_hits) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+    if ((!hit_offsets && !hit_counts) || !hits || !num_hits) return fail(GDX_ERR_BAD_ARG, "output is NULL");
     *hits = nullptr;
     *num_hits = 0;
+    if (hit_counts && (idx->h.wide || idx->h.ntexts > 0xffffffffull))
+        return fail(GDX_ERR_UNSUPPORTED, "32-bit hits need a text shorter than 2^32 symbols");
     std::shared_lock<std::shared_mutex> cfg(idx->cfg_mu);
     DeviceGuard guard(idx->device);
     WsLease lease(idx);
     Workspace *ws = lease.w;
     if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
     const uint64_t n = queries->nq;
-    static const bool pipelined = !(getenv("GDX_LOCATE_PIPELINE") && atoi(getenv("GDX_LOCATE_PIPELINE")) == 0);
+    static const bool pipelined_env = !(getenv("GDX_LOCATE_PIPELINE") && atoi(getenv("GDX_LOCATE_PIPELINE")) == 0);
+    const bool pipelined = pipelined_env || hit_counts;  // (the compact form exists in the pipelined path only)
     if (pipelined) {
         // every chunk of the search pipeline carries on with counts -> scan -> expand -> walk -> D2H
         LocatePipe lp{idx, ws, hit_offsets};
-        lp.stage_offsets = n * 8 >= kStageMinBytes && !is_pinned(hit_offsets);
-        GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * sizeof(gdx_hit), &lp.pinned, &lp.pinned_cap));
+        lp.hit_counts = hit_counts;
+        lp.hit_bytes = hit_counts ? 8 : sizeof(gdx_hit);
+        lp.stage_offsets = n * 8 >= kStageMinBytes && !is_pinned(hit_counts ? (const void *)hit_counts : (const void *)hit_offsets);
+        GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * lp.hit_bytes, &lp.pinned, &lp.pinned_cap));
         gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 8, 2, nullptr, nullptr, &lp);
         if (st != GDX_OK) {
             for (int s2 = 0; s2 < kSlots; ++s2) cudaStreamSynchronize(ws->slot[s2].stream);
             release_pinned_hits(idx, lp.pinned);
             return st;
         }
-        if (write_last) hit_offsets[n] = lp.total;
+        if (write_last && hit_offsets) hit_offsets[n] = lp.total;
         t_stats.hits = lp.total;
         *hits = (gdx_hit *)lp.pinned;
         *num_hits = lp.total;
@@ -2658,6 +2674,14 @@ extern "C" gdx_status gdx_count_many_u32(const gdx_index *idx, const gdx_queries
 extern "C" gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
                                       gdx_hit **hits, uint64_t *num_hits) {
     return guarded([&] { return locate_many_impl(idx, queries, hit_offsets, hits, num_hits); });
+}
+
+extern "C" gdx_status gdx_locate_many_compact(const gdx_index *idx, const gdx_queries *queries, uint32_t *hit_counts,
+                                              gdx_hit32 **hits, uint64_t *num_hits) {
+    return guarded([&]() -> gdx_status {
+        if (!hit_counts) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+        return locate_many_impl(idx, queries, nullptr, reinterpret_cast<gdx_hit **>(hits), num_hits, true, hit_counts);
+    });
 }
 
 extern "C" uint64_t gdx_packed_bytes(uint64_t total_symbols) { return align_up((total_symbols + 3) / 4, 4); }
@@ -2840,6 +2864,34 @@ extern "C" gdx_status gdx_cursors_many_sharded(gdx_index *const *replicas, uint3
             return search_many_impl(replicas[k], &sub, starts ? starts + b : nullptr, ends ? ends + b : nullptr, 8, 0,
                                     "gdx_cursors_many_sharded");
         });
+    });
+}
+
+extern "C" gdx_status gdx_locate_many_sharded_compact(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                                      uint32_t n_shards, const gdx_queries *queries, uint32_t *hit_counts,
+                                                      gdx_hit32 **shard_hits, uint64_t *shard_num_hits) {
+    return guarded([&]() -> gdx_status {
+        if (!hit_counts || !shard_hits || !shard_num_hits) return fail(GDX_ERR_BAD_ARG, "output is NULL");
+        for (uint32_t k = 0; k < n_local; ++k) {
+            shard_hits[k] = nullptr;
+            shard_num_hits[k] = 0;
+        }
+        gdx_status st = run_sharded(replicas, n_local, first_shard, n_shards, queries, [&](uint32_t k, uint64_t b, uint64_t e) {
+            const gdx_queries sub = sub_batch(*queries, b, e);
+            return locate_many_impl(replicas[k], &sub, nullptr, reinterpret_cast<gdx_hit **>(&shard_hits[k]), &shard_num_hits[k], true,
+                                    hit_counts + b);
+        });
+        uint64_t total = 0;
+        for (uint32_t k = 0; k < n_local; ++k) {
+            if (st != GDX_OK && shard_hits[k]) {
+                gdx_free_hits(replicas[k], reinterpret_cast<gdx_hit *>(shard_hits[k]));
+                shard_hits[k] = nullptr;
+                shard_num_hits[k] = 0;
+            }
+            total += shard_num_hits[k];
+        }
+        t_stats.hits = total;
+        return st;
     });
 }
 

@@ -940,11 +940,17 @@ __global__ void k_expand_big_rows(const uint64_t *__restrict__ starts, const uin
         rows[off + j] = s + j;
 }
 
+// a hit as gdx_hit (2 x u64) or, for texts shorter than 2^32, as gdx_hit32 (2 x u32: half the D2H bytes)
+__device__ __forceinline__ void store_hit(ulonglong2 *hits, uint64_t h, uint64_t text_id, uint64_t position, int compact) {
+    if (compact) reinterpret_cast<uint2 *>(hits)[h] = make_uint2((uint32_t)text_id, (uint32_t)position);
+    else hits[h] = make_ulonglong2(text_id, position);
+}
+
 // ---- K3 + K4: LF-walk to the next sample, then position -> (text id, position in text) ---------------
 template <class L>
 __global__ void __launch_bounds__(256)
 k_locate_walk(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ rows, uint64_t nh,
-              ulonglong2 *__restrict__ hits, unsigned long long *stat_steps) {
+              ulonglong2 *__restrict__ hits, unsigned long long *stat_steps, int compact) {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t steps = 0;
     if (h < nh) {
@@ -954,7 +960,7 @@ k_locate_walk(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ 
         uint64_t id = lower_bound_u64(ix.sentinels, ix.ntexts, pos);
         if (id >= ix.ntexts) id = ix.ntexts - 1;
         const uint64_t base = id == 0 ? 0 : __ldg(ix.sentinels + id - 1) + 1;
-        hits[h] = make_ulonglong2(id, pos - base);
+        store_hit(hits, h, id, pos - base, compact);
     }
     if (stat_steps) {
         uint32_t tot = __reduce_add_sync(0xffffffffu, steps);
@@ -971,7 +977,7 @@ constexpr uint32_t kWalkSlice = 2048;  // hits per CTA slice
 template <class L>
 __global__ void __launch_bounds__(256)
 k_locate_walk_compact(const __grid_constant__ DevIndex ix, const uint64_t *__restrict__ rows, uint64_t nh,
-                      ulonglong2 *__restrict__ hits, unsigned long long *stat_steps) {
+                      ulonglong2 *__restrict__ hits, unsigned long long *stat_steps, int compact) {
     __shared__ uint32_t next;  // next unclaimed hit of the slice
     const uint64_t slice0 = (uint64_t)blockIdx.x * kWalkSlice;
     const uint32_t slice_n = (uint32_t)(nh - slice0 < kWalkSlice ? nh - slice0 : kWalkSlice);
@@ -1037,7 +1043,7 @@ k_locate_walk_compact(const __grid_constant__ DevIndex ix, const uint64_t *__res
                 uint64_t id = lower_bound_u64(ix.sentinels, ix.ntexts, pos);  // text_id_search_tree.rs:35-64
                 if (id >= ix.ntexts) id = ix.ntexts - 1;
                 const uint64_t base = id == 0 ? 0 : __ldg(ix.sentinels + id - 1) + 1;
-                hits[h] = make_ulonglong2(id, pos - base);
+                store_hit(hits, h, id, pos - base, compact);
                 active = false;
             }
         }

@@ -304,6 +304,25 @@ class FmIndex:
             hits = np.zeros((0, 2), dtype=np.uint64)
         return hit_offsets, hits, (lambda: self._lib.gdx_free_hits(self._h, hp))
 
+    def locate_many_compact_view(self, data: np.ndarray, offsets: np.ndarray | None = None, fixed_len: int = 0,
+                                 nq: int | None = None, hit_counts: np.ndarray | None = None,
+                                 encoding: int = _lib.GDX_QUERIES_IO_BYTES):
+        """gdx_locate_many_compact (texts < 2^32 symbols): -> (hit_counts uint32[nq], hits view uint32[n, 2] on the
+        library's pinned buffer, release).  The CSR offsets are the prefix sums of hit_counts."""
+        nq = (offsets.size - 1) if offsets is not None else nq
+        if hit_counts is None:
+            hit_counts = np.zeros(max(nq, 1), dtype=np.uint32)
+        hp, nh = C.c_void_p(), C.c_uint64()
+        q = _queries_struct(data, offsets, fixed_len, nq, encoding)
+        _check(self._lib.gdx_locate_many_compact(self._h, C.byref(q), hit_counts.ctypes.data, C.byref(hp), C.byref(nh)))
+        n = nh.value
+        if n:
+            buf = (C.c_uint32 * (2 * n)).from_address(hp.value)
+            hits = np.frombuffer(buf, dtype=np.uint32).reshape(n, 2)
+        else:
+            hits = np.zeros((0, 2), dtype=np.uint32)
+        return hit_counts[:nq], hits, (lambda: self._lib.gdx_free_hits(self._h, hp))
+
     def _take_hits(self, hp: C.c_void_p, n: int) -> np.ndarray:
         try:
             if n == 0:

@@ -137,6 +137,35 @@ class ReplicaSet:
                     self._lib.gdx_free_hits(r.handle, C.c_void_p(ptr))
         return hit_offsets, views, np.array(list(first), dtype=np.uint64), release
 
+    def locate_many_compact_view(self, data, offsets=None, fixed_len: int = 0, nq: int | None = None, hit_counts=None,
+                                 encoding: int = _lib.GDX_QUERIES_IO_BYTES):
+        """gdx_locate_many_sharded_compact -> (hit_counts uint32[nq] (owned ranges filled), [uint32 hits view per local
+        shard], release)."""
+        nq = (offsets.size - 1) if offsets is not None else nq
+        if hit_counts is None:
+            hit_counts = np.zeros(max(nq, 1), dtype=np.uint32)
+        n_local = len(self.replicas)
+        hp = (C.c_void_p * n_local)()
+        nh = (C.c_uint64 * n_local)()
+        q = _queries_struct(data, offsets, fixed_len, nq, encoding)
+        _check(self._lib.gdx_locate_many_sharded_compact(self._handles, n_local, self.first_shard, self.n_shards, C.byref(q),
+                                                         hit_counts.ctypes.data, hp, nh))
+        views = []
+        for k in range(n_local):
+            n = int(nh[k])
+            if n:
+                buf = (C.c_uint32 * (2 * n)).from_address(hp[k])
+                views.append(np.frombuffer(buf, dtype=np.uint32).reshape(n, 2))
+            else:
+                views.append(np.zeros((0, 2), dtype=np.uint32))
+        ptrs = [hp[k] for k in range(n_local)]
+
+        def release():
+            for r, ptr in zip(self.replicas, ptrs):
+                if ptr:
+                    self._lib.gdx_free_hits(r.handle, C.c_void_p(ptr))
+        return hit_counts[:nq], views, release
+
     def locate_many_packed(self, data, offsets=None, fixed_len: int = 0, nq: int | None = None,
                            encoding: int = _lib.GDX_QUERIES_IO_BYTES):
         """Concatenating convenience form (copies): -> (hit_offsets of the owned range rebased to 0, hits[n, 2])."""

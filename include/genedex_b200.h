@@ -97,6 +97,11 @@ typedef struct gdx_hit {
     uint64_t text_id;
     uint64_t position;
 } gdx_hit;
+/* the same for texts shorter than 2^32 symbols: half the bytes per hit on the way back from the GPU */
+typedef struct gdx_hit32 {
+    uint32_t text_id;
+    uint32_t position;
+} gdx_hit32;
 
 /* How the symbols of a query batch are stored. */
 typedef enum gdx_query_encoding {
@@ -359,6 +364,13 @@ gdx_status gdx_pack_symbols(const gdx_alphabet *alphabet, const uint8_t *io_byte
  * of query i are hits[hit_offsets[i] .. hit_offsets[i+1]) in the reference's SA-row order. */
 gdx_status gdx_locate_many(const gdx_index *idx, const gdx_queries *queries, uint64_t *hit_offsets,
                            gdx_hit **hits, uint64_t *num_hits);
+/* FmIndex::locate_many in its compact result form (texts shorter than 2^32 symbols, else GDX_ERR_UNSUPPORTED):
+ * hit_counts[i] = number of hits of query i (nq entries; their prefix sums are the CSR offsets), hits as gdx_hit32 in
+ * the same order as gdx_locate_many.  8 B per hit + 4 B per query cross PCIe instead of 16 + 8: locate is bound by
+ * exactly those bytes end to end.  A host binding widens lazily while it iterates (the crate hands out
+ * `Hit { usize, usize }` one at a time anyway, lib.rs:179-197).  Release with gdx_free_hits(idx, (gdx_hit *)hits). */
+gdx_status gdx_locate_many_compact(const gdx_index *idx, const gdx_queries *queries, uint32_t *hit_counts,
+                                   gdx_hit32 **hits, uint64_t *num_hits);
 /* Cursor::locate / FmIndex::locate_interval (src/cursor.rs:71-73, src/lib.rs:187-197) for many
  * cursors at once. */
 gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t *starts, const uint64_t *ends,
@@ -387,6 +399,11 @@ gdx_status gdx_cursors_many_sharded(gdx_index *const *replicas, uint32_t n_local
 gdx_status gdx_locate_many_sharded(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
                                    uint32_t n_shards, const gdx_queries *queries, uint64_t *hit_offsets,
                                    gdx_hit **shard_hits, uint64_t *shard_first_hit);
+/* compact form: hit_counts (nq entries, the owned ranges are written), per local shard its gdx_hit32 array and its
+ * number of hits (n_local entries each); the hits of a shard's queries follow each other in query order */
+gdx_status gdx_locate_many_sharded_compact(gdx_index *const *replicas, uint32_t n_local, uint32_t first_shard,
+                                           uint32_t n_shards, const gdx_queries *queries, uint32_t *hit_counts,
+                                           gdx_hit32 **shard_hits, uint64_t *shard_num_hits);
 /* Cursor::extend_query_front (src/cursor.rs:34-51) for many cursors: in-place on starts/ends.  On an error
  * status the contents of pinned starts/ends are unspecified (the reference panics); pageable arrays are
  * left untouched. */

@@ -249,3 +249,33 @@ def test_a_result_that_cannot_fit_is_refused_and_leaves_the_index_usable(gdx, dn
     ooff, ohits = oidx.locate_many_packed(data2, off2)
     poff, phits = pidx.locate_many_packed(data2, off2)
     assert np.array_equal(ooff, poff) and np.array_equal(ohits, phits)
+
+
+def test_compact_locate_results(gdx, dna_case):
+    """gdx_locate_many_compact / _sharded_compact: u32 hits per query + gdx_hit32 hits = the same hits in the same order"""
+    from genedex_b200.replicate import ReplicaSet, shard_range
+    c = dna_case
+    oidx, pidx, data, off = c["oidx"], c["pidx"], c["data"], c["off"]
+    sub = 150_001
+    sdata, soff = data[: int(off[sub])], off[: sub + 1]
+    ooff, ohits = oidx.locate_many_packed(sdata, soff)
+    counts, hits, release = pidx.locate_many_compact_view(sdata, soff)
+    try:
+        assert counts.dtype == np.uint32 and hits.dtype == np.uint32
+        assert np.array_equal(counts.astype(np.uint64), ooff[1:] - ooff[:-1])
+        assert np.array_equal(hits.astype(np.uint64), ohits)
+    finally:
+        release()
+    rs = ReplicaSet.replicate(pidx, [0])
+    counts2, views, release2 = rs.locate_many_compact_view(sdata, soff)
+    try:
+        assert np.array_equal(counts2.astype(np.uint64), ooff[1:] - ooff[:-1])
+        assert np.array_equal(np.concatenate(views).astype(np.uint64), ohits)
+        b, e = shard_range(sub, 1, 2)
+        assert views[0].shape[0] == int(ooff[b]) and views[1].shape[0] == int(ooff[e] - ooff[b])
+    finally:
+        release2()
+    few, fhits, frel = pidx.locate_many_compact_view(*O.pack([b"ACGTAC", b"", b"TTTTTTTTTTTTTTTTTTTTTTTTT"][::2]))
+    o2, h2 = oidx.locate_many_packed(*O.pack([b"ACGTAC", b"TTTTTTTTTTTTTTTTTTTTTTTTT"]))
+    assert np.array_equal(few.astype(np.uint64), o2[1:] - o2[:-1]) and np.array_equal(fhits.astype(np.uint64), h2)
+    frel()
