@@ -34,4 +34,5 @@ def test_repeat_rich_text_at_two_percent():
     import run_configs
     res = list(run_configs.run(["c2r"], 0.02))
     assert len(res) == 1 and "parity" in res[0], res
-    assert res[0]["hits"] > 20 * res[0]["queries"] and res[0]["lf_steps"] > 3 * res[0]["queries"]
+    # (at 2 % scale a repeat family has 2 % of its copies: a few hits per query instead of the 226 of the full size)
+    assert res[0]["hits"] > 2 * res[0]["queries"] and res[0]["lf_steps"] > res[0]["queries"]
