@@ -270,8 +270,14 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
     const __m512i code_tab = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)t.code_lo));
     const __m512i nib = _mm512_set1_epi8(0x0f);
     const __m512i mul_1_4 = _mm512_set1_epi16(0x0401), mul_1_16 = _mm512_set1_epi32(0x00100001);
+    // A/B knobs (tools/host_pack_bench.py): software prefetch distance in bytes (0 = none) and non-temporal stores of
+    // the packed words (they are read next by the DMA engine, not by a CPU: no need to pull their lines into a cache)
+    static const uint64_t prefetch = getenv("GDX_PACK_PREFETCH") ? (uint64_t)atoi(getenv("GDX_PACK_PREFETCH")) : 0;
+    static const bool stream = getenv("GDX_PACK_STREAM") && atoi(getenv("GDX_PACK_STREAM")) != 0;
+    const bool nt = stream && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
     uint64_t i = 0;
     for (; i + 64 <= n; i += 64) {
+        if (prefetch) _mm_prefetch((const char *)(src + i + prefetch), _MM_HINT_T0);
         const __m512i x = _mm512_loadu_si512((const void *)(src + i));
         const __m512i lo = _mm512_and_si512(x, nib);
         const __m512i hi = _mm512_and_si512(_mm512_srli_epi16(x, 4), nib);
@@ -283,8 +289,10 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
             for (uint64_t mm = ~(uint64_t)valid; mm; mm &= mm - 1) exc.push_back(pos0 + i + (uint64_t)__builtin_ctzll(mm));
         }
         const __m512i p32 = _mm512_madd_epi16(_mm512_maddubs_epi16(code, mul_1_4), mul_1_16);
-        _mm_storeu_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
+        if (nt) _mm_stream_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
+        else _mm_storeu_si128((__m128i *)(dst + (i >> 2)), _mm512_cvtepi32_epi8(p32));
     }
+    if (nt) _mm_sfence();
     if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
 }
 

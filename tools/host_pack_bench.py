@@ -76,8 +76,27 @@ def latency(n=134_217_728, iters=300):
               f"p99 {ts[int(0.99 * len(ts))]:.2f}  max {ts[-1]:.2f} ms", flush=True)
 
 
+def knobs(n=1_500_000_000):
+    """A/B of the packer's prefetch / streaming-store knobs (read once per process: one subprocess per setting)"""
+    code = ("import sys, time, ctypes as C, numpy as np; sys.path.insert(0, %r); import genedex_b200 as gdx\n"
+            "from genedex_b200.index import _alphabet_struct\n"
+            "lib = gdx._lib.load(); a = _alphabet_struct(gdx.alphabet.ascii_dna_with_n()); n = %d\n"
+            "rng = np.random.default_rng(1); data = np.frombuffer(b'ACGT', dtype=np.uint8)[rng.integers(0, 4, n, dtype=np.uint8)].copy()\n"
+            "out = np.zeros(n // 4 + 64, dtype=np.uint8); ne = C.c_uint64(); best = 1e9\n"
+            "for _ in range(5):\n"
+            "    t = time.perf_counter(); lib.gdx_pack_symbols(C.byref(a), data.ctypes.data, n, out.ctypes.data, None, 0, C.byref(ne)); best = min(best, time.perf_counter() - t)\n"
+            "print('%%.1f GB/s' %% (n / best / 1e9))" % (ROOT, n))
+    for env in ({}, {"GDX_PACK_STREAM": "1"}, {"GDX_PACK_PREFETCH": "512"}, {"GDX_PACK_PREFETCH": "2048"},
+                {"GDX_PACK_PREFETCH": "2048", "GDX_PACK_STREAM": "1"}, {"GDX_PACK_ISA": "avx2"}, {"GDX_PACK_ISA": "vbmi"},
+                {"GDX_HOST_THREADS": "1"}, {"GDX_HOST_THREADS": "1", "GDX_PACK_PREFETCH": "2048", "GDX_PACK_STREAM": "1"}):
+        out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
+        print(env or "default", out.stdout.strip(), out.stderr.strip()[-200:], flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "latency":
+    if len(sys.argv) > 1 and sys.argv[1] == "knobs":
+        knobs()
+    elif len(sys.argv) > 1 and sys.argv[1] == "latency":
         latency()
     else:
         main()
