@@ -270,10 +270,13 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
     const __m512i code_tab = _mm512_broadcast_i32x4(_mm_loadu_si128((const __m128i *)t.code_lo));
     const __m512i nib = _mm512_set1_epi8(0x0f);
     const __m512i mul_1_4 = _mm512_set1_epi16(0x0401), mul_1_16 = _mm512_set1_epi32(0x00100001);
-    // A/B knobs (tools/host_pack_bench.py): software prefetch distance in bytes (0 = none) and non-temporal stores of
-    // the packed words (they are read next by the DMA engine, not by a CPU: no need to pull their lines into a cache)
-    static const uint64_t prefetch = getenv("GDX_PACK_PREFETCH") ? (uint64_t)atoi(getenv("GDX_PACK_PREFETCH")) : 0;
-    static const bool stream = getenv("GDX_PACK_STREAM") && atoi(getenv("GDX_PACK_STREAM")) != 0;
+    // A packer thread streams from DRAM, so it is bound by how many cache-line fills one core keeps in flight:
+    // a software prefetch 2 KB ahead and non-temporal stores of the packed words (they are read next by the DMA
+    // engine, not by a CPU: no need to pull their lines into a cache) lift one thread from 8.0 to 13.8 GB/s and 16
+    // threads from 91 to 125 GB/s on the bench host (profiles/r2_host_pack_knobs.txt).  GDX_PACK_PREFETCH=<bytes>
+    // (0 = none) and GDX_PACK_STREAM=0 are the A/B switches.
+    static const uint64_t prefetch = getenv("GDX_PACK_PREFETCH") ? (uint64_t)atoi(getenv("GDX_PACK_PREFETCH")) : 2048;
+    static const bool stream = !(getenv("GDX_PACK_STREAM") && atoi(getenv("GDX_PACK_STREAM")) == 0);
     const bool nt = stream && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
     uint64_t i = 0;
     for (; i + 64 <= n; i += 64) {

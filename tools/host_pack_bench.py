@@ -86,9 +86,10 @@ def knobs(n=1_500_000_000):
             "for _ in range(5):\n"
             "    t = time.perf_counter(); lib.gdx_pack_symbols(C.byref(a), data.ctypes.data, n, out.ctypes.data, None, 0, C.byref(ne)); best = min(best, time.perf_counter() - t)\n"
             "print('%%.1f GB/s' %% (n / best / 1e9))" % (ROOT, n))
-    for env in ({}, {"GDX_PACK_STREAM": "1"}, {"GDX_PACK_PREFETCH": "512"}, {"GDX_PACK_PREFETCH": "2048"},
-                {"GDX_PACK_PREFETCH": "2048", "GDX_PACK_STREAM": "1"}, {"GDX_PACK_ISA": "avx2"}, {"GDX_PACK_ISA": "vbmi"},
-                {"GDX_HOST_THREADS": "1"}, {"GDX_HOST_THREADS": "1", "GDX_PACK_PREFETCH": "2048", "GDX_PACK_STREAM": "1"}):
+    for env in ({}, {"GDX_PACK_STREAM": "0"}, {"GDX_PACK_PREFETCH": "0"}, {"GDX_PACK_PREFETCH": "0", "GDX_PACK_STREAM": "0"},
+                {"GDX_PACK_PREFETCH": "1024"}, {"GDX_PACK_PREFETCH": "4096"}, {"GDX_PACK_PREFETCH": "8192"},
+                {"GDX_PACK_ISA": "avx2"}, {"GDX_PACK_ISA": "vbmi"},
+                {"GDX_HOST_THREADS": "1"}, {"GDX_HOST_THREADS": "1", "GDX_PACK_PREFETCH": "0", "GDX_PACK_STREAM": "0"}):
         out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True)
         print(env or "default", out.stdout.strip(), out.stderr.strip()[-200:], flush=True)
 
