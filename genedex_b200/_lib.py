@@ -134,6 +134,7 @@ PROTOTYPES = {
     "gdx_count_many_device": (C.c_int, [_vp, _P(gdx_queries), _vp, _vp, _vp]),
     "gdx_locate_intervals_device": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
     "gdx_host_pool_resize": (_u32, [_u32]),
+    "gdx_host_pack_tuning": (None, [_i32, _i32]),
     "gdx_host_alloc": (C.c_int, [_u64, _P(_vp)]),
     "gdx_host_free": (None, [_vp]),
     "gdx_get_stats": (C.c_int, [_P(gdx_stats)]),

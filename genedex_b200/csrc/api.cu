@@ -895,6 +895,7 @@ extern "C" gdx_status gdx_get_stats(gdx_stats *out) {
     return GDX_OK;
 }
 extern "C" uint32_t gdx_host_pool_resize(uint32_t threads) { return HostPool::get().resize(threads); }
+extern "C" void gdx_host_pack_tuning(int32_t prefetch_bytes, int32_t streaming_stores) { set_pack_tuning(prefetch_bytes, streaming_stores); }
 extern "C" gdx_status gdx_host_alloc(uint64_t bytes, void **out) {
     if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
     CUDA_TRY(cudaMallocHost(out, bytes ? bytes : 1));

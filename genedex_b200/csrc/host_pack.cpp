@@ -262,6 +262,13 @@ __attribute__((target("avx2"))) static void pack2_avx2(const PackTable &t, const
     if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
 }
 
+static std::atomic<int> g_pack_prefetch{getenv("GDX_PACK_PREFETCH") ? atoi(getenv("GDX_PACK_PREFETCH")) : 2048};
+static std::atomic<int> g_pack_stream{getenv("GDX_PACK_STREAM") ? (atoi(getenv("GDX_PACK_STREAM")) != 0) : 1};
+void set_pack_tuning(int prefetch_bytes, int stream) {
+    g_pack_prefetch.store(prefetch_bytes < 0 ? 0 : prefetch_bytes);
+    g_pack_stream.store(stream != 0);
+}
+
 // the same 64 bytes at a time: in-lane nibble shuffles, a mask register for the validity, vpmovdb for the gather
 __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackTable &t, const uint8_t *src, uint64_t n,
                                                                      uint8_t *dst, uint64_t pos0, std::vector<uint64_t> &exc) {
@@ -275,8 +282,8 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
     // engine, not by a CPU: no need to pull their lines into a cache) lift one thread from 8.0 to 13.8 GB/s and 16
     // threads from 91 to 125 GB/s on the bench host (profiles/r2_host_pack_knobs.txt).  GDX_PACK_PREFETCH=<bytes>
     // (0 = none) and GDX_PACK_STREAM=0 are the A/B switches.
-    static const uint64_t prefetch = getenv("GDX_PACK_PREFETCH") ? (uint64_t)atoi(getenv("GDX_PACK_PREFETCH")) : 2048;
-    static const bool stream = !(getenv("GDX_PACK_STREAM") && atoi(getenv("GDX_PACK_STREAM")) == 0);
+    const uint64_t prefetch = (uint64_t)g_pack_prefetch.load(std::memory_order_relaxed);
+    const bool stream = g_pack_stream.load(std::memory_order_relaxed) != 0;
     const bool nt = stream && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
     uint64_t i = 0;
     for (; i + 64 <= n; i += 64) {

@@ -50,6 +50,8 @@ struct PackTable {
     bool simd_ok;
     bool usable;  // the alphabet has at most four searchable symbols
 };
+// run-time form of GDX_PACK_PREFETCH / GDX_PACK_STREAM (A/B measurements inside one process)
+void set_pack_tuning(int prefetch_bytes, int stream);
 void build_pack_table(const uint8_t io_to_dense[256], uint32_t num_searchable, PackTable &out);
 
 // Packs src[0, n) into dst (4 symbols per byte, symbol i at bits [2(i%4), 2(i%4)+2) of byte i/4, the last
