@@ -262,7 +262,7 @@ __attribute__((target("avx2"))) static void pack2_avx2(const PackTable &t, const
     if (i < n) pack2_scalar(t, src + i, n - i, dst + (i >> 2), pos0 + i, exc);
 }
 
-static std::atomic<int> g_pack_prefetch{getenv("GDX_PACK_PREFETCH") ? atoi(getenv("GDX_PACK_PREFETCH")) : 2048};
+static std::atomic<int> g_pack_prefetch{getenv("GDX_PACK_PREFETCH") ? atoi(getenv("GDX_PACK_PREFETCH")) : 4096};
 static std::atomic<int> g_pack_stream{getenv("GDX_PACK_STREAM") ? (atoi(getenv("GDX_PACK_STREAM")) != 0) : 1};
 void set_pack_tuning(int prefetch_bytes, int stream) {
     g_pack_prefetch.store(prefetch_bytes < 0 ? 0 : prefetch_bytes);
@@ -278,10 +278,11 @@ __attribute__((target("avx512f,avx512bw"))) static void pack2_avx512(const PackT
     const __m512i nib = _mm512_set1_epi8(0x0f);
     const __m512i mul_1_4 = _mm512_set1_epi16(0x0401), mul_1_16 = _mm512_set1_epi32(0x00100001);
     // A packer thread streams from DRAM, so it is bound by how many cache-line fills one core keeps in flight:
-    // a software prefetch 2 KB ahead and non-temporal stores of the packed words (they are read next by the DMA
-    // engine, not by a CPU: no need to pull their lines into a cache) lift one thread from 8.0 to 13.8 GB/s and 16
-    // threads from 91 to 125 GB/s on the bench host (profiles/r2_host_pack_knobs.txt).  GDX_PACK_PREFETCH=<bytes>
-    // (0 = none) and GDX_PACK_STREAM=0 are the A/B switches.
+    // a software prefetch 4 KB ahead and non-temporal stores of the packed words (they are read next by the DMA
+    // engine, not by a CPU: no need to pull their lines into a cache) lift the pool from 85 to 108 GB/s and a 30 M-query
+    // gdx_count_many from 19.7 to 16.4 ms on a bench host (alternating runs inside one process,
+    // profiles/r2_pack_tuning_ab.txt).  GDX_PACK_PREFETCH=<bytes> (0 = none), GDX_PACK_STREAM=0 and
+    // gdx_host_pack_tuning() are the A/B switches.
     const uint64_t prefetch = (uint64_t)g_pack_prefetch.load(std::memory_order_relaxed);
     const bool stream = g_pack_stream.load(std::memory_order_relaxed) != 0;
     const bool nt = stream && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;

@@ -435,7 +435,7 @@ gdx_status gdx_locate_intervals_device(const gdx_index *idx, const uint64_t *d_s
  * re-creates it with `threads` threads (0 = the default rule, evaluated for the calling thread now); the new
  * workers inherit the caller's CPU affinity.  Must not run concurrently with searches.  Returns the new size. */
 uint32_t gdx_host_pool_resize(uint32_t threads);
-/* Tuning of the host packer (defaults: software prefetch 2048 bytes ahead, non-temporal stores of the packed words;
+/* Tuning of the host packer (defaults: software prefetch 4096 bytes ahead, non-temporal stores of the packed words;
  * GDX_PACK_PREFETCH / GDX_PACK_STREAM set the same at start-up): for A/B measurements on a given host. */
 void gdx_host_pack_tuning(int32_t prefetch_bytes, int32_t streaming_stores);
 
