@@ -253,6 +253,52 @@ std::vector<Cursor> FmIndex::cursors_for_many_queries(const Range &queries) cons
     return out;
 }
 
+// ---- one batch over several GPUs (no counterpart in the crate) ---------------------------------
+// Full replicas of an index on other devices (one ncclBroadcast of the device image) and the *_many calls over
+// all of them: the batch is cut into contiguous ranges by the library, results come back in input order.
+class ReplicaSet {
+public:
+    ReplicaSet(const FmIndex &index, const std::vector<int32_t> &other_devices) {
+        std::vector<gdx_index *> out(other_devices.size(), nullptr);
+        check(gdx_index_replicate(index.handle(), other_devices.data(), (int32_t)other_devices.size(), out.data()));
+        replicas_.push_back(index);
+        for (gdx_index *h : out) replicas_.emplace_back(h, index.alphabet());
+        for (const FmIndex &r : replicas_) handles_.push_back(const_cast<gdx_index *>(r.handle()));
+    }
+    size_t size() const { return replicas_.size(); }
+    template <class Range>
+    std::vector<size_t> count_many(const Range &queries) const {                          // lib.rs:155-161
+        detail::Packed p(queries);
+        std::vector<uint64_t> c(p.offsets.size());
+        gdx_queries q = p.view();
+        check(gdx_count_many_sharded(handles_.data(), (uint32_t)handles_.size(), 0, (uint32_t)handles_.size(), &q, c.data()));
+        return std::vector<size_t>(c.begin(), c.end() - 1);
+    }
+    template <class Range>
+    std::vector<std::vector<Hit>> locate_many(const Range &queries) const {               // lib.rs:179-185
+        detail::Packed p(queries);
+        const size_t nq = p.offsets.size() - 1, ns = handles_.size();
+        std::vector<uint64_t> off(nq + 1), first(ns + 1);
+        std::vector<gdx_hit *> hits(ns, nullptr);
+        gdx_queries q = p.view();
+        check(gdx_locate_many_sharded(handles_.data(), (uint32_t)ns, 0, (uint32_t)ns, &q, off.data(), hits.data(), first.data()));
+        std::vector<std::vector<Hit>> out(nq);
+        for (size_t k = 0; k < ns; ++k) {
+            uint64_t b = 0, e = 0;
+            gdx_shard_range(nq, (uint32_t)k, (uint32_t)ns, &b, &e);
+            for (uint64_t i = b; i < e; ++i)
+                for (uint64_t j = off[i]; j < off[i + 1]; ++j)
+                    out[i].push_back(Hit{hits[k][j - first[k]].text_id, hits[k][j - first[k]].position});
+            gdx_free_hits(handles_[k], hits[k]);
+        }
+        return out;
+    }
+
+private:
+    std::vector<FmIndex> replicas_;
+    std::vector<gdx_index *> handles_;
+};
+
 // ---- src/config.rs:9-82 ---------------------------------------------------------------------------------
 template <class I = I32>
 class FmIndexConfig {

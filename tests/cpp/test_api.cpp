@@ -85,6 +85,17 @@ int main() {
         }
         REQUIRE(thrown);
     }
+    {  // one batch over two replicas (both on the current device here; other devices work the same way)
+        std::vector<std::string> texts{"cccaaagggttt", "acgtacgtacgt"};
+        FmIndex index = FmIndexConfig<U32>().suffix_array_sampling_rate(3).construct_index(texts, alphabet::ascii_dna());
+        ReplicaSet replicas(index, {index.info().device});
+        REQUIRE(replicas.size() == 2);
+        std::vector<std::string> qs{"gg", "gt", "tc", "acgt", "cc"};
+        REQUIRE((replicas.count_many(qs) == index.count_many(qs)));
+        auto a = replicas.locate_many(qs), b = index.locate_many(qs);
+        REQUIRE(a.size() == b.size());
+        for (size_t i = 0; i < a.size(); ++i) REQUIRE(set_of(a[i]) == set_of(b[i]) && a[i].size() == b[i].size());
+    }
     std::printf("cpp api ok\n");
     return 0;
 }

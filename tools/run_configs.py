@@ -178,7 +178,7 @@ def time_device_cursors(gdx, pidx, q_dev, m, nq, reps=5):
 
 
 def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev, m, nq, depth, s,
-             origin=None, oracle_sample=200_000, locate=True, verify_text=None):
+             origin=None, oracle_sample=200_000, locate=True, verify_text=None, dense_suffix_array=True):
     """texts_io: host uint8 array of all texts back to back; origin = (text ids, positions) of the first
     len(origin[0]) queries (those were sampled from the texts)."""
     torch = _torch()
@@ -187,6 +187,8 @@ def run_case(name, gdx, texts_io, text_offsets, alphabet, oracle_alphabet, q_dev
            .construct_on_device(True, verify=True))
     pidx = cfg.construct_index_packed(texts_io, np.asarray(text_offsets, dtype=np.uint64), alphabet)
     build_s = time.perf_counter() - t0
+    if not dense_suffix_array:  # locate by LF-walk to a sample, like the reference (sampled_suffix_array.rs:110-138)
+        pidx.set_dense_suffix_array(False)
     info = pidx.info()
     q_host = torch.empty(nq * m, dtype=torch.uint8).pin_memory()
     q_host.copy_(q_dev)
@@ -357,14 +359,14 @@ def run(configs, scale=1.0):
         yield res
         del q, host
         torch.cuda.empty_cache()
-    dna = [c for c in configs if (c.startswith("c2") and c != "c2r") or c == "c3"]
+    dna = [c for c in configs if (c.startswith("c2") and c != "c2r") or c in ("c3", "c3s")]
     if dna:
         n = int(3_100_000_000 * scale)
         nq, m = int(7_500_000 * scale), 50
         text = bench.make_text_on_device(n, 0.05, dev)
         host = text.cpu().numpy()
         for c in dna:
-            if c == "c3":
+            if c in ("c3", "c3s"):  # c3s: the same with the configured sampled suffix array only (no dense accelerator)
                 lens = np.array(HG38, dtype=np.float64) * scale
                 offs = np.concatenate([[0], np.cumsum(lens.astype(np.int64))])
                 offs = np.minimum(offs, n)
@@ -380,7 +382,7 @@ def run(configs, scale=1.0):
             origin = (tid.cpu().numpy(), pos.cpu().numpy())
             out.append(run_case(c, gdx, host[:tn], offs, gdx.alphabet.ascii_dna_with_n(),
                                 O.ALPHABETS["ascii_dna_with_n"](), q, m, nq, depth, 4, origin=origin,
-                                locate=True, verify_text=dna_fold))
+                                locate=True, verify_text=dna_fold, dense_suffix_array=(c != "c3s")))
             yield out[-1]
             del q
             torch.cuda.empty_cache()
