@@ -418,7 +418,7 @@ def test_reentrant_from_many_host_threads(gdx):
 
     def work(i):
         try:
-            for _ in range(5):
+            for _ in range(2):
                 assert pidx.count_many(batches[i]) == want[i][0]
                 got = [[(h.text_id, h.position) for h in hs] for hs in pidx.locate_many(batches[i])]
                 assert got == want[i][1]
