@@ -2164,6 +2164,11 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         if (pack_chunk || !(hybrid && pack_on)) budget = std::min<uint64_t>(budget * 2, kChunkMax);
         const uint64_t cq = q1 - q0;
         const uint64_t sym0 = query_bytes_end(qs, q0), sym1 = query_bytes_end(qs, q1), nsym = sym1 - sym0;
+        if (sym1 < sym0 || sym1 > sym_end) {  // (inside a chunk the kernel checks every query against the chunk's extent)
+            t_error_query = q0;
+            return fail(GDX_ERR_BAD_ARG, "queries->offsets must not decrease and must stay inside the batch (near query %llu)",
+                        (unsigned long long)q0);
+        }
         Slot &sl = ws->slot[k % kSlots];
         const SortPlan sp = plan_sort(idx, cq, qs->offsets ? 0 : qs->fixed_len);
         // growing a slot buffer frees the old one: only safe once the slot's stream has drained
@@ -2192,6 +2197,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
         dq.nq = cq;
         dq.base = 0;
         dq.shift = 0;
+        dq.limit = nsym;  // (+ shift once a packed chunk decides it)
         // large variable-length batches: offsets cross PCIe chunk relative as uint32
         const bool narrow_off = qs->offsets && nq * 8 >= kStageMinBytes && nsym + 4 < 0xffffffffull && narrow_enabled();
         bool used_staging = false;
@@ -2206,6 +2212,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
                 if (qs->offsets) {
                     const uint64_t *ob = qs->offsets + q0, *oe = qs->offsets + q1 + 1;
                     q = (uint64_t)(std::upper_bound(ob, oe, sym0 + pos) - ob) - 1;
+                    q = std::min(q, cq - 1);  // (offsets that are not sorted are reported by the kernel; stay in the chunk)
                 } else {
                     q = pos / qs->fixed_len;
                 }
@@ -2239,6 +2246,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
                 dq.bytes = nullptr;
                 dq.packed = sl.bytes.as<uint32_t>();
                 dq.shift = sym0 & 3;
+                dq.limit = nsym + dq.shift;
             } else {
                 const uint8_t *src = qs->bytes + sym0;
                 if (stage_in) {
@@ -2319,6 +2327,7 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
             xq.bytes = sl.xbuf.as<uint8_t>() + off_bytes;
             xq.offsets = sl.xbuf.as<uint64_t>();
             xq.nq = nx;
+            xq.limit = xbytes;
             x_slots = reinterpret_cast<const uint32_t *>(sl.xbuf.as<uint8_t>() + off_slots);
             used_staging = true;
         }
@@ -2462,6 +2471,11 @@ gdx_status search_host(const gdx_index *idx, Workspace *ws, const gdx_queries *q
     t_stats.d2h_bytes += d2h_bytes;
     uint64_t bad = kNoError;
     for (int s = 0; s < kSlots; ++s) bad = std::min(bad, ws->small.h[s]);
+    if (bad != kNoError && (bad & kBadOffsetFlag)) {
+        t_error_query = bad & ~kBadOffsetFlag;
+        return fail(GDX_ERR_BAD_ARG, "query %llu: queries->offsets must not decrease and must stay inside the batch",
+                    (unsigned long long)t_error_query);
+    }
     if (bad != kNoError) {
         t_error_query = bad;
         return fail(GDX_ERR_INVALID_SYMBOL,
@@ -3094,6 +3108,7 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
     dq.nq = dq_in->nq;
     dq.base = 0;
     dq.shift = dq_in->first_symbol;
+    dq.limit = ~0ull;  // device-resident batch: its extent is the caller's contract (header)
     cudaStream_t st = (cudaStream_t)stream;
     const SortPlan sp = plan_sort(idx, dq.nq, dq.offsets ? 0 : dq.fixed_len);
     const uint32_t *perm = nullptr;

@@ -65,6 +65,9 @@ struct DevQueries {
     // Every symbol of a packed batch is searchable by construction (the host packer routes queries with
     // any other byte to the IO-byte kernel), so the packed kernel has no invalid-symbol path.
     const uint32_t *packed;
+    // number of symbols the stream holds (host pipeline: the chunk that was uploaded; ~0 = unknown): a query whose
+    // offsets point outside is reported instead of read -- offsets are caller data and not checked on the host
+    uint64_t limit;
 };
 
 // symbols [begin, begin + len) of the batch's stream belong to query q
@@ -635,6 +638,10 @@ constexpr uint32_t kQuerySlotWords = kQueryStage / 4 + 1;  // 17: odd stride, co
 // kernel because they hold a byte the packer cannot encode); errors are reported for that slot.
 // out_bits: 64 or 32 (narrow results for texts shorter than 2^32: half the D2H bytes).
 constexpr int kModeNarrow = 8;  // mode flag: results are written as uint32
+// error word of k_search: smallest failing query index (atomicMin); a query whose offsets leave the uploaded stream
+// carries this flag (so an invalid symbol in an earlier or later query still wins the report, as it would in the
+// reference, which cannot express broken offsets at all)
+constexpr uint64_t kBadOffsetFlag = 1ull << 62;
 
 template <class L, bool VERIFY, bool CURSORS, bool PACKED>
 __global__ void __launch_bounds__(256, VERIFY ? L::kVerifyMinBlocks : L::kSearchMinBlocks)
@@ -659,6 +666,10 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         const uint64_t q = perm ? (uint64_t)__ldg(perm + t) : t;
         uint64_t begin, len;
         query_extent(qs, q, begin, len);
+        if ((qs.offsets32 || qs.offsets) && (begin > qs.limit || len > qs.limit - begin)) {  // decreasing / out-of-range offsets
+            report_error(err, kBadOffsetFlag | (q_index_base + (slot_map ? (uint64_t)__ldg(slot_map + q) : q)));
+            len = 0;  // (nothing of an empty query is read)
+        }
         const uint8_t *p = PACKED ? nullptr : qs.bytes + begin;
 
         // the last kQueryStage symbols of the query

@@ -118,6 +118,11 @@ typedef enum gdx_query_encoding {
 /* A batch of queries: query i = symbols [offsets[i], offsets[i+1]) of the batch's symbol stream.
  * offsets == NULL means every query has length fixed_len and query i starts at symbol i * fixed_len
  * (+ first_symbol).  With GDX_QUERIES_IO_BYTES symbol k is bytes[k].
+ * offsets must not decrease and the symbols [offsets[0], offsets[nq]) must exist; the host entry points do not
+ * scan the array (60 M entries would cost more than the search) -- chunk boundaries are checked on the host and
+ * every query against its uploaded chunk on the device, so a broken array fails with GDX_ERR_BAD_ARG
+ * (gdx_last_error_query names the query) and nothing outside the batch is read.  Device-resident batches
+ * (gdx_count_many_device ...) are the caller's contract.
  * Replaces `impl IntoIterator<Item = Q: AsRef<[u8]>>` of src/lib.rs:155-158,179-182,241-244. */
 typedef struct gdx_queries {
     const uint8_t *bytes;

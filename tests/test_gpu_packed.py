@@ -279,3 +279,31 @@ def test_compact_locate_results(gdx, dna_case):
     o2, h2 = oidx.locate_many_packed(*O.pack([b"ACGTAC", b"TTTTTTTTTTTTTTTTTTTTTTTTT"]))
     assert np.array_equal(few.astype(np.uint64), o2[1:] - o2[:-1]) and np.array_equal(fhits.astype(np.uint64), h2)
     frel()
+
+
+def test_offsets_that_leave_the_batch_are_refused(gdx, dna_case):
+    """A C caller can hand over offsets a Rust slice-of-slices cannot express (decreasing, or past the bytes).  Nothing is
+    read outside the batch: the kernel checks every query against the extent of the uploaded chunk, the host the chunk
+    boundaries; the call fails with GDX_ERR_BAD_ARG naming the query, and the index stays usable."""
+    c = dna_case
+    pidx, oidx, data, off = c["pidx"], c["oidx"], c["data"], c["off"]
+    lib = gdx._lib.load()
+    small, small_off = O.pack([b"ACGTACGT", b"ACG", b"TTGACA", b"GATTACA"])
+    for bad_at, value in ((2, 3), (2, 10**12)):          # decreasing / far outside (the total stays plausible)
+        broken = small_off.copy()
+        broken[bad_at] = value
+        with pytest.raises(gdx.GenedexError) as e:
+            pidx.count_many_packed(small, broken)
+        assert e.value.status == gdx._lib.GDX_ERR_BAD_ARG and not isinstance(e.value, gdx.InvalidSymbolError)
+        assert int(lib.gdx_last_error_query()) in (bad_at - 1, bad_at)
+    # the large-batch forms: packed chunks with 32-bit chunk-relative offsets, and the same with packing off
+    for where in (7, 123_457, off.size - 3):
+        broken = off.copy()
+        broken[where] = broken[where + 1] + 5            # query `where` gets a negative length ...
+        with pytest.raises(gdx.GenedexError) as e:
+            pidx.count_many_packed(data, broken)
+        assert e.value.status == gdx._lib.GDX_ERR_BAD_ARG
+        assert int(lib.gdx_last_error_query()) in (where - 1, where)
+        with pytest.raises(gdx.GenedexError):
+            pidx.locate_many_packed(data, broken)
+    assert np.array_equal(pidx.count_many_packed(data, off), oidx.count_many_packed(data, off))

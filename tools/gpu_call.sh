@@ -1,6 +1,7 @@
 #!/bin/bash
-# sanitizer passes with every batch forced through the host packer / packed kernel / exception path
+# offsets guard: the new test first (short timeout), then the whole GPU suite, then the headline bench
 mkdir -p gpurun_out
-GDX_PACK_MIN_BYTES=0 GDX_STAGE_MIN_BYTES=0 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "kat or edge or invalid or unsearchable or verification_shortcut" > gpurun_out/r2_sanitizer_memcheck_packed_tests.log 2>&1; echo "memcheck packed rc=$?"; tail -4 gpurun_out/r2_sanitizer_memcheck_packed_tests.log
-GDX_PACK_MIN_BYTES=0 GDX_STAGE_MIN_BYTES=0 timeout 900 compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "kat or edge or invalid" > gpurun_out/r2_sanitizer_racecheck_packed_tests.log 2>&1; echo "racecheck packed rc=$?"; tail -4 gpurun_out/r2_sanitizer_racecheck_packed_tests.log
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "rank_variants or reference_parts or many_hits" > gpurun_out/r2_sanitizer_memcheck_ingest.log 2>&1; echo "memcheck ingest rc=$?"; tail -4 gpurun_out/r2_sanitizer_memcheck_ingest.log
+timeout 300 python -m pytest tests/test_gpu_packed.py -m gpu -q -x > gpurun_out/t_packed.log 2>&1; rc=$?; echo "packed rc=$rc"; tail -5 gpurun_out/t_packed.log
+if [ $rc -ne 0 ]; then exit 1; fi
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/t_all.log 2>&1; echo "all rc=$?"; tail -3 gpurun_out/t_all.log
+timeout 600 python bench.py > gpurun_out/bench_n1_guard.json 2> gpurun_out/bench_n1_guard.err; echo "bench rc=$?"; cat gpurun_out/bench_n1_guard.json | cut -c1-1500
