@@ -894,7 +894,13 @@ extern "C" gdx_status gdx_get_stats(gdx_stats *out) {
     *out = t_stats;
     return GDX_OK;
 }
-extern "C" uint32_t gdx_host_pool_resize(uint32_t threads) { return HostPool::get().resize(threads); }
+extern "C" uint32_t gdx_host_pool_resize(uint32_t threads) {
+    try {
+        return HostPool::get().resize(threads);
+    } catch (...) {  // (a thread could not be started: the pool keeps the workers it has)
+        return HostPool::get().threads();
+    }
+}
 extern "C" void gdx_host_pack_tuning(int32_t prefetch_bytes, int32_t streaming_stores) { set_pack_tuning(prefetch_bytes, streaming_stores); }
 extern "C" gdx_status gdx_host_alloc(uint64_t bytes, void **out) {
     if (!out) return fail(GDX_ERR_BAD_ARG, "out is NULL");
@@ -1432,33 +1438,39 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
 }
 
 extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth) {
-    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
-    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the seed table cannot change now");
-    DeviceGuard guard(idx->device);
-    if (depth <= 0) {
-        drop_seed_table(idx);
-        return GDX_OK;
-    }
-    return build_seed_table(idx, (uint32_t)depth);
+    return guarded([&]() -> gdx_status {
+        if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+        if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the seed table cannot change now");
+        DeviceGuard guard(idx->device);
+        if (depth <= 0) {
+            drop_seed_table(idx);
+            return GDX_OK;
+        }
+        return build_seed_table(idx, (uint32_t)depth);
+    });
 }
 
 extern "C" gdx_status gdx_index_set_text_verification(gdx_index *idx, int32_t on) {
-    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
-    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index");
-    idx->verify = on != 0;
-    return GDX_OK;
+    return guarded([&]() -> gdx_status {
+        if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+        if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index");
+        idx->verify = on != 0;
+        return GDX_OK;
+    });
 }
 
 extern "C" gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on) {
-    if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
-    std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
-    if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the dense suffix array cannot change now");
-    DeviceGuard guard(idx->device);
-    if (on) return build_dense_sa(idx);
-    drop_dense_sa(idx);
-    return GDX_OK;
+    return guarded([&]() -> gdx_status {
+        if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+        if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the dense suffix array cannot change now");
+        DeviceGuard guard(idx->device);
+        if (on) return build_dense_sa(idx);
+        drop_dense_sa(idx);
+        return GDX_OK;
+    });
 }
 
 // ---- NCCL, loaded at run time ---------------------------------------------------------------------------
@@ -2590,10 +2602,18 @@ gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64
     cudaStream_t st = ws->slot[0].stream;
     void *h = nullptr;
     GDX_TRY(acquire_pinned_hits(idx, total * sizeof(gdx_hit), &h));
-    if (total) CUDA_TRY(cudaMemcpyAsync(h, ws->hits.p, total * sizeof(gdx_hit), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(hit_offsets, ws->hit_offsets.p, (n + (write_last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    const gdx_status copied = [&]() -> gdx_status {
+        if (total) CUDA_TRY(cudaMemcpyAsync(h, ws->hits.p, total * sizeof(gdx_hit), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(hit_offsets, ws->hit_offsets.p, (n + (write_last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->small.h, ws->small.d, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return GDX_OK;
+    }();
+    if (copied != GDX_OK) {
+        cudaStreamSynchronize(st);
+        release_pinned_hits(idx, h);
+        return copied;
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, ws->ev_a, ws->ev_b);
     t_stats.kernel_ms_locate = ms;
@@ -2609,6 +2629,13 @@ gdx_status finish_locate(const gdx_index *idx, Workspace *ws, uint64_t n, uint64
 
 namespace {
 
+// a failed call must not return while one of its streams still reads or writes the caller's buffers; the error that
+// made it fail stays the reported one
+void drain(Workspace *ws) {
+    for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(ws->slot[s].stream);
+    cudaGetLastError();
+}
+
 // mode 0: cursors, 1: counts; elem: bytes per element of the caller's arrays
 gdx_status search_many_impl(const gdx_index *idx, const gdx_queries *queries, void *a, void *b, uint32_t elem, int mode,
                             const char *what) {
@@ -2620,7 +2647,9 @@ gdx_status search_many_impl(const gdx_index *idx, const gdx_queries *queries, vo
     DeviceGuard guard(idx->device);
     WsLease lease(idx);
     if (!lease.w) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
-    return search_host(idx, lease.w, queries, a, b, elem, mode, nullptr, nullptr);
+    const gdx_status st = search_host(idx, lease.w, queries, a, b, elem, mode, nullptr, nullptr);
+    if (st != GDX_OK) drain(lease.w);  // copies into the caller's arrays may still be in flight
+    return st;
 }
 
 // write_last = false: hit_offsets[nq] is left alone (it is the first entry of the next shard's range)
@@ -2651,7 +2680,7 @@ gdx_status locate_many_impl(const gdx_index *idx, const gdx_queries *queries, ui
         GDX_TRY(acquire_pinned_hits(idx, std::max<uint64_t>(n, 4096) * lp.hit_bytes, &lp.pinned, &lp.pinned_cap));
         gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 8, 2, nullptr, nullptr, &lp);
         if (st != GDX_OK) {
-            for (int s2 = 0; s2 < kSlots; ++s2) cudaStreamSynchronize(ws->slot[s2].stream);
+            drain(ws);
             release_pinned_hits(idx, lp.pinned);
             return st;
         }
@@ -2664,10 +2693,12 @@ gdx_status locate_many_impl(const gdx_index *idx, const gdx_queries *queries, ui
     // a buffer may only be replaced once nothing in flight uses it: every call ends synchronized
     CUDA_TRY(ws->starts.reserve((n + 1) * 8));
     CUDA_TRY(ws->ends.reserve((n + 1) * 8));
-    GDX_TRY(search_host(idx, ws, queries, nullptr, nullptr, 8, 2, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>()));
+    gdx_status st = search_host(idx, ws, queries, nullptr, nullptr, 8, 2, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>());
     uint64_t total = 0;
-    GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
-    return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits, write_last);
+    if (st == GDX_OK) st = locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total);
+    if (st == GDX_OK) st = finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits, write_last);
+    if (st != GDX_OK) drain(ws);
+    return st;
 }
 
 }  // namespace
@@ -2964,6 +2995,7 @@ extern "C" gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t 
         for (uint64_t i = 0; i < n; ++i)
             if (starts[i] > ends[i] || ends[i] > idx->h.n)
                 return fail(GDX_ERR_BAD_ARG, "interval %llu is not inside [0, text_len]", (unsigned long long)i);
+        std::shared_lock<std::shared_mutex> cfg(idx->cfg_mu);
         DeviceGuard guard(idx->device);
         WsLease lease(idx);
         Workspace *ws = lease.w;
@@ -2976,8 +3008,10 @@ extern "C" gdx_status gdx_locate_intervals(const gdx_index *idx, const uint64_t 
             CUDA_TRY(cudaMemcpyAsync(ws->ends.p, ends, n * 8, cudaMemcpyHostToDevice, st));
         }
         uint64_t total = 0;
-        GDX_TRY(locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total));
-        return finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+        gdx_status rc = locate_device_intervals(idx, ws, ws->starts.as<uint64_t>(), ws->ends.as<uint64_t>(), n, &total);
+        if (rc == GDX_OK) rc = finish_locate(idx, ws, n, total, hit_offsets, hits, num_hits);
+        if (rc != GDX_OK) drain(ws);
+        return rc;
     });
 }
 
@@ -2988,16 +3022,29 @@ extern "C" void gdx_free_hits(const gdx_index *idx, gdx_hit *hits) {
         if (p.p == hits) p.in_use = false;
 }
 
+static gdx_status extend_many_on(const gdx_index *idx, Workspace *ws, uint64_t *starts, uint64_t *ends,
+                                 const uint8_t *io_symbols, uint64_t n);
+
 extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, uint64_t *ends,
                                       const uint8_t *io_symbols, uint64_t n) {
     return guarded([&]() -> gdx_status {
         GDX_TRY(begin_call(idx, "gdx_extend_many"));
         if (n == 0) return GDX_OK;
         if (!starts || !ends || !io_symbols) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        std::shared_lock<std::shared_mutex> cfg(idx->cfg_mu);
         DeviceGuard guard(idx->device);
         WsLease lease(idx);
         Workspace *ws = lease.w;
         if (!ws) return fail(GDX_ERR_CUDA, "could not create a CUDA workspace: %s", cudaGetErrorString(cudaGetLastError()));
+        const gdx_status rc = extend_many_on(idx, ws, starts, ends, io_symbols, n);
+        if (rc != GDX_OK) drain(ws);
+        return rc;
+    });
+}
+
+static gdx_status extend_many_on(const gdx_index *idx, Workspace *ws, uint64_t *starts, uint64_t *ends,
+                                 const uint8_t *io_symbols, uint64_t n) {
+    {
         cudaStream_t st = ws->slot[0].stream;
         CUDA_TRY(ws->starts.reserve(n * 8));
         CUDA_TRY(ws->ends.reserve(n * 8));
@@ -3057,7 +3104,7 @@ extern "C" gdx_status gdx_extend_many(const gdx_index *idx, uint64_t *starts, ui
             HostPool::get().copy(ends, sl0.h_out_b.p, n * 8);
         }
         return GDX_OK;
-    });
+    }
 }
 
 extern "C" gdx_status gdx_cursor_for_query(const gdx_index *idx, const uint8_t *query, uint64_t len, uint64_t *start,
@@ -3128,11 +3175,11 @@ static gdx_status search_device(const gdx_index *idx, const gdx_queries *dq_in, 
 
 extern "C" gdx_status gdx_cursors_many_device(const gdx_index *idx, const gdx_queries *d_queries, uint64_t *d_starts,
                                               uint64_t *d_ends, uint64_t *d_error, void *stream) {
-    return search_device(idx, d_queries, d_starts, d_ends, 0, d_error, stream);
+    return guarded([&] { return search_device(idx, d_queries, d_starts, d_ends, 0, d_error, stream); });
 }
 extern "C" gdx_status gdx_count_many_device(const gdx_index *idx, const gdx_queries *d_queries, uint64_t *d_counts,
                                             uint64_t *d_error, void *stream) {
-    return search_device(idx, d_queries, d_counts, nullptr, 1, d_error, stream);
+    return guarded([&] { return search_device(idx, d_queries, d_counts, nullptr, 1, d_error, stream); });
 }
 
 extern "C" gdx_status gdx_locate_intervals_device(const gdx_index *idx, const uint64_t *d_starts,

@@ -10,8 +10,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <exception>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <thread>
 
 namespace gdx {
@@ -23,6 +25,8 @@ struct Job {
     uint64_t pieces;
     std::atomic<uint64_t> next{0};
     std::atomic<uint64_t> done{0};
+    std::atomic<bool> failed{false};
+    std::exception_ptr error;  // the first exception a piece threw (rethrown on the thread that posted the job)
 };
 }  // namespace
 
@@ -32,13 +36,18 @@ struct HostPool::Impl {
     std::condition_variable cv, done_cv;
     std::deque<std::shared_ptr<Job>> queue;  // jobs that may still have unclaimed pieces
     bool stop = false;
+    std::shared_mutex life;  // shared: a job is posted and waited for; exclusive: the workers are being replaced
 
     // claims and runs pieces of `job` until none is left
     void work(const std::shared_ptr<Job> &job) {
         for (;;) {
             const uint64_t k = job->next.fetch_add(1, std::memory_order_relaxed);
             if (k >= job->pieces) break;
-            (*job->fn)(k);
+            try {
+                (*job->fn)(k);
+            } catch (...) {
+                if (!job->failed.exchange(true)) job->error = std::current_exception();
+            }
             if (job->done.fetch_add(1, std::memory_order_acq_rel) + 1 == job->pieces) {
                 std::lock_guard<std::mutex> lk(mu);
                 done_cv.notify_all();
@@ -77,8 +86,9 @@ static unsigned usable_cpus() {
 HostPool::HostPool() : impl_(new Impl()) { resize(0); }
 
 // total = threads that work on one staging job incl. the caller; 0 = GDX_HOST_THREADS, else the CPUs the
-// calling thread may run on (new workers inherit its affinity), at most 32.  Not while jobs are running.
+// calling thread may run on (new workers inherit its affinity), at most 32.  Waits for running jobs.
 unsigned HostPool::resize(unsigned total) {
+    std::unique_lock<std::shared_mutex> life(impl_->life);
     {
         std::lock_guard<std::mutex> lk(impl_->mu);
         impl_->stop = true;
@@ -121,7 +131,12 @@ unsigned HostPool::threads() const { return (unsigned)impl_->workers.size() + 1;
 
 void HostPool::parallel_for(uint64_t pieces, const std::function<void(uint64_t)> &fn) {
     if (pieces == 0) return;
-    if (pieces == 1 || impl_->workers.empty() || (!t_caller_helps && pieces <= 2)) {
+    if (pieces == 1) {
+        fn(0);
+        return;
+    }
+    std::shared_lock<std::shared_mutex> life(impl_->life);
+    if (impl_->workers.empty() || (!t_caller_helps && pieces <= 2)) {
         for (uint64_t k = 0; k < pieces; ++k) fn(k);
         return;
     }
@@ -134,8 +149,11 @@ void HostPool::parallel_for(uint64_t pieces, const std::function<void(uint64_t)>
     }
     impl_->cv.notify_all();
     if (t_caller_helps) impl_->work(job);
-    std::unique_lock<std::mutex> lk(impl_->mu);
-    impl_->done_cv.wait(lk, [&] { return job->done.load(std::memory_order_acquire) == job->pieces; });
+    {
+        std::unique_lock<std::mutex> lk(impl_->mu);
+        impl_->done_cv.wait(lk, [&] { return job->done.load(std::memory_order_acquire) == job->pieces; });
+    }
+    if (job->failed.load(std::memory_order_acquire)) std::rethrow_exception(job->error);
 }
 
 void HostPool::copy(void *dst, const void *src, uint64_t bytes) {

@@ -666,10 +666,9 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         const uint64_t q = perm ? (uint64_t)__ldg(perm + t) : t;
         uint64_t begin, len;
         query_extent(qs, q, begin, len);
-        if ((qs.offsets32 || qs.offsets) && (begin > qs.limit || len > qs.limit - begin)) {  // decreasing / out-of-range offsets
-            report_error(err, kBadOffsetFlag | (q_index_base + (slot_map ? (uint64_t)__ldg(slot_map + q) : q)));
-            len = 0;  // (nothing of an empty query is read)
-        }
+        // decreasing / out-of-range offsets: nothing of the query is read, its result is the empty interval
+        const bool broken = (qs.offsets32 || qs.offsets) && (begin > qs.limit || len > qs.limit - begin);
+        if (broken) len = 0;
         const uint8_t *p = PACKED ? nullptr : qs.bytes + begin;
 
         // the last kQueryStage symbols of the query
@@ -747,7 +746,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             // reference mis-indexes its table here (lookup_table.rs:154-157) -- documented deviation.
             bool ok = true;
             const uint64_t li = lookup_index(pos, depth, ok);
-            bad = !ok;
+            bad = !ok || broken;
             if (!bad) lut_load(ix, ix.lut_level_off[depth] + li, s, e);
         }
 
@@ -841,7 +840,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         }
         const uint64_t slot_q = slot_map ? (uint64_t)__ldg(slot_map + q) : q;
         if (bad) {
-            report_error(err, q_index_base + slot_q);
+            report_error(err, (broken ? kBadOffsetFlag : 0ull) | (q_index_base + slot_q));
             s = e = 0;
             direct = false;
         }
