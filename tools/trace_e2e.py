@@ -1,4 +1,5 @@
-"""Per-chunk timeline of gdx_count_many / gdx_locate_many (GDX_TRACE=1) on a 30 M-query batch, pinned buffers."""
+"""Per-chunk timeline of gdx_count_many / gdx_locate_many (GDX_TRACE=1), pinned buffers.  TRACE_QUERIES (default
+30 M) queries; TRACE_LOCATE=0 skips the locate calls."""
 import os, sys, time
 os.environ["GDX_TRACE"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,7 +7,7 @@ import numpy as np, torch
 import bench
 import genedex_b200 as gdx
 args = bench.parse_args()
-nq = min(args.queries, 30_000_000)
+nq = min(args.queries, int(os.environ.get("TRACE_QUERIES", 30_000_000)))
 dev = torch.device("cuda", 0)
 text = bench.make_text_on_device(args.text_len, args.n_fraction, dev)
 qn = torch.empty(nq * args.query_len, dtype=torch.uint8).pin_memory().numpy()
@@ -18,6 +19,8 @@ for i in range(3):
     t0 = time.perf_counter()
     idx.count_many_packed(qn, None, args.query_len, nq, out=cn)
     print("call", i, "ms", (time.perf_counter() - t0) * 1e3, file=sys.stderr)
+if os.environ.get("TRACE_LOCATE", "1") == "0":
+    sys.exit(0)
 print("---- locate", file=sys.stderr)
 hit_off = np.zeros(nq + 1, dtype=np.uint64)
 for i in range(3):
