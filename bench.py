@@ -619,7 +619,9 @@ def run_ours(args, rank, world, local_rank):
     no_accel = None
     if extras:
         seed_depth0 = int(info.seed_table_depth)
+        row_ctx0 = int(info.row_context_entry_bytes) != 0
         pidx.set_text_verification(False)
+        pidx.set_row_context_table(False)
         pidx.set_dense_suffix_array(False)
         pidx.set_seed_table_depth(0)
         n3 = max(3, steps // 3)
@@ -644,6 +646,8 @@ def run_ours(args, rank, world, local_rank):
         pidx.set_dense_suffix_array(True)
         if seed_depth0:
             pidx.set_seed_table_depth(seed_depth0)
+        if row_ctx0:
+            pidx.set_row_context_table(True)
     del d_q
 
     # ---- every shard's results to rank 0 -----------------------------------------------------------------
@@ -780,15 +784,18 @@ def assemble(args, world, info, st, kernel_ms, step_ms, e2e, locate, no_accel, s
         "config": {"workload": workload_name(args, world), "queries_per_gpu": nq // world,
                    "index": ("replica = the configured index (s=%d, D=%d: rank records %.2f GB + samples %.2f GB) + packed text "
                              "%.2f GB + sampled inverse SA %.2f GB + accelerators derived per replica: dense suffix array %.2f GB, "
-                             "seed table depth %d %.2f GB" % (
+                             "seed table depth %d %.2f GB, row context table %.2f GB" % (
                                  args.sampling_rate, args.lookup_depth, int(info.rank_bytes) / 1e9, int(info.sample_bytes) / 1e9,
                                  int(info.text_bytes) / 1e9, int(info.inverse_sample_bytes) / 1e9,
-                                 int(info.dense_suffix_array_bytes) / 1e9, seed_depth, int(info.seed_table_bytes) / 1e9)),
-                   "l2": "inputs larger than L2: %.2f GB rank records + %.1f GB suffix array + %.1f GB seed table accessed at "
-                         "random, %.2f GB of queries per GPU" % (int(info.rank_bytes) / 1e9, int(info.dense_suffix_array_bytes) / 1e9,
-                                                                 int(info.seed_table_bytes) / 1e9, nq // world * m / 1e9),
+                                 int(info.dense_suffix_array_bytes) / 1e9, seed_depth, int(info.seed_table_bytes) / 1e9,
+                                 int(info.row_context_entry_bytes) * int(info.text_len) / 1e9)),
+                   "l2": "inputs larger than L2: %.2f GB rank records + %.1f GB suffix array + %.1f GB seed table + %.1f GB row "
+                         "context table accessed at random, %.2f GB of queries per GPU" % (
+                             int(info.rank_bytes) / 1e9, int(info.dense_suffix_array_bytes) / 1e9, int(info.seed_table_bytes) / 1e9,
+                             int(info.row_context_entry_bytes) * int(info.text_len) / 1e9, nq // world * m / 1e9),
                    "index_image_bytes": int(info.image_bytes), "dense_suffix_array_bytes": int(info.dense_suffix_array_bytes),
-                   "seed_table_depth": seed_depth, "seed_table_bytes": int(info.seed_table_bytes), "rank_record_bytes": R,
+                   "seed_table_depth": seed_depth, "seed_table_bytes": int(info.seed_table_bytes),
+                   "row_context_table_bytes": int(info.row_context_entry_bytes) * int(info.text_len), "rank_record_bytes": R,
                    "lf_steps_per_step": int(lf_steps), "verified_queries_per_step": int(verified),
                    "verify_walk_steps_per_step": int(walk),
                    "step_ms_min_median_max_rank0": [round(min(step_ms), 3), round(statistics.median(step_ms), 3), round(max(step_ms), 3)],

@@ -21,6 +21,7 @@ GDX_FLAG_NO_TEXT = 2
 GDX_FLAG_NO_INVERSE_SAMPLES = 4
 GDX_FLAG_NO_DENSE_SUFFIX_ARRAY = 8
 GDX_FLAG_NO_SEED_TABLE = 16
+GDX_FLAG_NO_ROW_CONTEXT_TABLE = 32
 GDX_QUERIES_IO_BYTES, GDX_QUERIES_PACKED_2BIT = 0, 1
 GDX_RANK_CONDENSED, GDX_RANK_FLAT = 0, 1
 GDX_NCCL_UNIQUE_ID_BYTES = 128
@@ -69,7 +70,7 @@ class gdx_index_info(C.Structure):
                 ("sample_bytes", C.c_uint64), ("lookup_bytes", C.c_uint64), ("num_samples", C.c_uint64),
                 ("num_text_borders", C.c_uint64), ("text_bytes", C.c_uint64),
                 ("inverse_sample_bytes", C.c_uint64), ("dense_suffix_array_bytes", C.c_uint64), ("seed_table_bytes", C.c_uint64),
-                ("seed_table_depth", C.c_uint32), ("reserved", C.c_uint32)]
+                ("seed_table_depth", C.c_uint32), ("row_context_entry_bytes", C.c_uint32)]
 
 
 class gdx_stats(C.Structure):
@@ -103,6 +104,7 @@ PROTOTYPES = {
     "gdx_index_set_dense_suffix_array": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_set_seed_table_depth": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_set_text_verification": (C.c_int, [_vp, C.c_int32]),
+    "gdx_index_set_row_context_table": (C.c_int, [_vp, C.c_int32]),
     "gdx_index_save_to_file": (C.c_int, [_vp, C.c_char_p, _vp, _u64]),
     "gdx_index_load_from_file": (C.c_int, [C.c_char_p, _i32, _P(_vp), _vp, _u64, _P(_u64)]),
     "gdx_index_header_bytes": (_u64, []),

@@ -315,6 +315,8 @@ struct gdx_index {
     uint64_t dense_sa_bytes = 0;
     void *seed_lut = nullptr;      // accelerator outside the image (gdx_index_set_seed_table_depth)
     uint64_t seed_lut_bytes = 0;
+    void *row_ctx = nullptr;       // accelerator outside the image (gdx_index_set_row_context_table)
+    uint64_t row_ctx_bytes = 0;
     bool verify = true;            // finish one-row intervals through the text section (gdx_index_set_text_verification)
     PackTable pack;                // io byte -> 2-bit code (host packer, host_pack.h)
     // host-buffer queries hold this shared for the whole call; (re)building or freeing an accelerator needs it
@@ -417,7 +419,8 @@ struct ImageSources {
 
 uint32_t accel_flags_from_config(uint32_t flags) {
     return ((flags & GDX_FLAG_NO_DENSE_SUFFIX_ARRAY) ? kAccelNoDenseSA : 0u) |
-           ((flags & GDX_FLAG_NO_SEED_TABLE) ? kAccelNoSeedTable : 0u);
+           ((flags & GDX_FLAG_NO_SEED_TABLE) ? kAccelNoSeedTable : 0u) |
+           ((flags & GDX_FLAG_NO_ROW_CONTEXT_TABLE) ? kAccelNoRowContext : 0u);
 }
 
 gdx_status validate_alphabet(const gdx_alphabet &a) {
@@ -591,6 +594,46 @@ void drop_dense_sa(gdx_index *idx) {
     idx->dense_sa_bytes = 0;
 }
 
+// ---- row context table accelerator (include/genedex_b200.h: gdx_index_set_row_context_table) ------------
+void drop_row_context(gdx_index *idx) {
+    if (!idx->row_ctx) return;
+    idx->dev.row_context = nullptr;
+    cudaFree(idx->row_ctx);
+    idx->row_ctx = nullptr;
+    idx->row_ctx_bytes = 0;
+}
+
+bool row_context_possible(const gdx_index *idx) {
+    const ImageHeader &h = idx->h;
+    return h.n > 0 && !h.wide && h.n < (1ull << 32) && h.ns >= 1 && h.ns <= 4 && h.text_bits != 0;
+}
+
+gdx_status build_row_context(gdx_index *idx) {
+    if (idx->row_ctx) return GDX_OK;
+    if (!row_context_possible(idx))
+        return fail(GDX_ERR_UNSUPPORTED, "the row context table needs the text section, at most 4 searchable symbols and a "
+                                         "text shorter than 2^32 symbols");
+    const uint64_t n = idx->h.n, bytes = n * 16;
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(GDX_ERR_OOM, "row context table: %llu bytes of device memory not available", (unsigned long long)bytes);
+    }
+    gdx_status st = dispatch_layout(idx->h.layout, [&](auto L) -> gdx_status {
+        k_build_row_context<decltype(L)><<<(unsigned)div_up(n, 256), 256>>>(idx->dev, reinterpret_cast<uint4 *>(d), n);
+        return GDX_OK;
+    });
+    cudaError_t e = st == GDX_OK ? cudaDeviceSynchronize() : cudaSuccess;
+    if (st != GDX_OK || e != cudaSuccess) {
+        cudaFree(d);
+        return st != GDX_OK ? st : fail(GDX_ERR_CUDA, "row context table: %s", cudaGetErrorString(e));
+    }
+    idx->row_ctx = d;
+    idx->row_ctx_bytes = bytes;
+    idx->dev.row_context = d;
+    return GDX_OK;
+}
+
 // ---- seed table accelerator (include/genedex_b200.h: gdx_index_set_seed_table_depth) -------------------
 void drop_seed_table(gdx_index *idx) {
     if (!idx->seed_lut) return;
@@ -665,7 +708,7 @@ gdx_status build_seed_table(gdx_index *idx, uint32_t depth) {
 // that is free right now.  GDX_DENSE_SA / GDX_SEED_TABLE override the policy for measurements.
 uint64_t accel_room(const gdx_index *idx) {
     if (idx->h.accel_budget) {
-        const uint64_t used = idx->dense_sa_bytes + idx->seed_lut_bytes;
+        const uint64_t used = idx->dense_sa_bytes + idx->seed_lut_bytes + idx->row_ctx_bytes;
         return idx->h.accel_budget > used ? idx->h.accel_budget - used : 0;
     }
     size_t free_b = 0, total_b = 0;
@@ -708,6 +751,20 @@ void auto_dense_sa(gdx_index *idx) {
         if (idx->h.n * (idx->h.wide ? 8ull : 4ull) > accel_room(idx)) return;
     }
     if (build_dense_sa(idx) != GDX_OK) t_error.clear();  // optional: not an error of the call
+}
+
+// built last (it is the largest: 16 B per text position) and only from what the other two left: the budget when
+// one is set, else up to half of the memory that is still free
+void auto_row_context(gdx_index *idx) {
+    if (!idx || !row_context_possible(idx)) return;
+    const char *e = getenv("GDX_ROW_CONTEXT");
+    if (e && atoi(e) == 0) return;
+    if (!(e && atoi(e) != 0)) {
+        if (idx->h.accel_flags & kAccelNoRowContext) return;
+        const uint64_t room = idx->h.accel_budget ? accel_room(idx) : 2 * accel_room(idx);
+        if (idx->h.n * 16 > room) return;
+    }
+    if (build_row_context(idx) != GDX_OK) t_error.clear();  // optional: not an error of the call
 }
 
 gdx_status build_image(const ImageSources &src, int device, gdx_index **out) {
@@ -999,6 +1056,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
             if (st == GDX_OK) {
                 auto_dense_sa(*out);
                 auto_seed_table(*out);
+                auto_row_context(*out);
             }
             return st;
         }
@@ -1023,6 +1081,7 @@ extern "C" gdx_status gdx_index_build(const uint8_t *texts, const uint64_t *text
         if (st == GDX_OK) {
             auto_dense_sa(*out);
             auto_seed_table(*out);
+            auto_row_context(*out);
         }
         return st;
     });
@@ -1092,6 +1151,7 @@ extern "C" gdx_status gdx_index_create_from_bwt(const uint8_t *bwt, const gdx_pa
         if (st == GDX_OK) {
             auto_dense_sa(*out);
             auto_seed_table(*out);
+            auto_row_context(*out);
         }
         return st;
     });
@@ -1136,6 +1196,7 @@ extern "C" gdx_status gdx_index_create_from_parts(const gdx_parts *parts, int32_
         if (st == GDX_OK) {
             auto_dense_sa(*out);
             auto_seed_table(*out);
+            auto_row_context(*out);
         }
         return st;
     });
@@ -1263,6 +1324,7 @@ extern "C" void gdx_index_destroy(gdx_index *idx) {
         if (p.p) cudaFreeHost(p.p);
     if (idx->dense_sa) cudaFree(idx->dense_sa);
     if (idx->seed_lut) cudaFree(idx->seed_lut);
+    if (idx->row_ctx) cudaFree(idx->row_ctx);
     if (idx->own_image && idx->image) cudaFree(idx->image);
     delete idx;
 }
@@ -1292,7 +1354,7 @@ extern "C" gdx_status gdx_index_get_info(const gdx_index *idx, gdx_index_info *o
     out->dense_suffix_array_bytes = idx->dense_sa_bytes;
     out->seed_table_bytes = idx->seed_lut_bytes;
     out->seed_table_depth = idx->dev.seed_depth;
-    out->reserved = 0;
+    out->row_context_entry_bytes = idx->row_ctx ? 16 : 0;
     return GDX_OK;
 }
 
@@ -1431,6 +1493,7 @@ extern "C" gdx_status gdx_index_adopt_image(const void *header, void *device_ima
             }
             auto_dense_sa(idx);
             auto_seed_table(idx);
+            auto_row_context(idx);
         }
         *out = idx;
         return GDX_OK;
@@ -1448,6 +1511,18 @@ extern "C" gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t dep
             return GDX_OK;
         }
         return build_seed_table(idx, (uint32_t)depth);
+    });
+}
+
+extern "C" gdx_status gdx_index_set_row_context_table(gdx_index *idx, int32_t on) {
+    return guarded([&]() -> gdx_status {
+        if (!idx) return fail(GDX_ERR_BAD_ARG, "NULL argument");
+        std::unique_lock<std::shared_mutex> cfg(idx->cfg_mu, std::try_to_lock);
+        if (!cfg.owns_lock()) return fail(GDX_ERR_BUSY, "queries are running on this index: the row context table cannot change now");
+        DeviceGuard guard(idx->device);
+        if (on) return build_row_context(idx);
+        drop_row_context(idx);
+        return GDX_OK;
     });
 }
 

@@ -26,7 +26,7 @@ namespace gdx {
 
 constexpr uint64_t kImageMagic = 0x3130305842584447ull;  // "GDXBX001"
 constexpr uint32_t kMaxLookupDepth = 24;
-constexpr uint32_t kAccelNoDenseSA = 1, kAccelNoSeedTable = 2;
+constexpr uint32_t kAccelNoDenseSA = 1, kAccelNoSeedTable = 2, kAccelNoRowContext = 4;
 
 struct ImageHeader {
     uint64_t magic;
@@ -39,7 +39,7 @@ struct ImageHeader {
     uint64_t n_records;
     uint64_t n_superblocks;
     uint32_t sigma, ns, storage, sampling_rate, lookup_depth;
-    uint32_t accel_flags;  // kAccelNoDenseSA | kAccelNoSeedTable: accelerator policy, travels with the image
+    uint32_t accel_flags;  // kAccelNoDenseSA | kAccelNoSeedTable | kAccelNoRowContext: accelerator policy, travels with the image
     RankLayout layout;
     uint64_t off_records, off_sbc, off_samples, off_lookup, off_border_rows, off_border_pos,
         off_sentinels, off_count, off_text;
@@ -66,6 +66,7 @@ struct DevIndex {
     const uint8_t *text;
     const void *isa;  // sampled inverse suffix array (same element width as samples) or nullptr
     const void *seed_lookup;  // level seed_depth of a lookup table deeper than the configured one, or nullptr
+    const void *row_context;  // 16-byte entries: SA[row] + 45 symbols of text context per row (kernels.cuh: ctx_matches), or nullptr
     uint64_t n, ntexts, n_border;
     uint32_t sigma, ns, sampling_rate, lookup_depth;
     uint32_t wide, noff, stride, derived_symbol;
@@ -112,6 +113,7 @@ inline DevIndex make_dev_index(const ImageHeader &h, const void *image) {
     d.isa_rate = h.sampling_rate;
     d.seed_lookup = nullptr;
     d.seed_depth = 0;
+    d.row_context = nullptr;
     d.verify_max_rows = 1;
     if ((h.sampling_rate & (h.sampling_rate - 1)) == 0) {
         uint32_t s = 0;

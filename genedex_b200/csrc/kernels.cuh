@@ -18,6 +18,7 @@
 //   k_ref_blocks_to_bwt  the reference's block arrays (condensed / flat, Block64 / Block512) -> dense BWT
 //   k_records_to_bwt device records -> dense BWT (export)
 //   k_densify       SA[row] for every row from the sampled suffix array (accelerator)
+//   k_build_row_context  SA[row] + 45 symbols of text context per row (accelerator)
 //   k_lut_extend    one level of the seed table (accelerator: a deeper lookup level outside the image)
 //   k_gather        random-gather ceiling microbenchmark     
 //
@@ -469,6 +470,65 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, QW &&query_
     return 0;
 }
 
+// ---- row context table (accelerator, gdx_index_set_row_context_table) ------------------------------------
+// One 16-byte entry per SA row: x = SA[row]; the 96 bits y | z << 32 | w << 64 hold, at bits [2i, 2i + 2), the
+// 2-bit code (dense - 1) of text[SA[row] - 45 + i] for i = 0..44, and in the top 6 bits of w the number vl
+// (0..45) of symbols directly in front of SA[row] that are searchable symbols (the run ends at a sentinel, a
+// symbol like `N`, or the start of the text; codes outside the run are 0 and must not be compared).  A one-row
+// interval with at most vl query symbols left is then verified from this one entry -- one random DRAM line
+// instead of the SA entry plus the text window behind it.  Alphabets with at most 4 searchable symbols, n < 2^32.
+constexpr uint32_t kCtxSymbols = 45;
+
+__device__ __forceinline__ uint32_t ctx_valid_len(const uint4 &en) { return en.w >> 26; }
+
+// query[0..pos) (codes at bits [2j, 2j + 2) of qh:ql) against the last pos (1..vl) symbols of the entry
+__device__ __forceinline__ bool ctx_matches(const uint4 &en, uint32_t pos, uint64_t ql, uint64_t qh) {
+    const uint64_t lo = (uint64_t)en.y | ((uint64_t)en.z << 32), hi = en.w & 0x3ffffffu;
+    const uint32_t sh = 2 * (kCtxSymbols - pos);  // the symbol that meets query[0] moves to bit 0
+    uint64_t rl, rh;
+    if (sh == 0) {
+        rl = lo;
+        rh = hi;
+    } else if (sh < 64) {
+        rl = (lo >> sh) | (hi << (64 - sh));
+        rh = hi >> sh;
+    } else {
+        rl = hi >> (sh - 64);
+        rh = 0;
+    }
+    const uint32_t nb = 2 * pos;
+    const uint64_t ml = nb >= 64 ? ~0ull : (1ull << nb) - 1, mh = nb > 64 ? (1ull << (nb - 64)) - 1 : 0ull;
+    return (((rl ^ ql) & ml) | ((rh ^ qh) & mh)) == 0;
+}
+
+// 2-bit codes of the first pos (<= 45) bytes of a query staged in shared memory; false if one of them is not a
+// searchable symbol (invalid byte, `N`, ...): such a query takes the symbol-exact text comparison instead
+__device__ __forceinline__ bool ctx_query_codes(const uint8_t *tab, const uint8_t *sbytes, uint32_t pos, uint32_t ns,
+                                                uint64_t &ql, uint64_t &qh) {
+    uint32_t q0 = 0, q1 = 0, q2 = 0, special = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) {
+        if (j < pos) {
+            const uint32_t t = (uint32_t)tab[sbytes[j]] - 1u;
+            special |= (uint32_t)(t >= ns);
+            q0 |= (t & 3u) << (2 * j);
+        }
+        if (j + 16 < pos) {
+            const uint32_t t = (uint32_t)tab[sbytes[j + 16]] - 1u;
+            special |= (uint32_t)(t >= ns);
+            q1 |= (t & 3u) << (2 * j);
+        }
+        if (j + 32 < pos && j + 32 < kCtxSymbols) {
+            const uint32_t t = (uint32_t)tab[sbytes[j + 32]] - 1u;
+            special |= (uint32_t)(t >= ns);
+            q2 |= (t & 3u) << (2 * j);
+        }
+    }
+    ql = (uint64_t)q0 | ((uint64_t)q1 << 32);
+    qh = q2;
+    return special == 0;
+}
+
 // query words of an IO-byte query whose last bytes are staged in shared memory (tab = io -> dense)
 template <int BITS>
 struct ByteQueryWords {
@@ -791,12 +851,35 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             if (VERIFY && e - s == 1 && pos >= ix.verify_min_remaining &&
                 (!CURSORS || len - pos >= ix.isa_rate)) {
                 // one candidate row: SA[s] is where query[pos..len) occurs; compare query[0..pos)
-                const uint64_t at = resolve_row<L>(ix, s, vsteps);
+                uint64_t at;
                 vrows = 1;
                 uint64_t jm = 0;     // query position of the first mismatch (from the right)
                 uint32_t cm = 0;     // its dense symbol
-                int cmp;
-                if constexpr (PACKED) {
+                int cmp = -1;
+                if (!CURSORS && ix.row_context) {
+                    // count / locate with the row context table: position and context in one 16-byte load
+                    uint4 en;
+                    {
+                        uint64_t e0, e1;
+                        ldg128_na(reinterpret_cast<const uint4 *>(ix.row_context) + s, e0, e1);
+                        en = make_uint4((uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32));
+                    }
+                    at = en.x;
+                    if (tail_begin == 0 && pos <= ctx_valid_len(en)) {
+                        if constexpr (PACKED) {
+                            cmp = ctx_matches(en, (uint32_t)pos, ptail.lo, ptail.hi) ? 0 : 1;
+                        } else {
+                            uint64_t ql, qh;
+                            if (ctx_query_codes(tab, sbytes, (uint32_t)pos, ix.ns, ql, qh))
+                                cmp = ctx_matches(en, (uint32_t)pos, ql, qh) ? 0 : 1;
+                        }
+                    }
+                } else {
+                    at = resolve_row<L>(ix, s, vsteps);
+                }
+                if (cmp >= 0) {
+                    // decided from the entry (a mismatch needs no position: the interval is empty either way)
+                } else if constexpr (PACKED) {
                     cmp = ix.text_bits == 4
                               ? compare_with_text<4, false>(ix, PackedQueryWords<4>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm)
                               : compare_with_text<8, false>(ix, PackedQueryWords<8>{ptail, qs.packed, begin, tail_begin}, pos, at, jm, cm);
@@ -1254,6 +1337,28 @@ k_densify(const __grid_constant__ DevIndex ix, void *__restrict__ out, uint64_t 
     const uint64_t v = resolve_row<L>(ix, i, steps);
     if (ix.wide) reinterpret_cast<uint64_t *>(out)[i] = v;
     else reinterpret_cast<uint32_t *>(out)[i] = (uint32_t)v;
+}
+
+// ---- row context table: SA[row] + the 45 text symbols in front of it (layout: see ctx_matches) ------------
+template <class L>
+__global__ void __launch_bounds__(256)
+k_build_row_context(const __grid_constant__ DevIndex ix, uint4 *__restrict__ out, uint64_t n) {
+    const uint64_t row = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    uint32_t steps = 0;
+    const uint64_t at = resolve_row<L>(ix, row, steps);
+    uint32_t w0 = 0, w1 = 0, w2 = 0, vl = 0;
+#pragma unroll 1
+    for (uint32_t k = 1; k <= kCtxSymbols && k <= at; ++k) {  // text position at - k <-> code index 45 - k
+        const uint32_t d = text_symbol(ix, at - k);
+        if (d == 0 || d > ix.ns) break;
+        const uint32_t i = kCtxSymbols - k, bits = (d - 1) << ((i & 15) * 2);
+        if (i < 16) w0 |= bits;
+        else if (i < 32) w1 |= bits;
+        else w2 |= bits;
+        vl = k;
+    }
+    out[row] = make_uint4((uint32_t)at, w0, w1, w2 | (vl << 26));
 }
 
 // ---- random-gather ceiling ----------------------------------------------------------------

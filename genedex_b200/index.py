@@ -136,6 +136,14 @@ class FmIndexConfig:
         self._flags = (self._flags & ~_lib.GDX_FLAG_NO_SEED_TABLE) | (0 if allow else _lib.GDX_FLAG_NO_SEED_TABLE)
         return self
 
+    def row_context_table(self, allow: bool = True) -> "FmIndexConfig":
+        """Allow (default) or forbid the row context table accelerator: SA[row] + the 45 text symbols in front of it in
+        one 16-byte entry per row (DNA-sized alphabets, texts shorter than 2^32), built last when it fits what the other
+        accelerators left (`FmIndex.set_row_context_table` forces it).  Results are identical."""
+        self._flags = (self._flags & ~_lib.GDX_FLAG_NO_ROW_CONTEXT_TABLE) | (
+            0 if allow else _lib.GDX_FLAG_NO_ROW_CONTEXT_TABLE)
+        return self
+
     def accelerator_budget(self, nbytes: int) -> "FmIndexConfig":
         """Device memory the accelerators of a replica (dense suffix array, seed table) may take together;
         0 = automatic (each at most a quarter of the free memory).  Travels with the index image."""
@@ -206,6 +214,10 @@ class FmIndex:
     def set_seed_table_depth(self, depth: int) -> None:
         """(Re)build the seed table accelerator at this depth now (raises if it does not fit); 0 frees it."""
         _check(self._lib.gdx_index_set_seed_table_depth(self._h, int(depth)))
+
+    def set_row_context_table(self, on: bool = True) -> None:
+        """Build now (raises if it does not fit / does not apply) or free the row context table accelerator."""
+        _check(self._lib.gdx_index_set_row_context_table(self._h, 1 if on else 0))
 
     def set_text_verification(self, on: bool = True) -> None:
         """Finish one-row intervals through the text (default) or run every LF step like the reference."""

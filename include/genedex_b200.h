@@ -91,6 +91,8 @@ typedef struct gdx_config {
 #define GDX_FLAG_NO_DENSE_SUFFIX_ARRAY 8u
 /* never build the seed table accelerator (see gdx_index_set_seed_table_depth) for this index */
 #define GDX_FLAG_NO_SEED_TABLE 16u
+/* never build the row context table accelerator (see gdx_index_set_row_context_table) for this index */
+#define GDX_FLAG_NO_ROW_CONTEXT_TABLE 32u
 
 /* src/lib.rs:331-335 Hit { text_id, position } */
 typedef struct gdx_hit {
@@ -158,7 +160,7 @@ typedef struct gdx_parts {
     /* ... the crate's own `suffix_array_data: Vec<u32>` (sampled_suffix_array.rs:18-23) as it is for the
      * 32-bit storage types: no widened copy needed.  Exactly one of the two sample pointers is set. */
     const uint32_t *sampled_suffix_array_u32;
-    uint32_t flags;                       /* GDX_FLAG_NO_DENSE_SUFFIX_ARRAY | GDX_FLAG_NO_SEED_TABLE */
+    uint32_t flags;                       /* GDX_FLAG_NO_DENSE_SUFFIX_ARRAY | GDX_FLAG_NO_SEED_TABLE | GDX_FLAG_NO_ROW_CONTEXT_TABLE */
     uint64_t accelerator_budget_bytes;    /* as gdx_config.accelerator_budget_bytes                */
     /* Which TextWithRankSupport `interleaved_blocks` comes from (the crate's four type aliases, lib.rs:104-113):
      *   GDX_RANK_CONDENSED: [position group][bit plane] Blocks, NUM_BITS positions per group (condensed.rs:24-47);
@@ -196,7 +198,7 @@ typedef struct gdx_index_info {
     uint64_t dense_suffix_array_bytes; /* device-only accelerator outside the image, 0 if absent */
     uint64_t seed_table_bytes;         /* device-only accelerator outside the image, 0 if absent */
     uint32_t seed_table_depth;         /* 0 if absent */
-    uint32_t reserved;
+    uint32_t row_context_entry_bytes;  /* row context table: bytes per text position (16), 0 if absent */
 } gdx_index_info;
 
 /* counters of the last search / locate call on this thread (feeds the roofline arithmetic) */
@@ -288,6 +290,20 @@ gdx_status gdx_index_set_dense_suffix_array(gdx_index *idx, int32_t on);
  * for measurements).  depth > configured depth (re)builds it at that depth now (GDX_ERR_OOM /
  * GDX_ERR_UNSUPPORTED if it does not fit), any smaller depth just frees it.  GDX_ERR_BUSY as above. */
 gdx_status gdx_index_set_seed_table_depth(gdx_index *idx, int32_t depth);
+
+/* Row context table accelerator (memory for speed; alphabets with at most 4 searchable symbols, texts shorter than
+ * 2^32 symbols, needs the text section).  One 16-byte entry per suffix array row: SA[row] and the 45 text symbols in
+ * front of that position as 2-bit codes (+ how many of them are searchable symbols of the same text).  The text
+ * verification of count / locate (below) then decides a one-row interval from ONE random 16-byte read instead of the
+ * suffix array entry plus the text window behind it -- two dependent DRAM lines less the one.  Queries longer than 64
+ * symbols, queries with more than 45 symbols left to compare, and contexts that run into `N` / a text border fall
+ * back to the symbol-by-symbol text comparison, so results and error behaviour are identical with and without it.
+ * Derived on the device from the suffix array and the text; not part of the image, of files or of what is replicated.
+ * Built automatically last, after the other two accelerators, when it fits what they left: GDX_FLAG_NO_ROW_CONTEXT_TABLE
+ * never; gdx_config.accelerator_budget_bytes when set, else at most half of the free device memory (GDX_ROW_CONTEXT =
+ * 0 / 1 overrides the policy for measurements).  on != 0 builds it now (GDX_ERR_OOM / GDX_ERR_UNSUPPORTED), on == 0
+ * frees it.  GDX_ERR_BUSY as above. */
+gdx_status gdx_index_set_row_context_table(gdx_index *idx, int32_t on);
 
 /* Text verification (needs the text section of the image, i.e. no GDX_FLAG_NO_TEXT): count / locate finish an
  * interval that has narrowed to one row by resolving SA[row] and comparing the rest of the query with the

@@ -202,6 +202,8 @@ public:
     void set_dense_suffix_array(bool on) { check(gdx_index_set_dense_suffix_array(h_->p, on ? 1 : 0)); }
     // (re)build the seed table accelerator at this depth, 0 frees it; not while queries are running
     void set_seed_table_depth(int depth) { check(gdx_index_set_seed_table_depth(h_->p, depth)); }
+    // build (true) or free (false) the row context table accelerator; not while queries are running
+    void set_row_context_table(bool on) { check(gdx_index_set_row_context_table(h_->p, on ? 1 : 0)); }
 
 private:
     std::shared_ptr<detail::Handle> h_;  // FmIndex: Clone (lib.rs:92) shares the device image
@@ -328,6 +330,8 @@ public:
     FmIndexConfig &dense_suffix_array(bool allow = true) { return flag(GDX_FLAG_NO_DENSE_SUFFIX_ARRAY, !allow); }
     // seed table accelerator (gdx_index_set_seed_table_depth): default = built when memory is ample
     FmIndexConfig &seed_table(bool allow = true) { return flag(GDX_FLAG_NO_SEED_TABLE, !allow); }
+    // row context table accelerator (gdx_index_set_row_context_table): default = built when memory is ample
+    FmIndexConfig &row_context_table(bool allow = true) { return flag(GDX_FLAG_NO_ROW_CONTEXT_TABLE, !allow); }
     FmIndexConfig &device(int ordinal) {
         cfg_.device = ordinal;
         return *this;
