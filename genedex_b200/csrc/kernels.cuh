@@ -501,32 +501,38 @@ __device__ __forceinline__ bool ctx_matches(const uint4 &en, uint32_t pos, uint6
     return (((rl ^ ql) & ml) | ((rh ^ qh) & mh)) == 0;
 }
 
-// 2-bit codes of the first pos (<= 45) bytes of a query staged in shared memory; false if one of them is not a
-// searchable symbol (invalid byte, `N`, ...): such a query takes the symbol-exact text comparison instead
-__device__ __forceinline__ bool ctx_query_codes(const uint8_t *tab, const uint8_t *sbytes, uint32_t pos, uint32_t ns,
-                                                uint64_t &ql, uint64_t &qh) {
-    uint32_t q0 = 0, q1 = 0, q2 = 0, special = 0;
+// IO-byte queries of an alphabet with at most 4 searchable symbols are turned into the 2-bit form of the packed
+// kernel right after staging, four bytes at a time: tab2[b] = dense - 1 for a searchable byte, 0x100 for every other
+// one.  slot = the thread's staged words, the query bytes start at byte `mis` of it; tail <= 64 symbols.
+// Returns false (t unspecified) if a staged byte is not a searchable symbol: such a query keeps the byte-wise path
+// with its lazy error behaviour.  ~5 instructions per symbol once, instead of a table walk per symbol per use.
+__device__ __forceinline__ bool codes_from_staged(const uint16_t *tab2, const uint32_t *slot, uint32_t mis, uint32_t tail,
+                                                  PackedTail &t) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, flags = 0;
+    const uint32_t sel = 0x3210u + 0x1111u * mis;  // bytes mis .. mis + 3 of two neighbouring words
+    uint32_t w0 = slot[0];
 #pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) {
-        if (j < pos) {
-            const uint32_t t = (uint32_t)tab[sbytes[j]] - 1u;
-            special |= (uint32_t)(t >= ns);
-            q0 |= (t & 3u) << (2 * j);
-        }
-        if (j + 16 < pos) {
-            const uint32_t t = (uint32_t)tab[sbytes[j + 16]] - 1u;
-            special |= (uint32_t)(t >= ns);
-            q1 |= (t & 3u) << (2 * j);
-        }
-        if (j + 32 < pos && j + 32 < kCtxSymbols) {
-            const uint32_t t = (uint32_t)tab[sbytes[j + 32]] - 1u;
-            special |= (uint32_t)(t >= ns);
-            q2 |= (t & 3u) << (2 * j);
+    for (uint32_t k = 0; k < 16; ++k) {
+        if (4 * k < tail) {
+            const uint32_t w1 = slot[k + 1];
+            const uint32_t w = __byte_perm(w0, w1, sel);
+            w0 = w1;
+            // codes of the four symbols in bits 0..7, their "not searchable" flags in bits 8, 10, 12, 14
+            uint32_t x = (uint32_t)tab2[w & 0xffu] + 4u * tab2[(w >> 8) & 0xffu] + 16u * tab2[(w >> 16) & 0xffu] +
+                         64u * tab2[w >> 24];
+            const uint32_t cnt = tail - 4 * k;  // symbols of this word that belong to the query
+            if (cnt < 4) x &= 0x0101u * ((1u << (2 * cnt)) - 1u);
+            flags |= x;
+            const uint32_t bits = (x & 0xffu) << (8 * (k & 3));
+            if (k < 4) c0 |= bits;
+            else if (k < 8) c1 |= bits;
+            else if (k < 12) c2 |= bits;
+            else c3 |= bits;
         }
     }
-    ql = (uint64_t)q0 | ((uint64_t)q1 << 32);
-    qh = q2;
-    return special == 0;
+    t.lo = (uint64_t)c0 | ((uint64_t)c1 << 32);
+    t.hi = (uint64_t)c2 | ((uint64_t)c3 << 32);
+    return (flags >> 8) == 0;
 }
 
 // query words of an IO-byte query whose last bytes are staged in shared memory (tab = io -> dense)
@@ -712,9 +718,14 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
     constexpr uint32_t kTabBytes = PACKED ? 4 : 256;
     constexpr uint32_t kStageWords = PACKED ? 1 : 256 * kQuerySlotWords;
     __shared__ uint8_t tab[kTabBytes];
+    __shared__ uint16_t tab2[PACKED ? 2 : 256];  // io byte -> 2-bit code | 0x100 (codes_from_staged), ns <= 4 only
     __shared__ uint32_t stage[kStageWords];
     if constexpr (!PACKED) {
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = ix.io_to_dense[i];
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+            const uint32_t d = ix.io_to_dense[i];
+            tab[i] = (uint8_t)d;
+            tab2[i] = (uint16_t)((d >= 1 && d <= ix.ns) ? d - 1 : 0x100u);
+        }
         __syncthreads();
     }
     const int mode = mode_flags & 7;
@@ -736,6 +747,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         const uint64_t tail_begin = len - tail;  // query position of the first staged symbol
         PackedTail ptail = {0, 0};
         const uint8_t *sbytes = nullptr;
+        bool coded = PACKED;  // the staged symbols are held as 2-bit codes in ptail
         if constexpr (PACKED) {
             if (tail) ptail = load_packed_tail(qs.packed, begin + tail_begin, tail);
         } else {
@@ -754,22 +766,26 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                 asm volatile("cp.async.wait_all;" ::: "memory");
             }
             sbytes = reinterpret_cast<const uint8_t *>(slot) + mis;
+            // (pays with the row context table, where the kernel is bound by instructions; without the table it is
+            // bound by DRAM round trips and this pass in front of the first dependent load costs 5 % -- 6.50 -> 6.83
+            // ms per 60 M queries -- but making it conditional on the table costs the common case registers)
+            if (ix.ns <= 4 && tail) coded = codes_from_staged(tab2, slot, mis, tail, ptail);
         }
         // dense symbol of query position i
         auto symbol_at = [&](uint64_t i) -> uint32_t {
             if constexpr (PACKED)
                 return 1u + (i >= tail_begin ? tail_code(ptail, (uint32_t)(i - tail_begin))
                                              : packed_code_global(qs.packed, begin + i));
+            else if (i >= tail_begin)
+                return coded ? 1u + tail_code(ptail, (uint32_t)(i - tail_begin)) : (uint32_t)tab[sbytes[i - tail_begin]];
             else
-                return tab[i >= tail_begin ? sbytes[i - tail_begin] : __ldg(p + i)];
+                return tab[__ldg(p + i)];
         };
         // lookup index of the d symbols starting at query position p0 (lookup_table.rs:68-161: the first
         // symbol is the least significant digit); ok = false if one of them is invalid or not searchable
         auto lookup_index = [&](uint64_t p0, uint32_t d, bool &ok) -> uint64_t {
-            if constexpr (PACKED) {
-                if (ix.ns == 4 && d <= 32 && p0 >= tail_begin)  // the digits are the packed bits themselves
-                    return d ? tail_bits(ptail, (uint32_t)(p0 - tail_begin), d) : 0ull;
-            }
+            if (coded && ix.ns == 4 && d <= 32 && p0 >= tail_begin)  // the digits are the packed bits themselves
+                return d ? tail_bits(ptail, (uint32_t)(p0 - tail_begin), d) : 0ull;
             uint64_t li = 0, f = 1;
             for (uint32_t j = 0; j < d; ++j) {
                 const uint32_t c = symbol_at(p0 + j);
@@ -865,15 +881,8 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                         en = make_uint4((uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32));
                     }
                     at = en.x;
-                    if (tail_begin == 0 && pos <= ctx_valid_len(en)) {
-                        if constexpr (PACKED) {
-                            cmp = ctx_matches(en, (uint32_t)pos, ptail.lo, ptail.hi) ? 0 : 1;
-                        } else {
-                            uint64_t ql, qh;
-                            if (ctx_query_codes(tab, sbytes, (uint32_t)pos, ix.ns, ql, qh))
-                                cmp = ctx_matches(en, (uint32_t)pos, ql, qh) ? 0 : 1;
-                        }
-                    }
+                    if (coded && tail_begin == 0 && pos <= ctx_valid_len(en))
+                        cmp = ctx_matches(en, (uint32_t)pos, ptail.lo, ptail.hi) ? 0 : 1;
                 } else {
                     at = resolve_row<L>(ix, s, vsteps);
                 }

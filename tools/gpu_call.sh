@@ -1,12 +1,10 @@
 #!/bin/bash
-# row context table: targeted tests first, then the parity suites (the table is built automatically for DNA indexes),
-# then the headline kernel with and without it
+# final evidence for the row-context kernel: whole GPU suite, full bench line, launch list
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/test_gpu_row_context.py -m gpu -q -x > gpurun_out/t_rowctx.log 2>&1; rc=$?; echo "rowctx rc=$rc"; tail -15 gpurun_out/t_rowctx.log
-if [ $rc -ne 0 ]; then exit 1; fi
-timeout 500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_packed.py -m gpu -q -x > gpurun_out/t_parity.log 2>&1; echo "parity rc=$?"; tail -3 gpurun_out/t_parity.log
-for rc_on in 1 0; do
-  GDX_ROW_CONTEXT=$rc_on timeout 400 python bench.py --steps 10 --warmup 3 --no-extras --no-cpu-baseline --no-locate > gpurun_out/bench_rowctx_$rc_on.json 2> gpurun_out/bench_rowctx_$rc_on.err; echo "bench ctx=$rc_on rc=$?"
-  python -c "
-import json; d=json.load(open('gpurun_out/bench_rowctx_$rc_on.json')); print(json.dumps({'ctx':$rc_on,'value':d['value'],'ms':d['ms_per_step'],'e2e':d['e2e']['value'],'frac':d['roofline']['frac'],'rowctx_bytes':d['config'].get('row_context_table_bytes'),'setup':d['config']['setup_s']}))"
-done
+timeout 1000 python -m pytest tests -m gpu -q -x > gpurun_out/t_all.log 2>&1; echo "all rc=$?"; tail -3 gpurun_out/t_all.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/r2_bench.json 2> gpurun_out/r2_bench.err; echo "bench rc=$?"; tail -2 gpurun_out/r2_bench.err | cut -c1-300
+python -c "
+import json; d=json.load(open('gpurun_out/r2_bench.json')); print(json.dumps({'value':d['value'],'ms':d['ms_per_step'],'e2e':d['e2e']['value'],'pageable':d['e2e']['pageable']['value'],'prepacked':d['e2e']['prepacked']['value'],'locate':d['locate']['value'],'compact':d['locate']['compact']['value'],'noacc':d['no_accelerators']['value'],'frac':d['roofline']['frac'],'traffic':d['roofline']['traffic'],'cpu':d['cpu_baseline']['value'],'parity':d.get('oracle_parity'),'cores':d['e2e']['host_cores_per_rank']}))"
+NCU="ncu --clock-control none --nvtx --nvtx-include timed/"
+timeout 600 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2> gpurun_out/r2_ncu1.err; echo "ncu launches rc=$?"
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
