@@ -769,7 +769,10 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
             // (pays with the row context table, where the kernel is bound by instructions; without the table it is
             // bound by DRAM round trips and this pass in front of the first dependent load costs 5 % -- 6.50 -> 6.83
             // ms per 60 M queries -- but making it conditional on the table costs the common case registers)
-            if (ix.ns <= 4 && tail) coded = codes_from_staged(tab2, slot, mis, tail, ptail);
+            // The kernels without text verification run every LF step and are bound by rank records: left as they were.
+            if constexpr (VERIFY) {
+                if (ix.ns <= 4 && tail) coded = codes_from_staged(tab2, slot, mis, tail, ptail);
+            }
         }
         // dense symbol of query position i
         auto symbol_at = [&](uint64_t i) -> uint32_t {
