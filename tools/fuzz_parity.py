@@ -59,10 +59,11 @@ def one_case(seed):
     keep_text = rng.random() < 0.8
     dense = rng.random() < 0.6
     seed_tab = rng.choice([None, None, False, 1, 2, 4, 7])
-    desc = f"seed={seed} alph={alph} texts={[len(t) for t in texts]} s={s} D={depth} {storage} dev={on_device} text={keep_text} dense={dense} seed={seed_tab}"
+    row_ctx = rng.random() < 0.7
+    desc = f"seed={seed} alph={alph} texts={[len(t) for t in texts]} s={s} D={depth} {storage} dev={on_device} text={keep_text} dense={dense} seed={seed_tab} rowctx={row_ctx}"
     oidx = O.OracleIndex.build(texts, oa, storage, sampling_rate=s, lookup_depth=depth)
     cfg = (gdx.FmIndexConfig(storage).suffix_array_sampling_rate(s).lookup_table_depth(depth)
-           .construct_on_device(on_device, verify=on_device).keep_text(keep_text).dense_suffix_array(dense).seed_table(seed_tab is not False))
+           .construct_on_device(on_device, verify=on_device).keep_text(keep_text).dense_suffix_array(dense).seed_table(seed_tab is not False).row_context_table(row_ctx))
     pidx = cfg.construct_index(texts, util.product_alphabet(gdx, alph))
     if seed_tab and oa.num_searchable ** seed_tab <= 1 << 22:
         pidx.set_seed_table_depth(seed_tab)
