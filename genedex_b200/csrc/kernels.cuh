@@ -40,6 +40,7 @@
 #include <cub/block/block_scan.cuh>
 
 #include "device_index.h"
+#include "row_context.h"
 
 #ifndef GDX_MULTIROW
 #define GDX_MULTIROW 0
@@ -90,9 +91,7 @@ __device__ __forceinline__ void query_extent(const DevQueries &qs, uint64_t q, u
 // ---- 2-bit packed queries ----------------------------------------------------------------------------
 // The last 64 symbols of a query live in two registers: symbol j (counted from the first staged symbol)
 // at bits [2j, 2j+2) of the 128-bit value hi:lo.
-struct PackedTail {
-    uint64_t lo, hi;
-};
+// (struct PackedTail: row_context.h)
 __device__ __forceinline__ uint32_t packed_code_global(const uint32_t *pk, uint64_t g) {
     return (__ldg(pk + (g >> 4)) >> ((uint32_t)(g & 15) * 2)) & 3u;
 }
@@ -470,70 +469,7 @@ __device__ __forceinline__ int compare_with_text(const DevIndex &ix, QW &&query_
     return 0;
 }
 
-// ---- row context table (accelerator, gdx_index_set_row_context_table) ------------------------------------
-// One 16-byte entry per SA row: x = SA[row]; the 96 bits y | z << 32 | w << 64 hold, at bits [2i, 2i + 2), the
-// 2-bit code (dense - 1) of text[SA[row] - 45 + i] for i = 0..44, and in the top 6 bits of w the number vl
-// (0..45) of symbols directly in front of SA[row] that are searchable symbols (the run ends at a sentinel, a
-// symbol like `N`, or the start of the text; codes outside the run are 0 and must not be compared).  A one-row
-// interval with at most vl query symbols left is then verified from this one entry -- one random DRAM line
-// instead of the SA entry plus the text window behind it.  Alphabets with at most 4 searchable symbols, n < 2^32.
-constexpr uint32_t kCtxSymbols = 45;
-
-__device__ __forceinline__ uint32_t ctx_valid_len(const uint4 &en) { return en.w >> 26; }
-
-// query[0..pos) (codes at bits [2j, 2j + 2) of qh:ql) against the last pos (1..vl) symbols of the entry
-__device__ __forceinline__ bool ctx_matches(const uint4 &en, uint32_t pos, uint64_t ql, uint64_t qh) {
-    const uint64_t lo = (uint64_t)en.y | ((uint64_t)en.z << 32), hi = en.w & 0x3ffffffu;
-    const uint32_t sh = 2 * (kCtxSymbols - pos);  // the symbol that meets query[0] moves to bit 0
-    uint64_t rl, rh;
-    if (sh == 0) {
-        rl = lo;
-        rh = hi;
-    } else if (sh < 64) {
-        rl = (lo >> sh) | (hi << (64 - sh));
-        rh = hi >> sh;
-    } else {
-        rl = hi >> (sh - 64);
-        rh = 0;
-    }
-    const uint32_t nb = 2 * pos;
-    const uint64_t ml = nb >= 64 ? ~0ull : (1ull << nb) - 1, mh = nb > 64 ? (1ull << (nb - 64)) - 1 : 0ull;
-    return (((rl ^ ql) & ml) | ((rh ^ qh) & mh)) == 0;
-}
-
-// IO-byte queries of an alphabet with at most 4 searchable symbols are turned into the 2-bit form of the packed
-// kernel right after staging, four bytes at a time: tab2[b] = dense - 1 for a searchable byte, 0x100 for every other
-// one.  slot = the thread's staged words, the query bytes start at byte `mis` of it; tail <= 64 symbols.
-// Returns false (t unspecified) if a staged byte is not a searchable symbol: such a query keeps the byte-wise path
-// with its lazy error behaviour.  ~5 instructions per symbol once, instead of a table walk per symbol per use.
-__device__ __forceinline__ bool codes_from_staged(const uint16_t *tab2, const uint32_t *slot, uint32_t mis, uint32_t tail,
-                                                  PackedTail &t) {
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, flags = 0;
-    const uint32_t sel = 0x3210u + 0x1111u * mis;  // bytes mis .. mis + 3 of two neighbouring words
-    uint32_t w0 = slot[0];
-#pragma unroll
-    for (uint32_t k = 0; k < 16; ++k) {
-        if (4 * k < tail) {
-            const uint32_t w1 = slot[k + 1];
-            const uint32_t w = __byte_perm(w0, w1, sel);
-            w0 = w1;
-            // codes of the four symbols in bits 0..7, their "not searchable" flags in bits 8, 10, 12, 14
-            uint32_t x = (uint32_t)tab2[w & 0xffu] + 4u * tab2[(w >> 8) & 0xffu] + 16u * tab2[(w >> 16) & 0xffu] +
-                         64u * tab2[w >> 24];
-            const uint32_t cnt = tail - 4 * k;  // symbols of this word that belong to the query
-            if (cnt < 4) x &= 0x0101u * ((1u << (2 * cnt)) - 1u);
-            flags |= x;
-            const uint32_t bits = (x & 0xffu) << (8 * (k & 3));
-            if (k < 4) c0 |= bits;
-            else if (k < 8) c1 |= bits;
-            else if (k < 12) c2 |= bits;
-            else c3 |= bits;
-        }
-    }
-    t.lo = (uint64_t)c0 | ((uint64_t)c1 << 32);
-    t.hi = (uint64_t)c2 | ((uint64_t)c3 << 32);
-    return (flags >> 8) == 0;
-}
+// ---- row context table (accelerator, gdx_index_set_row_context_table): layout and arithmetic in row_context.h ----
 
 // query words of an IO-byte query whose last bytes are staged in shared memory (tab = io -> dense)
 template <int BITS>
@@ -724,7 +660,7 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
             const uint32_t d = ix.io_to_dense[i];
             tab[i] = (uint8_t)d;
-            tab2[i] = (uint16_t)((d >= 1 && d <= ix.ns) ? d - 1 : 0x100u);
+            tab2[i] = ctx_tab2_entry(d, ix.ns);
         }
         __syncthreads();
     }
@@ -877,11 +813,11 @@ k_search(const __grid_constant__ DevIndex ix, const DevQueries qs, uint64_t *__r
                 int cmp = -1;
                 if (!CURSORS && ix.row_context) {
                     // count / locate with the row context table: position and context in one 16-byte load
-                    uint4 en;
+                    CtxEntry en;
                     {
                         uint64_t e0, e1;
                         ldg128_na(reinterpret_cast<const uint4 *>(ix.row_context) + s, e0, e1);
-                        en = make_uint4((uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32));
+                        en = CtxEntry{(uint32_t)e0, (uint32_t)(e0 >> 32), (uint32_t)e1, (uint32_t)(e1 >> 32)};
                     }
                     at = en.x;
                     if (coded && tail_begin == 0 && pos <= ctx_valid_len(en))
@@ -1359,18 +1295,8 @@ k_build_row_context(const __grid_constant__ DevIndex ix, uint4 *__restrict__ out
     if (row >= n) return;
     uint32_t steps = 0;
     const uint64_t at = resolve_row<L>(ix, row, steps);
-    uint32_t w0 = 0, w1 = 0, w2 = 0, vl = 0;
-#pragma unroll 1
-    for (uint32_t k = 1; k <= kCtxSymbols && k <= at; ++k) {  // text position at - k <-> code index 45 - k
-        const uint32_t d = text_symbol(ix, at - k);
-        if (d == 0 || d > ix.ns) break;
-        const uint32_t i = kCtxSymbols - k, bits = (d - 1) << ((i & 15) * 2);
-        if (i < 16) w0 |= bits;
-        else if (i < 32) w1 |= bits;
-        else w2 |= bits;
-        vl = k;
-    }
-    out[row] = make_uint4((uint32_t)at, w0, w1, w2 | (vl << 26));
+    const CtxEntry en = ctx_make_entry(at, ix.ns, [&](uint64_t p) { return text_symbol(ix, p); });
+    out[row] = make_uint4(en.x, en.y, en.z, en.w);
 }
 
 // ---- random-gather ceiling ----------------------------------------------------------------

@@ -149,3 +149,43 @@ extern "C" void emul_layout(const void *h, uint32_t out[6]) {
     out[0] = e->L.kind; out[1] = e->L.planes; out[2] = e->L.noff; out[3] = e->L.stride;
     out[4] = e->L.log2_pos; out[5] = e->L.derived_symbol;
 }
+
+// ---- row context table + 2-bit coded queries (genedex_b200/csrc/row_context.h) ------------------------------
+#include "../../genedex_b200/csrc/row_context.h"
+
+// entry for SA value `at` over a dense text (one byte per symbol); out = x, y, z, w
+extern "C" void emul_ctx_entry(const uint8_t *dense_text, uint64_t at, uint32_t ns, uint32_t *out) {
+    const CtxEntry en = ctx_make_entry(at, ns, [&](uint64_t p) { return (uint32_t)dense_text[p]; });
+    out[0] = en.x;
+    out[1] = en.y;
+    out[2] = en.z;
+    out[3] = en.w;
+}
+
+// the kernel's staging + coding of an IO-byte query: bytes are laid into a 17-word slot at byte offset `mis`
+// (garbage everywhere else), coded with codes_from_staged; returns 1 and the 128-bit tail if every byte is a
+// searchable symbol, else 0
+extern "C" int emul_code_query(const uint8_t *io_to_dense, uint32_t ns, const uint8_t *query, uint32_t tail, uint32_t mis,
+                               uint32_t garbage, uint64_t *lo, uint64_t *hi) {
+    uint16_t tab2[256];
+    for (int b = 0; b < 256; ++b) tab2[b] = ctx_tab2_entry(io_to_dense[b], ns);
+    uint32_t slot[17];
+    uint8_t *bytes = reinterpret_cast<uint8_t *>(slot);
+    for (uint32_t i = 0; i < sizeof slot; ++i) bytes[i] = (uint8_t)(garbage * 2654435761u >> (i % 24));
+    memcpy(bytes + mis, query, tail);
+    PackedTail t = {0, 0};
+    const bool ok = codes_from_staged(tab2, slot, mis, tail, t);
+    *lo = t.lo;
+    *hi = t.hi;
+    return ok ? 1 : 0;
+}
+
+extern "C" int emul_ctx_matches(const uint32_t *entry, uint32_t pos, uint64_t ql, uint64_t qh) {
+    const CtxEntry en = {entry[0], entry[1], entry[2], entry[3]};
+    return ctx_matches(en, pos, ql, qh) ? 1 : 0;
+}
+
+extern "C" uint32_t emul_ctx_valid_len(const uint32_t *entry) {
+    const CtxEntry en = {entry[0], entry[1], entry[2], entry[3]};
+    return ctx_valid_len(en);
+}

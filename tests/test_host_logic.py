@@ -421,3 +421,94 @@ def test_bad_arguments_return_codes_instead_of_crashing():
     # a corrupt image header is refused before anything is allocated from it (no device needed to find out)
     hdr = (C.c_uint8 * lib.gdx_index_header_bytes())()
     assert lib.gdx_index_adopt_image(hdr, C.c_void_p(16), -1, 0, C.byref(h)) == gdx._lib.GDX_ERR_BAD_ARG
+
+
+# ---- row context table + 2-bit coded byte queries, emulated on the host (row_context.h) ------------------
+def _ctx_lib(emul):
+    emul.emul_ctx_entry.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p]
+    emul.emul_code_query.restype = C.c_int
+    emul.emul_code_query.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    emul.emul_ctx_matches.restype = C.c_int
+    emul.emul_ctx_matches.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64]
+    emul.emul_ctx_valid_len.restype = C.c_uint32
+    emul.emul_ctx_valid_len.argtypes = [C.c_void_p]
+    return emul
+
+
+def test_row_context_entry_and_comparison_equal_a_plain_model(emul):
+    """The verification the kernel does from one 16-byte entry must say exactly what a symbol-by-symbol comparison of
+    query[0..pos) with the text in front of SA[row] says, whenever the entry claims to cover pos symbols."""
+    lib = _ctx_lib(emul)
+    rng = np.random.default_rng(12)
+    oa = O.ALPHABETS["ascii_dna_with_n"]()
+    io_to_dense = np.array(oa.io_to_dense, dtype=np.uint8)
+    ns = oa.num_searchable
+    # dense text: texts of many lengths separated by sentinels (0), N (5) sprinkled in runs
+    pieces = []
+    for m in (1, 2, 3, 44, 45, 46, 47, 90, 200, 1000):
+        t = rng.integers(1, 5, m, dtype=np.uint8)
+        if m >= 90:
+            for s in rng.integers(0, m - 3, 3):
+                t[s:s + int(rng.integers(1, 4))] = 5
+        pieces += [t, np.zeros(1, np.uint8)]
+    text = np.concatenate(pieces)
+    dense_to_io = {1: ord("A"), 2: ord("C"), 3: ord("G"), 4: ord("T"), 5: ord("N")}
+    entry = (C.c_uint32 * 4)()
+    lo, hi = C.c_uint64(), C.c_uint64()
+    checked = 0
+    for at in list(range(0, 120)) + rng.integers(0, text.size, 400).tolist():
+        lib.emul_ctx_entry(text.ctypes.data, at, ns, entry)
+        assert entry[0] == at
+        # model of vl: searchable symbols directly in front of `at`, capped at 45
+        vl = 0
+        while vl < 45 and at - vl - 1 >= 0 and 1 <= text[at - vl - 1] <= ns:
+            vl += 1
+        assert lib.emul_ctx_valid_len(entry) == vl, at
+        for pos in range(1, vl + 1):
+            want = text[at - pos:at]
+            for variant in range(3):
+                q = want.copy()
+                if variant == 1:
+                    j = int(rng.integers(0, pos))
+                    q[j] = (q[j] % 4) + 1          # a different searchable symbol at one place
+                elif variant == 2 and pos > 1:
+                    q[0] = (q[0] % 4) + 1          # the leftmost compared symbol (the last one the search reaches)
+                io = bytes(dense_to_io[int(c)] for c in q)
+                # the query may be longer than pos: the symbols right of pos were matched by the search already
+                extra = bytes(rng.choice(list(b"ACGT")) for _ in range(int(rng.integers(0, 64 - pos + 1))))
+                whole = np.frombuffer(io + extra, dtype=np.uint8)
+                mis = int(rng.integers(0, 4))
+                ok = lib.emul_code_query(io_to_dense.ctypes.data, ns, whole.ctypes.data, whole.size, mis,
+                                         int(rng.integers(0, 2 ** 31)), C.byref(lo), C.byref(hi))
+                assert ok == 1
+                got = lib.emul_ctx_matches(entry, pos, lo.value, hi.value)
+                assert got == int(np.array_equal(q, want)), (at, pos, variant)
+                checked += 1
+    assert checked > 20_000
+
+
+def test_coding_of_staged_byte_queries(emul):
+    """codes_from_staged: every length 1..64, every misalignment, garbage around the query in the slot; a byte that
+    is not a searchable symbol (N, lower-case n, an invalid byte) anywhere in the query makes it return false."""
+    lib = _ctx_lib(emul)
+    rng = np.random.default_rng(4)
+    oa = O.ALPHABETS["ascii_dna_with_n"]()
+    io_to_dense = np.array(oa.io_to_dense, dtype=np.uint8)
+    ns = oa.num_searchable
+    lo, hi = C.c_uint64(), C.c_uint64()
+    letters = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+    for tail in range(1, 65):
+        for mis in range(4):
+            q = letters[rng.integers(0, 8, tail)].copy()
+            ok = lib.emul_code_query(io_to_dense.ctypes.data, ns, q.ctypes.data, tail, mis, int(rng.integers(0, 2 ** 31)),
+                                     C.byref(lo), C.byref(hi))
+            assert ok == 1
+            value = lo.value | (hi.value << 64)
+            want = sum((int(io_to_dense[b]) - 1) << (2 * j) for j, b in enumerate(q.tolist()))
+            assert value == want, (tail, mis)          # also: nothing set above the last symbol
+            for bad in (ord("N"), ord("n"), ord("x"), 0, 255):
+                q2 = q.copy()
+                q2[int(rng.integers(0, tail))] = bad
+                assert lib.emul_code_query(io_to_dense.ctypes.data, ns, q2.ctypes.data, tail, mis, 7,
+                                           C.byref(lo), C.byref(hi)) == 0
