@@ -789,10 +789,13 @@ def assemble(args, world, info, st, kernel_ms, step_ms, e2e, locate, no_accel, s
                                  int(info.text_bytes) / 1e9, int(info.inverse_sample_bytes) / 1e9,
                                  int(info.dense_suffix_array_bytes) / 1e9, seed_depth, int(info.seed_table_bytes) / 1e9,
                                  int(info.row_context_entry_bytes) * int(info.text_len) / 1e9)),
-                   "l2": "inputs larger than L2: %.2f GB rank records + %.1f GB suffix array + %.1f GB seed table + %.1f GB row "
-                         "context table accessed at random, %.2f GB of queries per GPU" % (
-                             int(info.rank_bytes) / 1e9, int(info.dense_suffix_array_bytes) / 1e9, int(info.seed_table_bytes) / 1e9,
-                             int(info.row_context_entry_bytes) * int(info.text_len) / 1e9, nq // world * m / 1e9),
+                   "l2": "inputs larger than L2: %.2f GB rank records + %.1f GB seed table + %s accessed at random, %.2f GB of "
+                         "queries per GPU" % (
+                             int(info.rank_bytes) / 1e9, int(info.seed_table_bytes) / 1e9,
+                             ("%.1f GB row context table" % (int(info.row_context_entry_bytes) * int(info.text_len) / 1e9)
+                              if int(info.row_context_entry_bytes) else
+                              "%.1f GB suffix array + %.2f GB text" % (int(info.dense_suffix_array_bytes) / 1e9, int(info.text_bytes) / 1e9)),
+                             nq // world * m / 1e9),
                    "index_image_bytes": int(info.image_bytes), "dense_suffix_array_bytes": int(info.dense_suffix_array_bytes),
                    "seed_table_depth": seed_depth, "seed_table_bytes": int(info.seed_table_bytes),
                    "row_context_table_bytes": int(info.row_context_entry_bytes) * int(info.text_len), "rank_record_bytes": R,
