@@ -771,7 +771,9 @@ def assemble(args, world, info, st, kernel_ms, step_ms, e2e, locate, no_accel, s
     value = nq / (kernel_ms * 1e-3)
     traffic_file = "r2_k_search.txt"
     traffic = ncu_traffic_bytes(traffic_file)  # one launch over a 60 M-query shard (N = 1)
-    default_shape = (args.text_len == 3_100_000_000 and nq == 60_000_000 and m == 50 and args.lookup_depth == 0)
+    # (the committed capture is of the default workload with all three accelerators in place)
+    default_shape = (args.text_len == 3_100_000_000 and nq == 60_000_000 and m == 50 and args.lookup_depth == 0 and
+                     int(info.row_context_entry_bytes) != 0 and seed_depth == 16)
     if traffic and default_shape:
         traffic = traffic / world  # DRAM bytes per launch scale with the queries of the launch
     else:
