@@ -1,4 +1,5 @@
 #!/bin/bash
-# the library after moving the row context arithmetic into row_context.h: row context tests + packed tests + smoke
 mkdir -p gpurun_out
-timeout 90 python -m pytest tests/test_gpu_row_context.py tests/test_gpu_fuzz.py -m gpu -q -x > gpurun_out/t_refactor.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/t_refactor.log
+timeout 60 python bench.py --steps 5 --warmup 3 --no-extras --no-cpu-baseline --no-locate > gpurun_out/bench_last.json 2> gpurun_out/bench_last.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_last.err | cut -c1-200
+python -c "
+import json; d=json.load(open('gpurun_out/bench_last.json')); print(json.dumps({'value':d['value'],'ms':d['ms_per_step'],'l2':d['config']['l2'],'traffic':d['roofline']['traffic'],'frac':d['roofline']['frac']}))"
